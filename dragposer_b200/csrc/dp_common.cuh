@@ -1,0 +1,183 @@
+// dp_common.cuh -- shared definitions of the B200 DragPoser engine kernels.
+//
+// Model image: one contiguous, 16-byte aligned block in HBM that every CTA pulls into
+// shared memory with a single bulk-TMA copy (cp.async.bulk, UBLKCP in SASS) and keeps
+// resident for the whole frame.  Layout of the folded decoder (reference:
+// python/src/autoencoder.py:224-256 folded to 24->40->60->92, see dragposer_b200/model.py):
+//   W?t  forward operand,  [k][o]  (lanes own consecutive outputs -> conflict-free LDS.64)
+//   W?   backward operand, [o][k]  (same access pattern with the roles swapped)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DP_J 22
+#define DP_L 24
+#define DP_H0 40
+#define DP_H1 60
+#define DP_Y 92
+#define DP_PAST 60
+#define DP_NH 6
+#define DP_MAX_CHILD 4
+#define DP_JUMP_ROUNDS 4
+#define DP_SCRATCH 96  // floats per ping/pong activation buffer
+
+struct __align__(16) DpModelImage {
+  float W0t[DP_L * DP_H0];
+  float W1t[DP_H0 * DP_H1];
+  float W2t[DP_H1 * DP_Y];
+  float W0[DP_H0 * DP_L];
+  float W1[DP_H1 * DP_H0];
+  float W2[DP_Y * DP_H1];
+  float b0[DP_H0];
+  float b1[DP_H1];
+  float b2[DP_Y];
+  float mean_q[DP_J * 4];
+  float std_q[DP_J * 4];
+  float mean_d[4];
+  float std_d[4];
+  float off[32][4];                    // offset of joint j
+  float coff[DP_MAX_CHILD][32][4];     // offsets of the children of joint j
+  int32_t child[DP_MAX_CHILD][32];     // child joints of j or -1
+  int32_t jump[DP_JUMP_ROUNDS][32];    // ancestor of j at distance 1,2,4,8 or -1
+  int32_t parent[32];
+  int32_t last[32];                    // last joint of j's (preorder-contiguous) subtree
+  int32_t height_slot[32];             // slot in the heights vector or -1
+  int32_t pad[32];
+};
+static_assert(sizeof(DpModelImage) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
+
+struct DpFrameArgs {
+  const DpModelImage* model;
+  int n_clips;
+  // carried state (HBM)
+  float* latent;        // (B,24) latent after the last Adam step (seeds the next frame)
+  float* gpos;          // (B,3)
+  float* grot;          // (B,4) wxyz
+  float* latent_buf;    // (B,60,24) ring, slot = (head + chronological row) % 60
+  float* disp_buf;      // (B,60,3)
+  float* height_buf;    // (B,60,6)
+  int ring_head;        // slot holding the oldest row == slot written this frame
+  const float* target_buf;  // (B,target_rows,24) predicted target latents
+  int target_rows;
+  int target_index;
+  // per-frame inputs
+  const int32_t* n_ee;
+  const int32_t* joints;
+  const float* weights;
+  int shared_trackers;
+  const float* tgt_pos;
+  const float* tgt_rot;
+  int ee_stride;
+  // optimiser
+  double eps_pos, eps_rot, min_incr;
+  int max_iter;
+  float lambda_rot, lambda_t;
+  int adj_joint, adj_slot;
+  float adj_w;
+  const float* adam_tab;  // [2][max_iter]: lr/(1-b1^k), sqrt(1-b2^k), k = 1..max_iter
+  // outputs
+  float* out_pose;    // (B,88)
+  float* out_gpos;    // (B,3)
+  int32_t* out_iters; // (B)
+  float* out_losses;  // (B,3)
+  float* trace;       // (B,trace_iters,52) or null
+  int trace_iters;
+  // teacher-forced evaluation (dp_engine_eval_gradient)
+  int eval_only;
+  float* eval_grad;   // (B,24)
+  float* eval_pos;    // (B,22,3)
+};
+
+// ---------------------------------------------------------------- small math helpers
+__device__ __forceinline__ void quat_mul(const float a[4], const float b[4], float r[4]) {
+  r[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  r[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  r[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  r[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+
+// python/src/utils.py:34-76 (no normalisation, 1 - 2(yy+zz) form), row-major 3x3
+__device__ __forceinline__ void quat_to_mat(const float q[4], float m[9]) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float x2 = x + x, y2 = y + y, z2 = z + z;
+  const float xx = x * x2, yy = y * y2, wx = w * x2;
+  const float xy = x * y2, yz = y * z2, wy = w * y2;
+  const float xz = x * z2, zz = z * z2, wz = w * z2;
+  m[0] = 1.0f - (yy + zz); m[1] = xy - wz;          m[2] = xz + wy;
+  m[3] = xy + wz;          m[4] = 1.0f - (xx + zz); m[5] = yz - wx;
+  m[6] = xz - wy;          m[7] = yz + wx;          m[8] = 1.0f - (xx + yy);
+}
+
+// adjoint of quat_to_mat: G = dL/dM  ->  dL/dq   (Mbar2q)
+__device__ __forceinline__ void mat_bar_to_quat(const float q[4], const float G[9], float qb[4]) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  qb[0] = 2.0f * (-z * G[1] + y * G[2] + z * G[3] - x * G[5] - y * G[6] + x * G[7]);
+  qb[1] = 2.0f * (y * G[1] + z * G[2] + y * G[3] - 2.0f * x * G[4] - w * G[5] + z * G[6] + w * G[7] - 2.0f * x * G[8]);
+  qb[2] = 2.0f * (-2.0f * y * G[0] + x * G[1] + w * G[2] + x * G[3] + z * G[5] - w * G[6] + z * G[7] - 2.0f * y * G[8]);
+  qb[3] = 2.0f * (-2.0f * z * G[0] - w * G[1] + x * G[2] + w * G[3] - 2.0f * z * G[4] + y * G[5] + x * G[6] + y * G[7]);
+}
+
+__device__ __forceinline__ void mat_mul(const float a[9], const float b[9], float c[9]) {  // c = a b
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+__device__ __forceinline__ void mat_mul_bt(const float a[9], const float b[9], float c[9]) {  // c = a b^T
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[3 * j] + a[3 * i + 1] * b[3 * j + 1] + a[3 * i + 2] * b[3 * j + 2];
+}
+__device__ __forceinline__ void mat_mul_at(const float a[9], const float b[9], float c[9]) {  // c = a^T b
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
+}
+__device__ __forceinline__ void mat_vec(const float a[9], const float v[3], float r[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = a[3 * i] * v[0] + a[3 * i + 1] * v[1] + a[3 * i + 2] * v[2];
+}
+__device__ __forceinline__ void mat_t_vec(const float a[9], const float v[3], float r[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = a[i] * v[0] + a[3 + i] * v[1] + a[6 + i] * v[2];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------- mbarrier / bulk TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk tensor-memory-accelerator copy global -> shared, completion on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}

@@ -1,0 +1,547 @@
+// dp_engine.cu -- host side of the C ABI declared in include/dp_engine.h.
+//
+// Owns the HBM-resident per-clip state (laid out clip-major so one warp streams one
+// clip's rows with coalesced, vectorised accesses), the model images, pinned staging
+// buffers for the host-pointer entry points, and launches the persistent frame kernel
+// (and, when the reference would, the temporal predictor first).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/dp_engine.h"
+#include "dp_internal.h"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail(DP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct dp_engine {
+  int device = 0, max_clips = 0, n_clips = 0, num_sms = 148;
+  bool has_pose = false, has_temporal = false;
+  DpModelImage* d_model = nullptr;
+  float* d_tblob = nullptr;
+  float *d_mu = nullptr, *d_sigma = nullptr;
+  TpLayout tl;
+  // state
+  float *d_latent = nullptr, *d_gpos = nullptr, *d_grot = nullptr;
+  float *d_latent_buf = nullptr, *d_disp_buf = nullptr, *d_height_buf = nullptr;
+  float* d_target_buf = nullptr;  // (B, DP_MAX_WINDOW+1, 24) capacity; logical rows = window+1
+  int target_rows = 0;            // window + 1 of the current buffer, 0 = none yet
+  int ring_head = 0;
+  int current_index = 0;
+  // outputs / diagnostics
+  int32_t* d_iters = nullptr;
+  float* d_losses = nullptr;
+  float* d_trace = nullptr;
+  int trace_iters = 0, trace_enabled = 0;
+  float* d_adam = nullptr;
+  int adam_iters = 0;
+  float adam_lr = -1.0f;
+  TpWork tw{};
+  // staging for the host-pointer path
+  int stage_stride = 0;
+  int32_t *h_nee = nullptr, *d_nee = nullptr, *h_joints = nullptr, *d_joints = nullptr;
+  float *h_w = nullptr, *d_w = nullptr, *h_tp = nullptr, *d_tp = nullptr, *h_tr = nullptr, *d_tr = nullptr;
+  float *h_pose = nullptr, *d_pose = nullptr, *h_gp = nullptr, *d_gp = nullptr;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+};
+
+extern "C" const char* dp_engine_last_error(void) { return g_err.c_str(); }
+extern "C" int dp_engine_version(void) { return 100; }
+extern "C" size_t dp_engine_temporal_blob_floats(void) { return tp_layout().total; }
+extern "C" int dp_engine_n_clips(const dp_engine* e) { return e ? e->n_clips : 0; }
+extern "C" long long dp_engine_launch_count(const dp_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
+  if (!out || max_clips <= 0) return fail(DP_ERR_ARG, "dp_engine_create: bad arguments");
+  int count = 0;
+  CK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(DP_ERR_ARG, "dp_engine_create: no such CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DP_ERR_UNSUPPORTED, "dp_engine_create: needs an sm_100 (B200) device");
+  dp_engine* e = new dp_engine();
+  e->device = device;
+  e->max_clips = max_clips;
+  e->num_sms = prop.multiProcessorCount;
+  e->tl = tp_layout();
+  const size_t B = (size_t)max_clips;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&e->d_model, sizeof(DpModelImage)));
+  CK(cudaMalloc(&e->d_latent, B * DP_L * 4));
+  CK(cudaMalloc(&e->d_gpos, B * 3 * 4));
+  CK(cudaMalloc(&e->d_grot, B * 4 * 4));
+  CK(cudaMalloc(&e->d_latent_buf, B * DP_PAST * DP_L * 4));
+  CK(cudaMalloc(&e->d_disp_buf, B * DP_PAST * 3 * 4));
+  CK(cudaMalloc(&e->d_height_buf, B * DP_PAST * DP_NH * 4));
+  CK(cudaMalloc(&e->d_target_buf, B * (DP_MAX_WINDOW + 1) * DP_L * 4));
+  CK(cudaMemset(e->d_target_buf, 0, B * (DP_MAX_WINDOW + 1) * DP_L * 4));
+  CK(cudaMalloc(&e->d_iters, B * 4));
+  CK(cudaMalloc(&e->d_losses, B * 3 * 4));
+  CK(cudaMalloc(&e->d_mu, DP_L * 4));
+  CK(cudaMalloc(&e->d_sigma, DP_L * 4));
+  CK(cudaMalloc(&e->tw.enc, B * TP_S * TP_D * 4));
+  CK(cudaMalloc(&e->tw.enc2, B * TP_S * TP_D * 4));
+  CK(cudaMalloc(&e->tw.dec, B * TP_MAXT * TP_D * 4));
+  CK(cudaMalloc(&e->tw.dec2, B * TP_MAXT * TP_D * 4));
+  CK(cudaMalloc(&e->tw.dec_lat, B * TP_MAXT * TP_LAT * 4));
+  CK(cudaMalloc(&e->d_pose, B * DP_POSE * 4));
+  CK(cudaMalloc(&e->d_gp, B * 3 * 4));
+  CK(cudaMallocHost(&e->h_pose, B * DP_POSE * 4));
+  CK(cudaMallocHost(&e->h_gp, B * 3 * 4));
+  *out = e;
+  return DP_OK;
+}
+
+static void free_stage(dp_engine* e) {
+  cudaFreeHost(e->h_nee); cudaFreeHost(e->h_joints); cudaFreeHost(e->h_w); cudaFreeHost(e->h_tp); cudaFreeHost(e->h_tr);
+  cudaFree(e->d_nee); cudaFree(e->d_joints); cudaFree(e->d_w); cudaFree(e->d_tp); cudaFree(e->d_tr);
+  e->h_nee = e->h_joints = nullptr; e->d_nee = e->d_joints = nullptr;
+  e->h_w = e->h_tp = e->h_tr = e->d_w = e->d_tp = e->d_tr = nullptr;
+  e->stage_stride = 0;
+}
+
+extern "C" int dp_engine_destroy(dp_engine* e) {
+  if (!e) return DP_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_stage(e);
+  cudaFree(e->d_model); cudaFree(e->d_tblob); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
+  cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
+  cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam);
+  cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat);
+  cudaFree(e->d_pose); cudaFree(e->d_gp); cudaFreeHost(e->h_pose); cudaFreeHost(e->h_gp);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
+  if (!e || !m || !m->A0 || !m->A1 || !m->A2 || !m->parents || !m->offsets)
+    return fail(DP_ERR_ARG, "dp_engine_set_pose_model: null argument");
+  CK(cudaSetDevice(e->device));
+  std::vector<unsigned char> raw(sizeof(DpModelImage), 0);
+  DpModelImage& I = *reinterpret_cast<DpModelImage*>(raw.data());
+  const float* A[3] = {m->A0, m->A1, m->A2};
+  float* Wt[3] = {I.W0t, I.W1t, I.W2t};
+  float* Wr[3] = {I.W0, I.W1, I.W2};
+  const int dims[4] = {DP_L, DP_H0, DP_H1, DP_Y};
+  for (int l = 0; l < 3; ++l) {
+    const int K = dims[l], N = dims[l + 1];
+    for (int o = 0; o < N; ++o)
+      for (int k = 0; k < K; ++k) {
+        Wt[l][k * N + o] = A[l][o * K + k];
+        Wr[l][o * K + k] = A[l][o * K + k];
+      }
+  }
+  memcpy(I.b0, m->b0, sizeof(I.b0));
+  memcpy(I.b1, m->b1, sizeof(I.b1));
+  memcpy(I.b2, m->b2, sizeof(I.b2));
+  memcpy(I.mean_q, m->mean_q, sizeof(I.mean_q));
+  memcpy(I.std_q, m->std_q, sizeof(I.std_q));
+  for (int i = 0; i < 3; ++i) { I.mean_d[i] = m->mean_d[i]; I.std_d[i] = m->std_d[i]; }
+  // skeleton tables
+  const int32_t* par = m->parents;
+  if (par[0] != 0) return fail(DP_ERR_ARG, "skeleton: parents[0] must be 0");
+  int depth[DP_J] = {0}, nchild[DP_J] = {0}, last[DP_J];
+  for (int j = 1; j < DP_J; ++j) {
+    if (par[j] < 0 || par[j] >= j) return fail(DP_ERR_ARG, "skeleton: parents must be topologically ordered");
+    depth[j] = depth[par[j]] + 1;
+    if (depth[j] >= (1 << DP_JUMP_ROUNDS)) return fail(DP_ERR_UNSUPPORTED, "skeleton: chain deeper than 15");
+  }
+  for (int j = 0; j < DP_J; ++j) last[j] = j;
+  for (int j = DP_J - 1; j >= 1; --j) last[par[j]] = last[par[j]] > last[j] ? last[par[j]] : last[j];
+  for (int j = 1; j < DP_J; ++j)  // pre-order check: subtree(par) must be the contiguous range [par, last[par]]
+    if (j > last[par[j]]) return fail(DP_ERR_UNSUPPORTED, "skeleton: joints must be numbered in DFS pre-order");
+  {
+    std::vector<int> cnt(DP_J, 1);
+    for (int j = DP_J - 1; j >= 1; --j) cnt[par[j]] += cnt[j];
+    for (int j = 0; j < DP_J; ++j)
+      if (last[j] - j + 1 != cnt[j]) return fail(DP_ERR_UNSUPPORTED, "skeleton: joints must be numbered in DFS pre-order");
+  }
+  for (int k = 0; k < DP_MAX_CHILD; ++k)
+    for (int j = 0; j < 32; ++j) I.child[k][j] = -1;
+  for (int r = 0; r < DP_JUMP_ROUNDS; ++r)
+    for (int j = 0; j < 32; ++j) I.jump[r][j] = -1;
+  const int height_joints[DP_NH] = {0, 4, 8, 13, 17, 21};  // train_temporal.param["height_indices"]
+  for (int j = 0; j < 32; ++j) {
+    I.parent[j] = 0;
+    I.last[j] = j;
+    I.height_slot[j] = -1;
+  }
+  for (int s = 0; s < DP_NH; ++s) I.height_slot[height_joints[s]] = s;
+  for (int j = 0; j < DP_J; ++j) {
+    I.parent[j] = par[j];
+    I.last[j] = last[j];
+    for (int i = 0; i < 3; ++i) I.off[j][i] = (j == 0) ? 0.0f : m->offsets[3 * j + i];  // train.py:340
+    if (j > 0) {
+      const int p = par[j];
+      if (nchild[p] >= DP_MAX_CHILD) return fail(DP_ERR_UNSUPPORTED, "skeleton: more than 4 children on one joint");
+      I.child[nchild[p]][p] = j;
+      for (int i = 0; i < 3; ++i) I.coff[nchild[p]][p][i] = m->offsets[3 * j + i];
+      ++nchild[p];
+      int a = j;
+      for (int r = 0, dist = 1; r < DP_JUMP_ROUNDS; ++r, dist <<= 1) {
+        // ancestor at distance 2^r, if the chain is that long
+        if (depth[j] >= dist) {
+          a = j;
+          for (int s = 0; s < dist; ++s) a = par[a];
+          I.jump[r][j] = a;
+        }
+      }
+      (void)a;
+    }
+  }
+  CK(cudaMemcpy(e->d_model, raw.data(), raw.size(), cudaMemcpyHostToDevice));
+  e->has_pose = true;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, size_t n_floats, const float* means_latent,
+                                            const float* stds_latent) {
+  if (!e || !blob || !means_latent || !stds_latent) return fail(DP_ERR_ARG, "dp_engine_set_temporal_model: null argument");
+  if (n_floats != e->tl.total) return fail(DP_ERR_ARG, "dp_engine_set_temporal_model: blob size mismatch");
+  CK(cudaSetDevice(e->device));
+  if (!e->d_tblob) CK(cudaMalloc(&e->d_tblob, n_floats * 4));
+  CK(cudaMemcpy(e->d_tblob, blob, n_floats * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_mu, means_latent, DP_L * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_sigma, stds_latent, DP_L * 4, cudaMemcpyHostToDevice));
+  e->has_temporal = true;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_init_clips(dp_engine* e, int n, const float* latent0, const float* gpos, const float* grot,
+                                    const float* heights) {
+  if (!e || !latent0 || !gpos || !grot || !heights) return fail(DP_ERR_ARG, "dp_engine_init_clips: null argument");
+  if (n <= 0 || n > e->max_clips) return fail(DP_ERR_ARG, "dp_engine_init_clips: n_clips out of range");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  std::vector<float> lb((size_t)n * DP_PAST * DP_L), hb((size_t)n * DP_PAST * DP_NH);
+  for (int c = 0; c < n; ++c)
+    for (int r = 0; r < DP_PAST; ++r) {
+      memcpy(&lb[((size_t)c * DP_PAST + r) * DP_L], latent0 + (size_t)c * DP_L, DP_L * 4);
+      memcpy(&hb[((size_t)c * DP_PAST + r) * DP_NH], heights + (size_t)c * DP_NH, DP_NH * 4);
+    }
+  CK(cudaMemcpy(e->d_latent, latent0, (size_t)n * DP_L * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_gpos, gpos, (size_t)n * 3 * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_grot, grot, (size_t)n * 4 * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_latent_buf, lb.data(), lb.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_height_buf, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(e->d_disp_buf, 0, (size_t)n * DP_PAST * 3 * 4));
+  e->n_clips = n;
+  e->ring_head = 0;
+  e->current_index = 0;
+  e->target_rows = 0;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_global_pos(dp_engine* e, int first, int n, const float* gpos) {
+  if (!e || !gpos || first < 0 || n <= 0 || first + n > e->n_clips) return fail(DP_ERR_ARG, "dp_engine_set_global_pos: bad range");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(e->d_gpos + (size_t)first * 3, gpos, (size_t)n * 3 * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return DP_OK;
+}
+
+static int ensure_adam(dp_engine* e, int max_iter, float lr) {
+  if (e->d_adam && e->adam_iters == max_iter && e->adam_lr == lr) return DP_OK;
+  // torch/optim/adam.py:414-547: step_size = lr / (1 - beta1^k), sqrt(1 - beta2^k) -- Python doubles
+  std::vector<float> tab(2 * (size_t)max_iter);
+  const double lrd = (double)lr;
+  for (int k = 1; k <= max_iter; ++k) {
+    tab[k - 1] = (float)(lrd / (1.0 - std::pow(0.9, (double)k)));
+    tab[max_iter + k - 1] = (float)std::pow(1.0 - std::pow(0.999, (double)k), 0.5);
+  }
+  if (e->adam_iters != max_iter) {
+    cudaFree(e->d_adam);
+    e->d_adam = nullptr;
+    CK(cudaMalloc(&e->d_adam, tab.size() * 4));
+  }
+  // ordered after earlier frames on the engine stream
+  CK(cudaMemcpyAsync(e->d_adam, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->adam_iters = max_iter;
+  e->adam_lr = lr;
+  return DP_OK;
+}
+
+static int check_params(const dp_engine* e, const dp_run_params* p, int ee_stride) {
+  if (!e->has_pose) return fail(DP_ERR_STATE, "pose model not set");
+  if (e->n_clips <= 0) return fail(DP_ERR_STATE, "no clips initialised");
+  if (p->max_iter < 1 || p->max_iter > DP_MAX_ITER) return fail(DP_ERR_ARG, "max_iter out of range");
+  if (p->temporal_future_window < 0 || p->temporal_future_window > DP_MAX_WINDOW || p->temporal_future_window % 4)
+    return fail(DP_ERR_ARG, "temporal_future_window must be a multiple of 4 in [0,116]");  // drag_pose.py:236
+  if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
+  if (p->joint_adjust_joint >= DP_JOINTS || (p->joint_adjust_joint >= 0 && (p->joint_adjust_slot < 0 || p->joint_adjust_slot >= ee_stride)))
+    return fail(DP_ERR_ARG, "joint adjustment indices out of range");
+  if (p->decoder_path == 2) return fail(DP_ERR_UNSUPPORTED, "tcgen05 decoder path not built in this version");
+  return DP_OK;
+}
+
+static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, const int32_t* joints, const float* weights,
+                   int shared, const float* tgt_pos, const float* tgt_rot, int ee_stride, float* out_pose, float* out_gpos,
+                   cudaStream_t st) {
+  const int W = p->temporal_future_window;
+  if (e->target_rows != W + 1) {  // drag_pose.py:237-244: fresh zero buffer when the window changes
+    CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (W + 1) * DP_L * 4, st));
+    e->target_rows = W + 1;
+  }
+  if (e->current_index == 0) {
+    if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
+    CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
+                       e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, st, &e->launches));
+  }
+  if (e->trace_enabled && (!e->d_trace || e->trace_iters < p->max_iter)) {
+    cudaFree(e->d_trace);
+    e->d_trace = nullptr;
+    CK(cudaMalloc(&e->d_trace, (size_t)e->max_clips * p->max_iter * 52 * 4));
+    e->trace_iters = p->max_iter;
+  }
+  if (e->trace_enabled) CK(cudaMemsetAsync(e->d_trace, 0, (size_t)e->max_clips * e->trace_iters * 52 * 4, st));
+  DpFrameArgs a{};
+  a.model = e->d_model;
+  a.n_clips = e->n_clips;
+  a.latent = e->d_latent; a.gpos = e->d_gpos; a.grot = e->d_grot;
+  a.latent_buf = e->d_latent_buf; a.disp_buf = e->d_disp_buf; a.height_buf = e->d_height_buf;
+  a.ring_head = e->ring_head;
+  a.target_buf = e->d_target_buf; a.target_rows = W + 1; a.target_index = e->current_index;
+  a.n_ee = n_ee; a.joints = joints; a.weights = weights; a.shared_trackers = shared;
+  a.tgt_pos = tgt_pos; a.tgt_rot = tgt_rot; a.ee_stride = ee_stride;
+  a.eps_pos = p->stop_eps_pos; a.eps_rot = p->stop_eps_rot; a.min_incr = p->min_loss_incr;
+  a.max_iter = p->max_iter;
+  a.lambda_rot = p->lambda_rot; a.lambda_t = p->lambda_temporal;
+  a.adj_joint = p->joint_adjust_joint; a.adj_slot = p->joint_adjust_slot; a.adj_w = p->joint_adjust_weight;
+  a.adam_tab = e->d_adam;
+  a.out_pose = out_pose; a.out_gpos = out_gpos; a.out_iters = e->d_iters; a.out_losses = e->d_losses;
+  a.trace = e->trace_enabled ? e->d_trace : nullptr;
+  a.trace_iters = e->trace_iters;
+  CK(dp_frame_simt_launch(a, e->num_sms, st));
+  ++e->launches;
+  e->ring_head = (e->ring_head + 1) % DP_PAST;
+  e->current_index = (W == 0) ? 0 : (e->current_index + 1) % W;  // drag_pose.py:399-402
+  return DP_OK;
+}
+
+extern "C" int dp_engine_run_frames_device(dp_engine* e, const dp_run_params* p, int n_frames, const int32_t* n_ee,
+                                           const int32_t* joints, const float* weights, int shared, const float* tgt_pos,
+                                           const float* tgt_rot, int ee_stride, float* out_pose, float* out_gpos, void* stream) {
+  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || !out_gpos || n_frames < 1)
+    return fail(DP_ERR_ARG, "dp_engine_run_frames_device: null argument");
+  int rc = check_params(e, p, ee_stride);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  rc = ensure_adam(e, p->max_iter, p->learning_rate);
+  if (rc) return rc;
+  const size_t B = (size_t)e->n_clips, S = (size_t)ee_stride;
+  for (int f = 0; f < n_frames; ++f) {
+    rc = run_one(e, p, n_ee ? n_ee + f * B : nullptr, shared ? joints : joints + f * B * S,
+                 shared ? weights : weights + f * B * S * 2, shared, tgt_pos + f * B * S * 3, tgt_rot + f * B * S * 9,
+                 ee_stride, out_pose + f * B * DP_POSE, out_gpos + f * B * 3, st);
+    if (rc) return rc;
+  }
+  return DP_OK;
+}
+
+extern "C" int dp_engine_run_frame_device(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, const int32_t* joints,
+                                          const float* weights, int shared, const float* tgt_pos, const float* tgt_rot,
+                                          int ee_stride, float* out_pose, float* out_gpos, void* stream) {
+  return dp_engine_run_frames_device(e, p, 1, n_ee, joints, weights, shared, tgt_pos, tgt_rot, ee_stride, out_pose,
+                                     out_gpos, stream);
+}
+
+static int ensure_stage(dp_engine* e, int ee_stride) {
+  if (e->stage_stride >= ee_stride) return DP_OK;
+  free_stage(e);
+  const size_t B = (size_t)e->max_clips, S = (size_t)ee_stride;
+  CK(cudaMallocHost(&e->h_nee, B * 4)); CK(cudaMalloc(&e->d_nee, B * 4));
+  CK(cudaMallocHost(&e->h_joints, B * S * 4)); CK(cudaMalloc(&e->d_joints, B * S * 4));
+  CK(cudaMallocHost(&e->h_w, B * S * 2 * 4)); CK(cudaMalloc(&e->d_w, B * S * 2 * 4));
+  CK(cudaMallocHost(&e->h_tp, B * S * 3 * 4)); CK(cudaMalloc(&e->d_tp, B * S * 3 * 4));
+  CK(cudaMallocHost(&e->h_tr, B * S * 9 * 4)); CK(cudaMalloc(&e->d_tr, B * S * 9 * 4));
+  e->stage_stride = ee_stride;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, const int32_t* joints,
+                                        const float* weights, int shared, const float* tgt_pos, const float* tgt_rot,
+                                        int ee_stride, float* out_pose, float* out_gpos) {
+  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || !out_gpos)
+    return fail(DP_ERR_ARG, "dp_engine_run_frame_host: null argument");
+  int rc = check_params(e, p, ee_stride);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  rc = ensure_stage(e, ee_stride);
+  if (rc) return rc;
+  rc = ensure_adam(e, p->max_iter, p->learning_rate);
+  if (rc) return rc;
+  cudaStream_t st = e->stream;
+  const size_t B = (size_t)e->n_clips, S = (size_t)ee_stride;
+  const size_t nj = shared ? S : B * S;
+  if (n_ee) { memcpy(e->h_nee, n_ee, B * 4); CK(cudaMemcpyAsync(e->d_nee, e->h_nee, B * 4, cudaMemcpyHostToDevice, st)); }
+  memcpy(e->h_joints, joints, nj * 4);
+  memcpy(e->h_w, weights, nj * 2 * 4);
+  memcpy(e->h_tp, tgt_pos, B * S * 3 * 4);
+  memcpy(e->h_tr, tgt_rot, B * S * 9 * 4);
+  CK(cudaMemcpyAsync(e->d_joints, e->h_joints, nj * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_w, e->h_w, nj * 2 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_tp, e->h_tp, B * S * 3 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_tr, e->h_tr, B * S * 9 * 4, cudaMemcpyHostToDevice, st));
+  rc = run_one(e, p, n_ee ? e->d_nee : nullptr, e->d_joints, e->d_w, shared, e->d_tp, e->d_tr, ee_stride, e->d_pose, e->d_gp, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->h_pose, e->d_pose, B * DP_POSE * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(e->h_gp, e->d_gp, B * 3 * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(out_pose, e->h_pose, B * DP_POSE * 4);
+  memcpy(out_gpos, e->h_gp, B * 3 * 4);
+  return DP_OK;
+}
+
+extern "C" int dp_engine_get_frame_stats(dp_engine* e, int32_t* iters, float* losses) {
+  if (!e) return fail(DP_ERR_ARG, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaDeviceSynchronize());
+  if (iters) CK(cudaMemcpy(iters, e->d_iters, (size_t)e->n_clips * 4, cudaMemcpyDeviceToHost));
+  if (losses) CK(cudaMemcpy(losses, e->d_losses, (size_t)e->n_clips * 3 * 4, cudaMemcpyDeviceToHost));
+  return DP_OK;
+}
+
+extern "C" int dp_engine_enable_trace(dp_engine* e, int enable) {
+  if (!e) return fail(DP_ERR_ARG, "null engine");
+  e->trace_enabled = enable ? 1 : 0;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_get_trace(dp_engine* e, float* rows, int max_iter) {
+  if (!e || !rows) return fail(DP_ERR_ARG, "null argument");
+  if (!e->d_trace || max_iter > e->trace_iters) return fail(DP_ERR_STATE, "no trace recorded for that many iterations");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy2D(rows, (size_t)max_iter * 52 * 4, e->d_trace, (size_t)e->trace_iters * 52 * 4, (size_t)max_iter * 52 * 4,
+                  e->n_clips, cudaMemcpyDeviceToHost));
+  return DP_OK;
+}
+
+extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents, const float* grot, const float* tgt_latent,
+                                       const int32_t* n_ee, const int32_t* joints, const float* weights, int shared,
+                                       const float* tgt_pos, const float* tgt_rot, int ee_stride, float lambda_rot,
+                                       float lambda_temporal, int decoder_path, float* grad, float* losses, float* positions) {
+  if (!e || !latents || !grot || !tgt_latent || !joints || !weights || !tgt_pos || !tgt_rot || n < 1)
+    return fail(DP_ERR_ARG, "dp_engine_eval_gradient: null argument");
+  if (!e->has_pose) return fail(DP_ERR_STATE, "pose model not set");
+  if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
+  if (decoder_path == 2) return fail(DP_ERR_UNSUPPORTED, "tcgen05 decoder path not built in this version");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  const size_t N = (size_t)n, S = (size_t)ee_stride, nj = shared ? S : N * S;
+  float *d_lat, *d_g, *d_t, *d_w, *d_tp, *d_tr, *d_grad, *d_loss, *d_pos, *d_adam;
+  int32_t *d_ne = nullptr, *d_j;
+  CK(cudaMalloc(&d_lat, N * DP_L * 4)); CK(cudaMalloc(&d_g, N * 16)); CK(cudaMalloc(&d_t, N * DP_L * 4));
+  CK(cudaMalloc(&d_j, nj * 4)); CK(cudaMalloc(&d_w, nj * 8)); CK(cudaMalloc(&d_tp, N * S * 12)); CK(cudaMalloc(&d_tr, N * S * 36));
+  CK(cudaMalloc(&d_grad, N * DP_L * 4)); CK(cudaMalloc(&d_loss, N * 12)); CK(cudaMalloc(&d_pos, N * DP_J * 12));
+  CK(cudaMalloc(&d_adam, 8));
+  if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaMemcpyHostToDevice)); }
+  CK(cudaMemcpy(d_lat, latents, N * DP_L * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_g, grot, N * 16, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_t, tgt_latent, N * DP_L * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_j, joints, nj * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_w, weights, nj * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_tp, tgt_pos, N * S * 12, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_tr, tgt_rot, N * S * 36, cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_adam, 0, 8));
+  DpFrameArgs a{};
+  a.model = e->d_model; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
+  a.target_buf = d_t; a.target_rows = 1; a.target_index = 0;
+  a.n_ee = d_ne; a.joints = d_j; a.weights = d_w; a.shared_trackers = shared; a.tgt_pos = d_tp; a.tgt_rot = d_tr;
+  a.ee_stride = ee_stride;
+  a.eps_pos = -1.0; a.eps_rot = -1.0; a.min_incr = -std::numeric_limits<double>::infinity();
+  a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
+  a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
+  CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
+  ++e->launches;
+  CK(cudaStreamSynchronize(e->stream));
+  if (grad) CK(cudaMemcpy(grad, d_grad, N * DP_L * 4, cudaMemcpyDeviceToHost));
+  if (losses) CK(cudaMemcpy(losses, d_loss, N * 12, cudaMemcpyDeviceToHost));
+  if (positions) CK(cudaMemcpy(positions, d_pos, N * DP_J * 12, cudaMemcpyDeviceToHost));
+  cudaFree(d_lat); cudaFree(d_g); cudaFree(d_t); cudaFree(d_j); cudaFree(d_w); cudaFree(d_tp); cudaFree(d_tr);
+  cudaFree(d_grad); cudaFree(d_loss); cudaFree(d_pos); cudaFree(d_adam); cudaFree(d_ne);
+  return DP_OK;
+}
+
+static int copy_ring(dp_engine* e, const float* d_src, float* h_dst, int width) {
+  // device ring (slot order) -> host chronological order
+  const size_t B = (size_t)e->n_clips;
+  std::vector<float> tmp(B * DP_PAST * width);
+  CK(cudaMemcpy(tmp.data(), d_src, tmp.size() * 4, cudaMemcpyDeviceToHost));
+  for (size_t c = 0; c < B; ++c)
+    for (int r = 0; r < DP_PAST; ++r)
+      memcpy(h_dst + (c * DP_PAST + r) * width, &tmp[(c * DP_PAST + (e->ring_head + r) % DP_PAST) * width], (size_t)width * 4);
+  return DP_OK;
+}
+
+extern "C" int dp_engine_get_state(dp_engine* e, float* latent, float* gpos, float* grot, float* latent_buf, float* disp_buf,
+                                   float* height_buf, float* target_buf, int* current_index) {
+  if (!e) return fail(DP_ERR_ARG, "null engine");
+  if (e->n_clips <= 0) return fail(DP_ERR_STATE, "no clips initialised");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  const size_t B = (size_t)e->n_clips;
+  if (latent) CK(cudaMemcpy(latent, e->d_latent, B * DP_L * 4, cudaMemcpyDeviceToHost));
+  if (gpos) CK(cudaMemcpy(gpos, e->d_gpos, B * 12, cudaMemcpyDeviceToHost));
+  if (grot) CK(cudaMemcpy(grot, e->d_grot, B * 16, cudaMemcpyDeviceToHost));
+  int rc;
+  if (latent_buf && (rc = copy_ring(e, e->d_latent_buf, latent_buf, DP_L))) return rc;
+  if (disp_buf && (rc = copy_ring(e, e->d_disp_buf, disp_buf, 3))) return rc;
+  if (height_buf && (rc = copy_ring(e, e->d_height_buf, height_buf, DP_NH))) return rc;
+  if (target_buf) {
+    if (e->target_rows <= 0) return fail(DP_ERR_STATE, "no target buffer yet");
+    CK(cudaMemcpy(target_buf, e->d_target_buf, B * e->target_rows * DP_L * 4, cudaMemcpyDeviceToHost));
+  }
+  if (current_index) *current_index = e->current_index;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const float* disp_buf, const float* height_buf) {
+  if (!e || !latent_buf || !disp_buf || !height_buf) return fail(DP_ERR_ARG, "null argument");
+  if (e->n_clips <= 0) return fail(DP_ERR_STATE, "no clips initialised");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  const size_t B = (size_t)e->n_clips;
+  CK(cudaMemcpy(e->d_latent_buf, latent_buf, B * DP_PAST * DP_L * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_disp_buf, disp_buf, B * DP_PAST * 3 * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->d_height_buf, height_buf, B * DP_PAST * DP_NH * 4, cudaMemcpyHostToDevice));
+  e->ring_head = 0;  // rows were given in chronological order
+  return DP_OK;
+}
+
+extern "C" int dp_engine_predict_targets(dp_engine* e, int window, void* stream) {
+  if (!e) return fail(DP_ERR_ARG, "null engine");
+  if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
+  if (e->n_clips <= 0) return fail(DP_ERR_STATE, "no clips initialised");
+  if (window < 0 || window > DP_MAX_WINDOW || window % 4) return fail(DP_ERR_ARG, "window must be a multiple of 4 in [0,116]");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (e->target_rows != window + 1) {
+    CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (window + 1) * DP_L * 4, st));
+    e->target_rows = window + 1;
+  }
+  CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf, e->ring_head,
+                     e->n_clips, window, e->d_target_buf, e->tw, st, &e->launches));
+  return DP_OK;
+}

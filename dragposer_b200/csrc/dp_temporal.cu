@@ -1,0 +1,316 @@
+// dp_temporal.cu -- temporal predictor (target-latent warm start) on the GPU, fp32.
+//
+// Restates drag_pose.py:246-290 + temporal_transformer.py:53-78 for B clips at once:
+//   encoder tokens  = 14 x [ standardised latent(24) | sum of 4 displacements(3) | heights(6) ]
+//   decoder tokens  = standardised latent of ring row 56, then the predictions so far
+//   for i = 0,4,..,W: full decoder pass (NO causal mask), last token -> prediction@i
+// The encoder memory is computed once per call (the reference recomputes the identical
+// value on every autoregressive step).  The step-function "lerp" of drag_pose.py:282-289
+// is applied while writing target_buf: prediction@i lands in rows i-4..i-1 (and row W).
+#include "dp_common.cuh"
+#include "dp_temporal.cuh"
+#include "dp_internal.h"
+
+namespace {
+
+__device__ __forceinline__ void layer_norm_row(float v0, float v1, bool has1, const float* __restrict__ w,
+                                               const float* __restrict__ b, int lane, float& o0, float& o1) {
+  // one warp normalises one 48-wide row: lane holds features lane and lane+32 (<48)
+  const float s = warp_sum(v0 + (has1 ? v1 : 0.0f));
+  const float mean = s * (1.0f / TP_D);
+  const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.0f;
+  const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / TP_D);
+  const float rstd = rsqrtf(var + 1e-5f);
+  o0 = d0 * rstd * w[lane] + b[lane];
+  o1 = has1 ? d1 * rstd * w[lane + 32] + b[lane + 32] : 0.0f;
+}
+
+// ---- encoder token embedding + first decoder token
+__global__ void tp_embed_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ mu,
+                                const float* __restrict__ sigma, const float* __restrict__ latent_buf,
+                                const float* __restrict__ disp_buf, const float* __restrict__ height_buf, int head,
+                                float* __restrict__ enc, float* __restrict__ dec_lat) {
+  __shared__ float x[TP_S][TP_ENC_IN + 3];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int idx = tid; idx < TP_S * TP_ENC_IN; idx += blockDim.x) {
+    const int k = idx / TP_ENC_IN, i = idx % TP_ENC_IN;
+    const int slot = (head + 4 * k) % DP_PAST;
+    float v;
+    if (i < TP_LAT) {
+      v = (latent_buf[((size_t)b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
+    } else if (i < TP_LAT + 3) {
+      v = 0.0f;
+      for (int r = 0; r < 4; ++r) v += disp_buf[((size_t)b * DP_PAST + (head + 4 * k + r) % DP_PAST) * 3 + (i - TP_LAT)];
+    } else {
+      v = height_buf[((size_t)b * DP_PAST + slot) * DP_NH + (i - TP_LAT - 3)];
+    }
+    x[k][i] = v;
+  }
+  if (tid < TP_LAT) {
+    const int slot = (head + 56) % DP_PAST;
+    dec_lat[((size_t)b * TP_MAXT) * TP_LAT + tid] = (latent_buf[((size_t)b * DP_PAST + slot) * DP_L + tid] - mu[tid]) / sigma[tid];
+  }
+  __syncthreads();
+  const float* W = blob + L.enc_in_w;
+  for (int idx = tid; idx < TP_S * TP_D; idx += blockDim.x) {
+    const int k = idx / TP_D, f = idx % TP_D;
+    float a = blob[L.enc_in_b + f];
+    for (int i = 0; i < TP_ENC_IN; ++i) a = fmaf(x[k][i], W[i * TP_D + f], a);
+    enc[((size_t)b * TP_S + k) * TP_D + f] = a + blob[L.pe + k * TP_D + f];
+  }
+}
+
+__global__ void tp_dec_embed_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ dec_lat, int T,
+                                    float* __restrict__ dec) {
+  __shared__ float x[TP_MAXT][TP_LAT];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int idx = tid; idx < T * TP_LAT; idx += blockDim.x) x[idx / TP_LAT][idx % TP_LAT] = dec_lat[(size_t)b * TP_MAXT * TP_LAT + idx];
+  __syncthreads();
+  const float* W = blob + L.dec_in_w;
+  for (int idx = tid; idx < T * TP_D; idx += blockDim.x) {
+    const int t = idx / TP_D, f = idx % TP_D;
+    float a = blob[L.dec_in_b + f];
+    for (int i = 0; i < TP_LAT; ++i) a = fmaf(x[t][i], W[i * TP_D + f], a);
+    dec[((size_t)b * TP_MAXT + t) * TP_D + f] = a + blob[L.pe + t * TP_D + f];
+  }
+}
+
+// ---- out = LayerNorm(xq + MHA(xq, xkv, xkv)); one CTA per clip
+__global__ void __launch_bounds__(128) tp_mha_ln_kernel(const float* __restrict__ blob, TpAttn A, TpNorm N,
+                                                        const float* __restrict__ xq_g, int T, int q_stride,
+                                                        const float* __restrict__ xkv_g, int S, int kv_stride,
+                                                        float* __restrict__ out_g) {
+  __shared__ float xq[TP_MAXT][TP_D], xkv[TP_MAXT][TP_D];
+  __shared__ float q[TP_MAXT][TP_D], k[TP_MAXT][TP_D + 1], v[TP_MAXT][TP_D], o[TP_MAXT][TP_D];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < T * TP_D; idx += 128) xq[idx / TP_D][idx % TP_D] = xq_g[(size_t)b * q_stride * TP_D + idx];
+  for (int idx = tid; idx < S * TP_D; idx += 128) xkv[idx / TP_D][idx % TP_D] = xkv_g[(size_t)b * kv_stride * TP_D + idx];
+  __syncthreads();
+  const float* Win = blob + A.w_in;
+  const float* bin = blob + A.b_in;
+  const float scale = rsqrtf((float)TP_HD);
+  for (int idx = tid; idx < T * TP_D; idx += 128) {
+    const int t = idx / TP_D, f = idx % TP_D;
+    float a = bin[f];
+#pragma unroll 8
+    for (int i = 0; i < TP_D; ++i) a = fmaf(xq[t][i], Win[i * 3 * TP_D + f], a);
+    q[t][f] = a * scale;
+  }
+  for (int idx = tid; idx < S * TP_D; idx += 128) {
+    const int s = idx / TP_D, f = idx % TP_D;
+    float ak = bin[TP_D + f], av = bin[2 * TP_D + f];
+#pragma unroll 8
+    for (int i = 0; i < TP_D; ++i) {
+      const float xv = xkv[s][i];
+      ak = fmaf(xv, Win[i * 3 * TP_D + TP_D + f], ak);
+      av = fmaf(xv, Win[i * 3 * TP_D + 2 * TP_D + f], av);
+    }
+    k[s][f] = ak;
+    v[s][f] = av;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < T * TP_H; idx += 128) {
+    const int t = idx / TP_H, h = idx % TP_H;
+    float sc[TP_MAXT];
+    float mx = -3.0e38f;
+    for (int s = 0; s < S; ++s) {
+      float a = 0.0f;
+#pragma unroll
+      for (int d = 0; d < TP_HD; ++d) a = fmaf(q[t][h * TP_HD + d], k[s][h * TP_HD + d], a);
+      sc[s] = a;
+      mx = fmaxf(mx, a);
+    }
+    float den = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      sc[s] = expf(sc[s] - mx);
+      den += sc[s];
+    }
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int d = 0; d < TP_HD; ++d) {
+      float a = 0.0f;
+      for (int s = 0; s < S; ++s) a = fmaf(sc[s], v[s][h * TP_HD + d], a);
+      o[t][h * TP_HD + d] = a * inv;
+    }
+  }
+  __syncthreads();
+  const float* Wo = blob + A.w_out;
+  const float* bo = blob + A.b_out;
+  for (int t = warp; t < T; t += 4) {
+    const bool has1 = lane + 32 < TP_D;
+    float a0 = bo[lane], a1 = has1 ? bo[lane + 32] : 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < TP_D; ++i) {
+      const float ov = o[t][i];
+      a0 = fmaf(ov, Wo[i * TP_D + lane], a0);
+      if (has1) a1 = fmaf(ov, Wo[i * TP_D + lane + 32], a1);
+    }
+    a0 += xq[t][lane];
+    if (has1) a1 += xq[t][lane + 32];
+    float r0, r1;
+    layer_norm_row(a0, a1, has1, blob + N.w, blob + N.b, lane, r0, r1);
+    float* dst = out_g + ((size_t)b * q_stride + t) * TP_D;
+    dst[lane] = r0;
+    if (has1) dst[lane + 32] = r1;
+  }
+}
+
+// ---- out = LN(x + W2 relu(W1 x + b1) + b2) [then an optional second LayerNorm]; 64 tokens per CTA.
+// Rows are addressed as (clip, token): row r -> clip r / T, token r % T, stride `row_stride` tokens per clip.
+#define FF_TM 64
+#define FF_HC 64
+__global__ void __launch_bounds__(256) tp_ff_ln_kernel(const float* __restrict__ blob, TpFF F, TpNorm N, TpNorm N2, int has_n2,
+                                                       const float* __restrict__ x_g, int n_rows, int T, int row_stride,
+                                                       float* __restrict__ out_g) {
+  extern __shared__ __align__(16) unsigned char ff_smem[];
+  float (*w1s)[FF_HC] = reinterpret_cast<float (*)[FF_HC]>(ff_smem);
+  float (*w2s)[TP_D] = reinterpret_cast<float (*)[TP_D]>(ff_smem + sizeof(float) * TP_D * FF_HC);
+  float (*xs)[TP_D + 1] = reinterpret_cast<float (*)[TP_D + 1]>(ff_smem + sizeof(float) * 2 * TP_D * FF_HC);
+  float (*hs)[FF_HC + 1] = reinterpret_cast<float (*)[FF_HC + 1]>(ff_smem + sizeof(float) * (2 * TP_D * FF_HC + FF_TM * (TP_D + 1)));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * FF_TM;
+  for (int idx = tid; idx < FF_TM * TP_D; idx += 256) {
+    const int r = idx / TP_D, f = idx % TP_D, row = row0 + r;
+    float v = 0.0f;
+    if (row < n_rows) v = x_g[((size_t)(row / T) * row_stride + row % T) * TP_D + f];
+    xs[r][f] = v;
+  }
+  const int ty = tid >> 4, tx = tid & 15;       // phase A: 4 tokens x 4 hidden per thread
+  const bool outer = tx < 12;                   // phase B: 4 tokens x 4 features, 12 x 16 threads
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const float* W1 = blob + F.w1;
+  const float* W2 = blob + F.w2;
+  for (int hc = 0; hc < TP_FF; hc += FF_HC) {
+    __syncthreads();
+    for (int idx = tid; idx < TP_D * FF_HC / 4; idx += 256) {
+      const int kx = idx / (FF_HC / 4), c4 = idx % (FF_HC / 4);
+      reinterpret_cast<float4*>(&w1s[kx][0])[c4] = *reinterpret_cast<const float4*>(W1 + (size_t)kx * TP_FF + hc + 4 * c4);
+    }
+    for (int idx = tid; idx < FF_HC * TP_D / 4; idx += 256)
+      reinterpret_cast<float4*>(&w2s[0][0])[idx] = *reinterpret_cast<const float4*>(W2 + (size_t)hc * TP_D + 4 * idx);
+    __syncthreads();
+    float h[4][4];
+    {
+      const float4 bb = *reinterpret_cast<const float4*>(blob + F.b1 + hc + 4 * tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { h[i][0] = bb.x; h[i][1] = bb.y; h[i][2] = bb.z; h[i][3] = bb.w; }
+    }
+#pragma unroll 4
+    for (int kx = 0; kx < TP_D; ++kx) {
+      const float4 w = *reinterpret_cast<const float4*>(&w1s[kx][4 * tx]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xv = xs[4 * ty + i][kx];
+        h[i][0] = fmaf(xv, w.x, h[i][0]); h[i][1] = fmaf(xv, w.y, h[i][1]);
+        h[i][2] = fmaf(xv, w.z, h[i][2]); h[i][3] = fmaf(xv, w.w, h[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hs[4 * ty + i][4 * tx + j] = fmaxf(h[i][j], 0.0f);
+    __syncthreads();
+    if (outer) {
+#pragma unroll 4
+      for (int hx = 0; hx < FF_HC; ++hx) {
+        const float4 w = *reinterpret_cast<const float4*>(&w2s[hx][4 * tx]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float hv = hs[4 * ty + i][hx];
+          acc[i][0] = fmaf(hv, w.x, acc[i][0]); acc[i][1] = fmaf(hv, w.y, acc[i][1]);
+          acc[i][2] = fmaf(hv, w.z, acc[i][2]); acc[i][3] = fmaf(hv, w.w, acc[i][3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (outer) {
+    const float4 bb = *reinterpret_cast<const float4*>(blob + F.b2 + 4 * tx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* d = &hs[4 * ty + i][4 * tx];  // reuse hs as the residual-sum tile
+      d[0] = acc[i][0] + bb.x + xs[4 * ty + i][4 * tx];
+      d[1] = acc[i][1] + bb.y + xs[4 * ty + i][4 * tx + 1];
+      d[2] = acc[i][2] + bb.z + xs[4 * ty + i][4 * tx + 2];
+      d[3] = acc[i][3] + bb.w + xs[4 * ty + i][4 * tx + 3];
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < FF_TM; r += 8) {
+    const int row = row0 + r;
+    if (row >= n_rows) continue;
+    const bool has1 = lane + 32 < TP_D;
+    float r0, r1;
+    layer_norm_row(hs[r][lane], has1 ? hs[r][lane + 32] : 0.0f, has1, blob + N.w, blob + N.b, lane, r0, r1);
+    if (has_n2) layer_norm_row(r0, r1, has1, blob + N2.w, blob + N2.b, lane, r0, r1);
+    float* dst = out_g + ((size_t)(row / T) * row_stride + row % T) * TP_D;
+    dst[lane] = r0;
+    if (has1) dst[lane + 32] = r1;
+  }
+}
+
+// ---- prediction head on the last decoder token; appends to the decoder inputs and
+// writes the de-standardised prediction into target_buf with the step-function upsampling.
+__global__ void tp_out_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ mu,
+                              const float* __restrict__ sigma, const float* __restrict__ dec, int T, int step_i, int window,
+                              float* __restrict__ dec_lat, float* __restrict__ target_buf) {
+  const int b = blockIdx.x, f = threadIdx.x;
+  if (f >= TP_LAT) return;
+  const float* x = dec + ((size_t)b * TP_MAXT + (T - 1)) * TP_D;
+  float a = blob[L.out_b + f];
+  for (int i = 0; i < TP_D; ++i) a = fmaf(x[i], blob[L.out_w + i * TP_LAT + f], a);
+  if (T < TP_MAXT) dec_lat[((size_t)b * TP_MAXT + T) * TP_LAT + f] = a;
+  const float val = a * sigma[f] + mu[f];
+  float* tb = target_buf + (size_t)b * (window + 1) * TP_LAT;
+  if (window == 0) {
+    tb[f] = val;
+  } else if (step_i >= 4) {
+    for (int r = step_i - 4; r < step_i; ++r) tb[r * TP_LAT + f] = val;
+    if (step_i == window) tb[window * TP_LAT + f] = val;
+  }
+}
+
+}  // namespace
+
+static const size_t kFfSmem = sizeof(float) * (2 * TP_D * FF_HC + FF_TM * (TP_D + 1) + FF_TM * (FF_HC + 1));
+
+cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
+                            const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
+                            int window, float* target_buf, const TpWork& w, cudaStream_t st, long long* launches) {
+  cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
+  if (err != cudaSuccess) return err;
+  tp_embed_kernel<<<B, 128, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
+  ++*launches;
+  float* e = w.enc;
+  float* e2 = w.enc2;
+  const int enc_rows = B * TP_S;
+  for (int l = 0; l < TP_NENC; ++l) {
+    tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2);
+    tp_ff_ln_kernel<<<(enc_rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm,
+                                                                    l == TP_NENC - 1, e2, enc_rows, TP_S, TP_S, e);
+    *launches += 2;
+  }
+  int T = 1;
+  for (int i = 0; i <= window; i += 4, ++T) {
+    tp_dec_embed_kernel<<<B, 128, 0, st>>>(blob, L, w.dec_lat, T, w.dec);
+    ++*launches;
+    float* d = w.dec;
+    float* d2 = w.dec2;
+    const int rows = B * T;
+    for (int l = 0; l < TP_NDEC; ++l) {
+      tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2);
+      tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d);
+      tp_ff_ln_kernel<<<(rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
+                                                                  l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2);
+      float* t = d; d = d2; d2 = t;
+      *launches += 3;
+    }
+    tp_out_kernel<<<B, 32, 0, st>>>(blob, L, mu, sigma, d, T, i, window, w.dec_lat, target_buf);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}

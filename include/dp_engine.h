@@ -1,0 +1,164 @@
+/*
+ * dp_engine.h -- C ABI of the B200-native DragPoser optimisation engine.
+ *
+ * One engine owns the HBM-resident state of B independent clips (latent, root
+ * pose, the three 60-row ring buffers, the predicted target latents) and runs
+ * the reference's per-frame optimisation for all of them in one launch.
+ * Plain pointers and sizes only; no torch / C++ types.  Every entry point returns
+ * 0 on success or a negative dp_status; dp_engine_last_error() gives the text.
+ *
+ * Reference interface each entry point replaces (paths under /root/reference):
+ *   dp_engine_set_pose_model      python/src/train.py:257-269 (load_model) +
+ *                                 python/src/drag_pose.py:13-34 (DragPose.__init__)
+ *   dp_engine_set_temporal_model  python/src/train_temporal.py:474-482
+ *   dp_engine_init_clips          python/src/drag_pose.py:47-64 (set_initial_pose)
+ *   dp_engine_set_global_pos      python/src/run_drag.py:120-124
+ *   dp_engine_run_frame_*         python/src/drag_pose.py:196-414 (DragPose.run)
+ *   dp_engine_eval_gradient       python/src/drag_pose.py:310-343 (one decode +
+ *                                 loss + backward, no optimiser step; test hook)
+ *   dp_engine_get_state           attribute reads of DragPose (latent, buffers)
+ * The Unity-facing DragPoserDLL ABI (DragPoserDLL/exportFunc.h:61-70) is
+ * re-exported on top of this one by include/exportFunc.h.
+ */
+#ifndef DP_ENGINE_H
+#define DP_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_JOINTS 22
+#define DP_LATENT 24
+#define DP_POSE 88          /* 22 quaternions, standardised root-space */
+#define DP_PAST_ROWS 60     /* train_temporal.param["future_frames"][0] */
+#define DP_HEIGHTS 6
+#define DP_MAX_WINDOW 116
+#define DP_MAX_ITER 4096
+
+typedef enum {
+  DP_OK = 0,
+  DP_ERR_ARG = -1,
+  DP_ERR_CUDA = -2,
+  DP_ERR_STATE = -3,
+  DP_ERR_UNSUPPORTED = -4
+} dp_status;
+
+typedef struct dp_engine dp_engine;
+
+/* Optimiser settings of one DragPose.run call (drag_pose.py:196-215). */
+typedef struct {
+  double stop_eps_pos;        /* thresholds compared in double like the Python floats */
+  double stop_eps_rot;
+  double min_loss_incr;       /* -inf disables */
+  int32_t max_iter;           /* 1..DP_MAX_ITER */
+  float learning_rate;
+  float lambda_rot;
+  float lambda_temporal;
+  int32_t temporal_future_window;   /* multiple of 4, 0..DP_MAX_WINDOW */
+  int32_t joint_adjust_joint;       /* -1 = joint adjustment off */
+  int32_t joint_adjust_slot;        /* end-effector slot the joint is snapped towards */
+  float joint_adjust_weight;
+  int32_t decoder_path;             /* 0 = auto, 1 = fp32 CUDA-core decoder, 2 = tcgen05 3xTF32 decoder */
+} dp_run_params;
+
+/* Pose-VAE decoder folded to three dense layers + statistics + skeleton.
+ * All pointers are HOST memory, row-major, float32 unless stated. */
+typedef struct {
+  const float* A0; const float* b0;     /* (40,24), (40) */
+  const float* A1; const float* b1;     /* (60,40), (60) */
+  const float* A2; const float* b2;     /* (92,60), (92) */
+  const float* mean_q; const float* std_q;   /* (88) quaternion half of the dual-quat stats */
+  const float* mean_d; const float* std_d;   /* (3) displacement stats */
+  const int32_t* parents;                    /* (22), parents[0] = 0, topologically ordered */
+  const float* offsets;                      /* (22,3) */
+} dp_pose_model;
+
+int dp_engine_create(dp_engine** out, int device, int max_clips);
+int dp_engine_destroy(dp_engine* e);
+const char* dp_engine_last_error(void);
+int dp_engine_version(void);
+
+int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m);
+
+/* Temporal predictor: `blob` is the float32 concatenation, in the order
+ * documented in dragposer_b200/engine.py:pack_temporal(), of the reference
+ * Temporal.state_dict(); n_floats must be dp_engine_temporal_blob_floats(). */
+size_t dp_engine_temporal_blob_floats(void);
+int dp_engine_set_temporal_model(dp_engine* e, const float* blob, size_t n_floats,
+                                 const float* means_latent, const float* stds_latent);
+
+/* (Re)start n_clips clips: latent (n,24), global_pos (n,3), global_rot (n,4 wxyz),
+ * heights (n,6); ring buffers are filled like DragPose.set_initial_pose. HOST pointers. */
+int dp_engine_init_clips(dp_engine* e, int n_clips, const float* latent0, const float* global_pos,
+                         const float* global_rot, const float* heights);
+int dp_engine_set_global_pos(dp_engine* e, int first_clip, int n, const float* global_pos);
+int dp_engine_n_clips(const dp_engine* e);
+
+/* One frame for every clip.  Per clip c: n_ee[c] active trackers in slots
+ * [0, n_ee[c]); slot arrays have `ee_stride` slots per clip:
+ *   joints (B,ee_stride) int32, weights (B,ee_stride,2) (pos,rot),
+ *   tgt_pos (B,ee_stride,3), tgt_rot (B,ee_stride,3,3) row-major.
+ * n_ee may be NULL (all clips use ee_stride trackers).  joints/weights may be
+ * shared by all clips (shared_trackers != 0: arrays have a single row).
+ * Outputs: pose (B,88) standardised root-space quats with the root slot holding
+ * the standardised world rotation, global_pos (B,3).
+ * _device: every pointer is DEVICE memory, work is enqueued on `stream`
+ * (a cudaStream_t, may be NULL) and not synchronised.
+ * _host: every pointer is HOST memory; copies in, runs, copies out, synchronises. */
+int dp_engine_run_frame_device(dp_engine* e, const dp_run_params* p, const int32_t* n_ee,
+                               const int32_t* joints, const float* weights, int shared_trackers,
+                               const float* tgt_pos, const float* tgt_rot, int ee_stride,
+                               float* out_pose, float* out_global_pos, void* stream);
+int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, const int32_t* n_ee,
+                             const int32_t* joints, const float* weights, int shared_trackers,
+                             const float* tgt_pos, const float* tgt_rot, int ee_stride,
+                             float* out_pose, float* out_global_pos);
+
+/* n_frames consecutive frames with device-resident inputs laid out frame-major
+ * (frame stride = B*ee_stride*{1,2,3,9} elements; n_ee stride = B; joints/weights
+ * follow the frame stride unless shared_trackers).  Outputs (n_frames,B,88)/(n_frames,B,3). */
+int dp_engine_run_frames_device(dp_engine* e, const dp_run_params* p, int n_frames, const int32_t* n_ee,
+                                const int32_t* joints, const float* weights, int shared_trackers,
+                                const float* tgt_pos, const float* tgt_rot, int ee_stride,
+                                float* out_pose, float* out_global_pos, void* stream);
+
+/* Diagnostics of the last frame (HOST pointers, any may be NULL):
+ * iters (B) int32, losses (B,3) = weighted pos, lambda-scaled rot, lambda-scaled temporal. */
+int dp_engine_get_frame_stats(dp_engine* e, int32_t* iters, float* losses);
+/* Per-iteration trace of the NEXT frames: rows (B,max_iter,52) =
+ * [latent(24) | grad(24) | loss_pos | loss_rot | loss_temporal | active]. 0 disables. */
+int dp_engine_enable_trace(dp_engine* e, int enable);
+int dp_engine_get_trace(dp_engine* e, float* rows, int max_iter);
+
+/* Teacher-forced single evaluation (no state change): latents (n,24), global_rot (n,4),
+ * tgt_latent (n,24) + trackers as above; grad (n,24), losses (n,3), positions (n,22,3)
+ * (any output may be NULL).  HOST pointers. */
+int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents, const float* global_rot,
+                            const float* tgt_latent, const int32_t* n_ee, const int32_t* joints,
+                            const float* weights, int shared_trackers, const float* tgt_pos,
+                            const float* tgt_rot, int ee_stride, float lambda_rot, float lambda_temporal,
+                            int decoder_path, float* grad, float* losses, float* positions);
+
+/* Copies of the carried state in chronological ring order (HOST pointers, any may be
+ * NULL): latent (B,24), global_pos (B,3), global_rot (B,4), latent_buf (B,60,24),
+ * disp_buf (B,60,3), height_buf (B,60,6), target_buf (B,window+1,24). */
+int dp_engine_get_state(dp_engine* e, float* latent, float* global_pos, float* global_rot,
+                        float* latent_buf, float* disp_buf, float* height_buf, float* target_buf,
+                        int* current_index);
+int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const float* disp_buf,
+                               const float* height_buf);
+
+/* Predictor only (test hook / warm start): fills target_buf for `window` from the
+ * current ring buffers, as drag_pose.py:246-290 does when current_index == 0. */
+int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
+
+/* Number of kernels launched by this engine since creation (bench "gpu_launches"). */
+long long dp_engine_launch_count(const dp_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DP_ENGINE_H */
