@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: clip-frames/s of DragPoser's per-frame latent optimisation at fixed
+100 iterations, 4096 synthetic clips per GPU, 6 trackers (BASELINE.json metric / configs[3]).
+
+A "step" is one frame of the hot path for every clip of the batch: temporal-predictor
+target (window 0 => every frame) + 100 x {decode, FK, tracker loss, adjoint, decoder
+backward, latent Adam} + frame epilogue.  `value` has the tracker streams resident in
+HBM; `e2e` goes through the host-buffer API (H2D of the step's targets and D2H of the
+poses inside the timed region).  `--impl reference` times the CPU oracle port of the
+reference loop (the reference is Python and cannot travel to the GPU box) on all host
+cores.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden", "model_dancedb.npz")
+FLOP_PER_CLIP_ITER = 35520.0      # decoder fwd + bwd-data GEMMs, folded 24->40->60->92
+HBM_BYTES_PER_CLIP_FRAME = 1300.0  # algorithmic state + tracker + result bytes
+MAX_ITER = 100
+
+
+def fixed_opts(cfg):
+    return dict(stop_eps_pos=-1.0, stop_eps_rot=-1.0, max_iter=MAX_ITER, min_loss_incr=-float("inf"), learning_rate=1e-2,
+                lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window,
+                joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
+
+
+def get_config(name):
+    from dragposer_b200 import synthetic
+
+    return synthetic.config_3_trackers() if name == "3" else synthetic.config_6_trackers()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One single-threaded worker = one clip, like the reference (B = 1, CPU, fp32)."""
+    idx, n_warm, n_timed, tracker_cfg = args
+    import torch
+
+    torch.set_num_threads(1)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dragposer_port as port
+    from dragposer_b200 import model, synthetic
+
+    cfg = get_config(tracker_cfg)
+    pm = model.load_folded_npz(GOLDEN)
+    npz = np.load(GOLDEN)
+    wl = synthetic.make_workload(pm, npz["offsets"], cfg, 1, n_warm + n_timed, first_clip=idx)
+    drag = port.PortDragPose(port.PortWeights(npz), model.random_temporal_state(2222))
+    drag.set_initial_state(wl["latent0"], np.zeros((1, 3)), [[1.0, 0, 0, 0]], np.zeros((1, 6)))
+    o = fixed_opts(cfg)
+    kw = dict(stop_eps_pos=o["stop_eps_pos"], stop_eps_rot=o["stop_eps_rot"], max_iter=o["max_iter"], min_loss_incr=o["min_loss_incr"],
+              learning_rate=o["learning_rate"], lambda_rot=1.0, lambda_temporal=o["lambda_temporal"],
+              temporal_future_window=o["temporal_future_window"], joint_adjustment=o["joint_adjustment_indices"],
+              joint_adjustment_weight=o["joint_adjustment_weight"])
+    t0 = None
+    for t in range(n_warm + n_timed):
+        if t == n_warm:
+            t0 = time.perf_counter()
+        drag.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], **kw)
+    return time.perf_counter() - t0
+
+
+def cpu_reference(n_warm, n_timed, tracker_cfg, cores=None):
+    """All host cores, one clip per core; returns (clip-frames/s, cores, sample text)."""
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(i, n_warm, n_timed, tracker_cfg) for i in range(cores)])
+    value = cores * n_timed / max(times)
+    sample = (f"{cores} clips x {n_timed} frames (one single-threaded process per core, B=1 like the reference), "
+              f"{MAX_ITER} fixed iterations, {tracker_cfg} trackers, predictor every frame, after {n_warm} warm-up frames")
+    return value, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = get_config(args.trackers)
+    n_warm, n_timed = max(1, min(args.warmup, 1)), max(1, min(args.steps, 8))
+    value, cores, sample = cpu_reference(n_warm, n_timed, args.trackers)
+    line = {
+        "impl": "reference", "metric": "clip-frames/sec (fixed 100 opt iters)", "value": value, "unit": "clip-frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, args.clips * args.gpus),
+        "cpu_baseline": {"value": value, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clip-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, cfg, clips_total):
+    return {"workload": f"{args.trackers}-tracker synthetic streams (SURVEY 8d), model_dancedb weights, seed-2222 random-init predictor, "
+                        f"window {cfg.temporal_future_window}, fixed {MAX_ITER} iterations",
+            "clips_per_gpu": args.clips, "clips_total": clips_total, "trackers": int(args.trackers), "max_iter": MAX_ITER,
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"clip-shard x{args.gpus}"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from dragposer_b200 import dist as dpdist
+    from dragposer_b200 import model, synthetic
+    from dragposer_b200.engine import BatchedDragPose, RunOptions
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = get_config(args.trackers)
+    pm = model.load_folded_npz(GOLDEN)
+    offsets = np.load(GOLDEN)["offsets"]
+    tm = model.temporal_from_state(model.random_temporal_state(2222))
+    B, K, W = args.clips, args.steps, args.warmup
+    n_total = B * world
+    T = W + K
+    wl = synthetic.make_workload(pm, offsets, cfg, B, T, first_clip=rank * B, variable_mask=(args.trackers == "3"))
+    eng = BatchedDragPose(pm, offsets, tm, B, device=local)
+    eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+    opts = RunOptions(**fixed_opts(cfg))
+    E = wl["tgt_pos"].shape[2]
+    variable = "n_ee" in wl
+    d_tp = torch.from_numpy(wl["tgt_pos"]).to(dev)
+    d_tr = torch.from_numpy(wl["tgt_rot"]).to(dev)
+    if variable:
+        d_j, d_w = torch.from_numpy(wl["joints_tb"]).to(dev), torch.from_numpy(wl["weights_tb"]).to(dev)
+        d_ne = torch.from_numpy(wl["n_ee"]).to(dev)
+    else:
+        d_j = torch.from_numpy(wl["joints"].astype(np.int32)).to(dev)
+        d_w = torch.from_numpy(wl["weights"]).to(dev)
+        d_ne = None
+    d_pose = torch.empty((T, B, 88), dtype=torch.float32, device=dev)
+    d_gpos = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
+    gather_buf = torch.empty((world * B, dpdist.ROW), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    work_stream = torch.cuda.Stream(device=dev)  # everything timed runs (and is timed) on this stream
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+
+    def step(t):
+        eng.run_frames_device(1, d_tp[t], d_tr[t], d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_pose[t], d_gpos[t],
+                              n_ee=d_ne[t] if variable else None, shared=not variable, ee_stride=E, stream=stream, options=opts)
+        if world > 1:  # the only collective: gather of the result rows, in rank order
+            dpdist.gather_results(d_pose[t], d_gpos[t], n_total, out=gather_buf)
+
+    for t in range(W):
+        step(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    eng.set_profiling(True)
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    evs = []
+    for k in range(K):
+        flush.zero_()  # L2 flush between timed steps (outside the event pair)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(W + k)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = eng.launch_count() - l0
+    ms_pred, ms_frame, nprof = eng.profile()
+    eng.set_profiling(False)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = n_total * K / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region
+    h_tp, h_tr = wl["tgt_pos"], wl["tgt_rot"]
+    kw = fixed_opts(cfg)
+    run_kw = dict(options=opts)
+    for t in range(min(W, 2)):
+        eng.run(h_tp[t], h_tr[t], wl["joints_tb"][t] if variable else wl["joints"], wl["weights_tb"][t] if variable else wl["weights"],
+                n_ee=wl["n_ee"][t] if variable else None, **run_kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    last = None
+    for k in range(K):
+        t = W + k
+        last = eng.run(h_tp[t], h_tr[t], wl["joints_tb"][t] if variable else wl["joints"], wl["weights_tb"][t] if variable else wl["weights"],
+                       n_ee=wl["n_ee"][t] if variable else None, **run_kw)
+    if world > 1:  # final gather of the last frame's poses (NCCL)
+        dpdist.gather_results(torch.from_numpy(last[0]).to(dev), torch.from_numpy(last[1]).to(dev), n_total, out=gather_buf)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = n_total * K / e2e_s
+    h2d = B * E * (3 + 9) * 4 + (B * E * (1 + 2) * 4 + B * 4 if variable else E * 12)
+    d2h = B * (88 + 3) * 4
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        tf32_peak = (peaks.get("bf16_tflops_sustained") or 1400.0) / 2.0
+        hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        which = "of measured (bf16 sustained / 2 = TF32)" if peaks else "of fallback"
+        frame_ms = ms_frame / max(nprof, 1)
+        achieved_tf = B * MAX_ITER * FLOP_PER_CLIP_ITER / (frame_ms * 1e-3) / 1e12
+        achieved_gbs = B * HBM_BYTES_PER_CLIP_FRAME / (frame_ms * 1e-3) / 1e9
+        line = {
+            "metric": "clip-frames/sec (fixed 100 opt iters)", "value": value, "unit": "clip-frames/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, cfg, n_total),
+            "roofline": {"bound": "tensor", "kernel": "dp_frame_simt_kernel (persistent per-frame loop; fp32 CUDA-core decoder)",
+                         "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf32_peak,
+                         "traffic": None, "peak_source": which, "kernel_ms_per_launch": frame_ms,
+                         "predictor_ms_per_step": ms_pred / max(nprof, 1),
+                         "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
+                         "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"},
+            "e2e": {"value": e2e_value, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_reference(1, 6, args.trackers)
+            line["cpu_baseline"] = {"value": v, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=4096, help="clips per GPU (weak scaling)")
+    ap.add_argument("--trackers", default="6", choices=["6", "3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,9 @@ def build_engine(force=False, verbose=False):
     return ENGINE_SO
 
 
+def build_all(force=False, verbose=False):
+    return [build_engine(force=force, verbose=verbose)]
+
+
 if __name__ == "__main__":
-    build_engine(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(ENGINE_SO)
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -57,6 +57,9 @@ struct dp_engine {
   float *h_pose = nullptr, *d_pose = nullptr, *h_gp = nullptr, *d_gp = nullptr;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  // optional device-side timing of the two kernel groups (bench roofline)
+  int profiling = 0;
+  std::vector<cudaEvent_t> prof_events;  // triples: before predictor, before frame kernel, after frame kernel
 };
 
 extern "C" const char* dp_engine_last_error(void) { return g_err.c_str(); }
@@ -301,6 +304,11 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
     CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (W + 1) * DP_L * 4, st));
     e->target_rows = W + 1;
   }
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (e->profiling) {
+    for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&ev[i]));
+    CK(cudaEventRecord(ev[0], st));
+  }
   if (e->current_index == 0) {
     if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
     CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
@@ -330,8 +338,13 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.out_pose = out_pose; a.out_gpos = out_gpos; a.out_iters = e->d_iters; a.out_losses = e->d_losses;
   a.trace = e->trace_enabled ? e->d_trace : nullptr;
   a.trace_iters = e->trace_iters;
+  if (e->profiling) CK(cudaEventRecord(ev[1], st));
   CK(dp_frame_simt_launch(a, e->num_sms, st));
   ++e->launches;
+  if (e->profiling) {
+    CK(cudaEventRecord(ev[2], st));
+    for (int i = 0; i < 3; ++i) e->prof_events.push_back(ev[i]);
+  }
   e->ring_head = (e->ring_head + 1) % DP_PAST;
   e->current_index = (W == 0) ? 0 : (e->current_index + 1) % W;  // drag_pose.py:399-402
   return DP_OK;
@@ -543,5 +556,33 @@ extern "C" int dp_engine_predict_targets(dp_engine* e, int window, void* stream)
   }
   CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf, e->ring_head,
                      e->n_clips, window, e->d_target_buf, e->tw, st, &e->launches));
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_profiling(dp_engine* e, int enable) {
+  if (!e) return fail(DP_ERR_ARG, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  e->prof_events.clear();
+  e->profiling = enable ? 1 : 0;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double* ms_frame_kernel, long long* n_frames) {
+  if (!e) return fail(DP_ERR_ARG, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  double tp = 0.0, tf = 0.0;
+  for (size_t i = 0; i + 2 < e->prof_events.size(); i += 3) {
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, e->prof_events[i], e->prof_events[i + 1]));
+    CK(cudaEventElapsedTime(&b, e->prof_events[i + 1], e->prof_events[i + 2]));
+    tp += a;
+    tf += b;
+  }
+  if (ms_predictor) *ms_predictor = tp;
+  if (ms_frame_kernel) *ms_frame_kernel = tf;
+  if (n_frames) *n_frames = (long long)(e->prof_events.size() / 3);
   return DP_OK;
 }

@@ -221,5 +221,14 @@ class BatchedDragPose:
                                                     int(decoder_path), _ptr(grad), _ptr(losses), _ptr(pos)))
         return dict(grad=grad, lp=losses[:, 0], lr=losses[:, 1], lt=losses[:, 2], pos=pos)
 
+    def set_profiling(self, on=True):
+        _lib.check(self.lib.dp_engine_set_profiling(self.h, int(on)))
+
+    def profile(self):
+        """(ms in the temporal predictor, ms in the frame kernel, frames) since set_profiling(True)."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_longlong(0)
+        _lib.check(self.lib.dp_engine_get_profile(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def launch_count(self):
         return int(self.lib.dp_engine_launch_count(self.h))

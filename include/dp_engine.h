@@ -155,6 +155,12 @@ int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const floa
  * current ring buffers, as drag_pose.py:246-290 does when current_index == 0. */
 int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
 
+/* Device-side timing of the two kernel groups, measured with CUDA events on the
+ * launching stream: accumulated milliseconds of the temporal predictor and of the
+ * persistent frame kernel over the frames run since profiling was (re)enabled. */
+int dp_engine_set_profiling(dp_engine* e, int enable);
+int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double* ms_frame_kernel, long long* n_frames);
+
 /* Number of kernels launched by this engine since creation (bench "gpu_launches"). */
 long long dp_engine_launch_count(const dp_engine* e);
 
