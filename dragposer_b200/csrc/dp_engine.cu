@@ -32,6 +32,8 @@ struct dp_engine {
   bool has_pose = false, has_temporal = false;
   DpModelImage* d_model = nullptr;
   float* d_tblob = nullptr;
+  unsigned char* d_fftiles = nullptr;  // pre-tiled 3xTF32 FF weights of the 6 predictor layers
+  int predictor_path = 0;              // 0 = tcgen05 FF (default), 1 = fp32 CUDA-core FF
   float *d_mu = nullptr, *d_sigma = nullptr;
   TpLayout tl;
   // state
@@ -123,7 +125,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_stage(e);
-  cudaFree(e->d_model); cudaFree(e->d_tblob); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_model); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam);
@@ -224,6 +226,15 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
   CK(cudaMemcpy(e->d_tblob, blob, n_floats * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->d_mu, means_latent, DP_L * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->d_sigma, stds_latent, DP_L * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<unsigned char> tiles((size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES);
+    for (int l = 0; l < TP_NENC + TP_NDEC; ++l) {
+      const TpFF& f = l < TP_NENC ? e->tl.enc[l].ff : e->tl.dec[l - TP_NENC].ff;
+      dp_ff_tc_pack(blob + f.w1, blob + f.b1, blob + f.w2, tiles.data() + (size_t)l * FFT_LAYER_BYTES);
+    }
+    if (!e->d_fftiles) CK(cudaMalloc(&e->d_fftiles, tiles.size()));
+    CK(cudaMemcpy(e->d_fftiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
+  }
   e->has_temporal = true;
   return DP_OK;
 }
@@ -312,7 +323,8 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   if (e->current_index == 0) {
     if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
     CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
-                       e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, st, &e->launches));
+                       e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
+                       &e->launches));
   }
   if (e->trace_enabled && (!e->d_trace || e->trace_iters < p->max_iter)) {
     cudaFree(e->d_trace);
@@ -555,7 +567,8 @@ extern "C" int dp_engine_predict_targets(dp_engine* e, int window, void* stream)
     e->target_rows = window + 1;
   }
   CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf, e->ring_head,
-                     e->n_clips, window, e->d_target_buf, e->tw, st, &e->launches));
+                     e->n_clips, window, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
+                     &e->launches));
   return DP_OK;
 }
 
@@ -584,5 +597,11 @@ extern "C" int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double*
   if (ms_predictor) *ms_predictor = tp;
   if (ms_frame_kernel) *ms_frame_kernel = tf;
   if (n_frames) *n_frames = (long long)(e->prof_events.size() / 3);
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_predictor_path(dp_engine* e, int path) {
+  if (!e || path < 0 || path > 1) return fail(DP_ERR_ARG, "predictor path must be 0 (tcgen05 3xTF32 FF) or 1 (fp32 CUDA-core FF)");
+  e->predictor_path = path;
   return DP_OK;
 }

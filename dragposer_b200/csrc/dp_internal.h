@@ -12,6 +12,12 @@ struct TpWork {
 };
 
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
+// fftiles: (TP_NENC + TP_NDEC) x FFT_LAYER_BYTES pre-tiled 3xTF32 FF weights (encoder layers first), or null
+// to run the fp32 CUDA-core FF kernel.
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
                             const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
-                            int window, float* target_buf, const TpWork& w, cudaStream_t st, long long* launches);
+                            int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
+                            long long* launches);
+void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned char* dst);
+cudaError_t dp_ff_tc_launch(const unsigned char* wtiles, const float* blob, const TpFF& F, const TpNorm& N1, const TpNorm& N2,
+                            int has_n2, const float* x, int n_rows, int T, int row_stride, float* out, cudaStream_t st);

@@ -280,7 +280,8 @@ static const size_t kFfSmem = sizeof(float) * (2 * TP_D * FF_HC + FF_TM * (TP_D 
 
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
                             const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
-                            int window, float* target_buf, const TpWork& w, cudaStream_t st, long long* launches) {
+                            int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
+                            long long* launches) {
   cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
   if (err != cudaSuccess) return err;
   tp_embed_kernel<<<B, 128, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
@@ -290,8 +291,14 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
   const int enc_rows = B * TP_S;
   for (int l = 0; l < TP_NENC; ++l) {
     tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2);
-    tp_ff_ln_kernel<<<(enc_rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm,
-                                                                    l == TP_NENC - 1, e2, enc_rows, TP_S, TP_S, e);
+    if (fftiles) {
+      err = dp_ff_tc_launch(fftiles + (size_t)l * FFT_LAYER_BYTES, blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm, l == TP_NENC - 1, e2,
+                            enc_rows, TP_S, TP_S, e, st);
+      if (err != cudaSuccess) return err;
+    } else {
+      tp_ff_ln_kernel<<<(enc_rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm,
+                                                                      l == TP_NENC - 1, e2, enc_rows, TP_S, TP_S, e);
+    }
     *launches += 2;
   }
   int T = 1;
@@ -304,8 +311,14 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     for (int l = 0; l < TP_NDEC; ++l) {
       tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2);
       tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d);
-      tp_ff_ln_kernel<<<(rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
-                                                                  l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2);
+      if (fftiles) {
+        err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
+                              l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, st);
+        if (err != cudaSuccess) return err;
+      } else {
+        tp_ff_ln_kernel<<<(rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
+                                                                    l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2);
+      }
       float* t = d; d = d2; d2 = t;
       *launches += 3;
     }

@@ -19,6 +19,9 @@
 #define TP_PE 30
 #define TP_NENC 3
 #define TP_NDEC 3
+#define FFT_HC 64                 // hidden units per tensor-core FF chunk
+#define FFT_CHUNK_BYTES 49408     // W1c hi|lo (2 x 12288) + b1c (256) + W2c hi|lo (2 x 12288)
+#define FFT_LAYER_BYTES ((TP_FF / FFT_HC) * FFT_CHUNK_BYTES)
 
 struct TpAttn {   // offsets (floats) into the blob
   size_t w_in;    // [48][144]  (q | k | v columns)

@@ -221,6 +221,10 @@ class BatchedDragPose:
                                                     int(decoder_path), _ptr(grad), _ptr(losses), _ptr(pos)))
         return dict(grad=grad, lp=losses[:, 0], lr=losses[:, 1], lt=losses[:, 2], pos=pos)
 
+    def set_predictor_path(self, path):
+        """0 = tcgen05 3xTF32 feed-forward (default), 1 = fp32 CUDA-core feed-forward."""
+        _lib.check(self.lib.dp_engine_set_predictor_path(self.h, int(path)))
+
     def set_profiling(self, on=True):
         _lib.check(self.lib.dp_engine_set_profiling(self.h, int(on)))
 
