@@ -55,8 +55,23 @@ def build_engine(force=False, verbose=False):
     return ENGINE_SO
 
 
+def build_dll(force=False, verbose=False):
+    """libDragPoserDLL.so: the reference's exportFunc.h C ABI (host C++ only) linked against libdp_engine.so."""
+    build_engine(force=force, verbose=verbose)
+    src = os.path.join(HERE, "csrc_dll", "exportFunc.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "exportFunc.h"), os.path.join(HERE, "..", "include", "dp_engine.h"), ENGINE_SO]
+    if not force and not _stale(DLL_SO, deps):
+        return DLL_SO
+    cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-fvisibility=hidden", "-o", DLL_SO, src, "-L" + HERE, "-ldp_engine",
+           "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return DLL_SO
+
+
 def build_all(force=False, verbose=False):
-    return [build_engine(force=force, verbose=verbose)]
+    return [build_engine(force=force, verbose=verbose), build_dll(force=force, verbose=verbose)]
 
 
 if __name__ == "__main__":
