@@ -75,41 +75,68 @@ __global__ void tp_dec_embed_kernel(const float* __restrict__ blob, TpLayout L, 
   }
 }
 
-// ---- out = LayerNorm(xq + MHA(xq, xkv, xkv)); one CTA per clip
-__global__ void __launch_bounds__(128) tp_mha_ln_kernel(const float* __restrict__ blob, TpAttn A, TpNorm N,
-                                                        const float* __restrict__ xq_g, int T, int q_stride,
-                                                        const float* __restrict__ xkv_g, int S, int kv_stride,
-                                                        float* __restrict__ out_g) {
-  __shared__ float xq[TP_MAXT][TP_D], xkv[TP_MAXT][TP_D];
-  __shared__ float q[TP_MAXT][TP_D], k[TP_MAXT][TP_D + 1], v[TP_MAXT][TP_D], o[TP_MAXT][TP_D];
+// ---- out = LayerNorm(xq + MHA(xq, xkv, xkv)); one CTA (160 threads) per clip.
+// Projections are register tiled: a thread owns ONE output feature and keeps the accumulators of up to 16
+// tokens in registers, so every weight is fetched once per CTA (coalesced, L1/L2 resident) and every
+// activation is a broadcast LDS.128.
+#define MHA_THREADS 160
+#define MHA_TT 16
+template <int NT>
+__device__ __forceinline__ void project_feature(const float (*x)[TP_D], int t0, int nt, const float* __restrict__ W, int ldw, int col,
+                                                float bias, float (&acc)[NT]) {
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t] = bias;
+#pragma unroll 2
+  for (int i = 0; i < TP_D; i += 4) {
+    const float w0 = W[(i + 0) * ldw + col], w1 = W[(i + 1) * ldw + col], w2 = W[(i + 2) * ldw + col], w3 = W[(i + 3) * ldw + col];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t < nt) {
+        const float4 xv = *reinterpret_cast<const float4*>(&x[t0 + t][i]);
+        acc[t] = fmaf(xv.x, w0, acc[t]);
+        acc[t] = fmaf(xv.y, w1, acc[t]);
+        acc[t] = fmaf(xv.z, w2, acc[t]);
+        acc[t] = fmaf(xv.w, w3, acc[t]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __restrict__ blob, TpAttn A, TpNorm N,
+                                                                const float* __restrict__ xq_g, int T, int q_stride,
+                                                                const float* __restrict__ xkv_g, int S, int kv_stride,
+                                                                float* __restrict__ out_g) {
+  __shared__ __align__(16) float xq[TP_MAXT][TP_D], xkv[TP_MAXT][TP_D];
+  __shared__ __align__(16) float q[TP_MAXT][TP_D], k[TP_MAXT][TP_D + 1], v[TP_MAXT][TP_D], o[TP_MAXT][TP_D];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < T * TP_D; idx += 128) xq[idx / TP_D][idx % TP_D] = xq_g[(size_t)b * q_stride * TP_D + idx];
-  for (int idx = tid; idx < S * TP_D; idx += 128) xkv[idx / TP_D][idx % TP_D] = xkv_g[(size_t)b * kv_stride * TP_D + idx];
+  for (int idx = tid; idx < T * TP_D / 4; idx += MHA_THREADS)
+    reinterpret_cast<float4*>(&xq[0][0])[idx] = reinterpret_cast<const float4*>(xq_g + (size_t)b * q_stride * TP_D)[idx];
+  for (int idx = tid; idx < S * TP_D / 4; idx += MHA_THREADS)
+    reinterpret_cast<float4*>(&xkv[0][0])[idx] = reinterpret_cast<const float4*>(xkv_g + (size_t)b * kv_stride * TP_D)[idx];
   __syncthreads();
   const float* Win = blob + A.w_in;
   const float* bin = blob + A.b_in;
-  const float scale = rsqrtf((float)TP_HD);
-  for (int idx = tid; idx < T * TP_D; idx += 128) {
-    const int t = idx / TP_D, f = idx % TP_D;
-    float a = bin[f];
-#pragma unroll 8
-    for (int i = 0; i < TP_D; ++i) a = fmaf(xq[t][i], Win[i * 3 * TP_D + f], a);
-    q[t][f] = a * scale;
-  }
-  for (int idx = tid; idx < S * TP_D; idx += 128) {
-    const int s = idx / TP_D, f = idx % TP_D;
-    float ak = bin[TP_D + f], av = bin[2 * TP_D + f];
-#pragma unroll 8
-    for (int i = 0; i < TP_D; ++i) {
-      const float xv = xkv[s][i];
-      ak = fmaf(xv, Win[i * 3 * TP_D + TP_D + f], ak);
-      av = fmaf(xv, Win[i * 3 * TP_D + 2 * TP_D + f], av);
+  if (tid < 3 * TP_D) {  // feature tid of [q | k | v]
+    const bool is_q = tid < TP_D;
+    const int n_tok = is_q ? T : S;
+    const float (*src)[TP_D] = is_q ? xq : xkv;
+    const float bias = bin[tid];
+    const float scale = is_q ? rsqrtf((float)TP_HD) : 1.0f;
+    for (int t0 = 0; t0 < n_tok; t0 += MHA_TT) {
+      float acc[MHA_TT];
+      const int nt = min(MHA_TT, n_tok - t0);
+      project_feature<MHA_TT>(src, t0, nt, Win, 3 * TP_D, tid, bias, acc);
+#pragma unroll
+      for (int t = 0; t < MHA_TT; ++t)
+        if (t < nt) {
+          if (is_q) q[t0 + t][tid] = acc[t] * scale;
+          else if (tid < 2 * TP_D) k[t0 + t][tid - TP_D] = acc[t];
+          else v[t0 + t][tid - 2 * TP_D] = acc[t];
+        }
     }
-    k[s][f] = ak;
-    v[s][f] = av;
   }
   __syncthreads();
-  for (int idx = tid; idx < T * TP_H; idx += 128) {
+  for (int idx = tid; idx < T * TP_H; idx += MHA_THREADS) {
     const int t = idx / TP_H, h = idx % TP_H;
     float sc[TP_MAXT];
     float mx = -3.0e38f;
@@ -134,21 +161,28 @@ __global__ void __launch_bounds__(128) tp_mha_ln_kernel(const float* __restrict_
     }
   }
   __syncthreads();
+  // output projection + residual, register tiled the same way (48 features x up to 3 token groups), then LayerNorm per token
   const float* Wo = blob + A.w_out;
   const float* bo = blob + A.b_out;
-  for (int t = warp; t < T; t += 4) {
-    const bool has1 = lane + 32 < TP_D;
-    float a0 = bo[lane], a1 = has1 ? bo[lane + 32] : 0.0f;
-#pragma unroll 8
-    for (int i = 0; i < TP_D; ++i) {
-      const float ov = o[t][i];
-      a0 = fmaf(ov, Wo[i * TP_D + lane], a0);
-      if (has1) a1 = fmaf(ov, Wo[i * TP_D + lane + 32], a1);
+  {
+    const int f = tid % TP_D, grp = tid / TP_D;  // 3 groups of 48 threads take interleaved token blocks
+    if (grp < 3) {
+      const int per = (T + 2) / 3;
+      const int t0 = grp * per, nt = max(0, min(per, T - t0));
+      if (nt > 0) {
+        float acc[11];  // ceil(TP_MAXT / 3)
+        project_feature<11>(o, t0, nt, Wo, TP_D, f, bo[f], acc);
+#pragma unroll
+        for (int t = 0; t < 11; ++t)
+          if (t < nt) q[t0 + t][f] = acc[t] + xq[t0 + t][f];  // q is dead: reuse it for the residual sums
+      }
     }
-    a0 += xq[t][lane];
-    if (has1) a1 += xq[t][lane + 32];
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += MHA_THREADS / 32) {
+    const bool has1 = lane + 32 < TP_D;
     float r0, r1;
-    layer_norm_row(a0, a1, has1, blob + N.w, blob + N.b, lane, r0, r1);
+    layer_norm_row(q[t][lane], has1 ? q[t][lane + 32] : 0.0f, has1, blob + N.w, blob + N.b, lane, r0, r1);
     float* dst = out_g + ((size_t)b * q_stride + t) * TP_D;
     dst[lane] = r0;
     if (has1) dst[lane + 32] = r1;
@@ -290,7 +324,7 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
   for (int l = 0; l < TP_NENC; ++l) {
-    tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2);
+    tp_mha_ln_kernel<<<B, MHA_THREADS, 0, st>>>(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2);
     if (fftiles) {
       err = dp_ff_tc_launch(fftiles + (size_t)l * FFT_LAYER_BYTES, blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm, l == TP_NENC - 1, e2,
                             enc_rows, TP_S, TP_S, e, st);
@@ -309,8 +343,8 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     float* d2 = w.dec2;
     const int rows = B * T;
     for (int l = 0; l < TP_NDEC; ++l) {
-      tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2);
-      tp_mha_ln_kernel<<<B, 128, 0, st>>>(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d);
+      tp_mha_ln_kernel<<<B, MHA_THREADS, 0, st>>>(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2);
+      tp_mha_ln_kernel<<<B, MHA_THREADS, 0, st>>>(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d);
       if (fftiles) {
         err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
                               l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, st);
