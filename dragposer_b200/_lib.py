@@ -64,6 +64,7 @@ SIGNATURES = {
     "dp_engine_set_ring_buffers": (C.c_int, [_VP, _VP, _VP, _VP]),
     "dp_engine_predict_targets": (C.c_int, [_VP, C.c_int, _VP]),
     "dp_engine_launch_count": (C.c_longlong, [_VP]),
+    "dp_engine_last_decoder_path": (C.c_int, [_VP]),
     "dp_engine_set_predictor_path": (C.c_int, [_VP, C.c_int]),
     "dp_engine_set_profiling": (C.c_int, [_VP, C.c_int]),
     "dp_engine_get_profile": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -46,8 +46,38 @@ struct __align__(16) DpModelImage {
 };
 static_assert(sizeof(DpModelImage) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
 
+// Model image of the tcgen05 frame kernel: the three folded matrices as bf16 split pieces (x = x1 + x2 [+ x3]) in the
+// canonical no-swizzle UMMA layout -- element (o, i) of layer l at (o/8)*128*(kin/8) + (i/8)*128 + (o%8)*16 + (i%8)*2 --
+// read K-major by the forward GEMMs and MN-major by the backward GEMMs; zero padded to kin x kout (multiples of 16).
+#define DP_TC_CLIPS 32
+#define DP_TC_W0_OFF 0u
+#define DP_TC_W1_OFF 3072u    // W0: 48 rows x 32 cols x 2 B
+#define DP_TC_W2_OFF 9216u    // W1: 64 x 48 x 2 B = 6144
+#define DP_TC_W_BYTES 21504u  // W2: 96 x 64 x 2 B = 12288
+#define DP_TC_PIECES 3
+struct __align__(16) DpModelImageTC {
+  unsigned char w[DP_TC_PIECES][DP_TC_W_BYTES];
+  float b0[DP_H0];
+  float b1[DP_H1];
+  float b2[DP_Y];
+  float mean_q[DP_J * 4];
+  float std_q[DP_J * 4];
+  float mean_d[4];
+  float std_d[4];
+  float off[32][4];
+  float coff[DP_MAX_CHILD][32][4];
+  int32_t child[DP_MAX_CHILD][32];
+  int32_t jump[DP_JUMP_ROUNDS][32];
+  int32_t parent[32];
+  int32_t last[32];
+  int32_t height_slot[32];
+  int32_t pad[32];
+};
+static_assert(sizeof(DpModelImageTC) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
+
 struct DpFrameArgs {
   const DpModelImage* model;
+  const DpModelImageTC* model_tc;
   int n_clips;
   // carried state (HBM)
   float* latent;        // (B,24) latent after the last Adam step (seeds the next frame)

@@ -31,9 +31,11 @@ struct dp_engine {
   int device = 0, max_clips = 0, n_clips = 0, num_sms = 148;
   bool has_pose = false, has_temporal = false;
   DpModelImage* d_model = nullptr;
+  DpModelImageTC* d_model_tc = nullptr;
   float* d_tblob = nullptr;
   unsigned char* d_fftiles = nullptr;  // pre-tiled 3xTF32 FF weights of the 6 predictor layers
   int predictor_path = 0;              // 0 = tcgen05 FF (default), 1 = fp32 CUDA-core FF
+  int last_path = 0;                   // decoder path of the last frame: 1 = fp32, 2 = tcgen05
   float *d_mu = nullptr, *d_sigma = nullptr;
   TpLayout tl;
   // state
@@ -87,6 +89,7 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   const size_t B = (size_t)max_clips;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&e->d_model, sizeof(DpModelImage)));
+  CK(cudaMalloc(&e->d_model_tc, sizeof(DpModelImageTC)));
   CK(cudaMalloc(&e->d_latent, B * DP_L * 4));
   CK(cudaMalloc(&e->d_gpos, B * 3 * 4));
   CK(cudaMalloc(&e->d_grot, B * 4 * 4));
@@ -125,7 +128,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_stage(e);
-  cudaFree(e->d_model); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam);
@@ -213,6 +216,44 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     }
   }
   CK(cudaMemcpy(e->d_model, raw.data(), raw.size(), cudaMemcpyHostToDevice));
+  {  // tcgen05 image: bf16 split pieces of the same matrices + the same statistics / skeleton tables
+    std::vector<unsigned char> raw_tc(sizeof(DpModelImageTC), 0);
+    DpModelImageTC& T = *reinterpret_cast<DpModelImageTC*>(raw_tc.data());
+    auto bf16_rn = [](float x) -> uint16_t {  // round-to-nearest-even, what cvt.rn.bf16.f32 does
+      uint32_t u;
+      memcpy(&u, &x, 4);
+      u += 0x7FFFu + ((u >> 16) & 1u);
+      return (uint16_t)(u >> 16);
+    };
+    auto bf16_val = [](uint16_t h) -> float {
+      const uint32_t u = (uint32_t)h << 16;
+      float f;
+      memcpy(&f, &u, 4);
+      return f;
+    };
+    const uint32_t woff[3] = {DP_TC_W0_OFF, DP_TC_W1_OFF, DP_TC_W2_OFF};
+    const int kin[3] = {32, 48, 64};
+    for (int l = 0; l < 3; ++l) {
+      const int K = dims[l], N = dims[l + 1];
+      for (int o = 0; o < N; ++o)
+        for (int i = 0; i < K; ++i) {
+          float r = A[l][o * K + i];
+          const uint32_t at = woff[l] + (o / 8) * 128 * (kin[l] / 8) + (i / 8) * 128 + (o % 8) * 16 + (i % 8) * 2;
+          for (int p = 0; p < DP_TC_PIECES; ++p) {
+            const uint16_t h = bf16_rn(r);
+            memcpy(&T.w[p][at], &h, 2);
+            r -= bf16_val(h);
+          }
+        }
+    }
+    memcpy(T.b0, I.b0, sizeof(I.b0)); memcpy(T.b1, I.b1, sizeof(I.b1)); memcpy(T.b2, I.b2, sizeof(I.b2));
+    memcpy(T.mean_q, I.mean_q, sizeof(I.mean_q)); memcpy(T.std_q, I.std_q, sizeof(I.std_q));
+    memcpy(T.mean_d, I.mean_d, sizeof(I.mean_d)); memcpy(T.std_d, I.std_d, sizeof(I.std_d));
+    memcpy(T.off, I.off, sizeof(I.off)); memcpy(T.coff, I.coff, sizeof(I.coff)); memcpy(T.child, I.child, sizeof(I.child));
+    memcpy(T.jump, I.jump, sizeof(I.jump)); memcpy(T.parent, I.parent, sizeof(I.parent)); memcpy(T.last, I.last, sizeof(I.last));
+    memcpy(T.height_slot, I.height_slot, sizeof(I.height_slot));
+    CK(cudaMemcpy(e->d_model_tc, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
+  }
   e->has_pose = true;
   return DP_OK;
 }
@@ -303,7 +344,7 @@ static int check_params(const dp_engine* e, const dp_run_params* p, int ee_strid
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
   if (p->joint_adjust_joint >= DP_JOINTS || (p->joint_adjust_joint >= 0 && (p->joint_adjust_slot < 0 || p->joint_adjust_slot >= ee_stride)))
     return fail(DP_ERR_ARG, "joint adjustment indices out of range");
-  if (p->decoder_path == 2) return fail(DP_ERR_UNSUPPORTED, "tcgen05 decoder path not built in this version");
+  if (p->decoder_path < 0 || p->decoder_path > 2) return fail(DP_ERR_ARG, "decoder_path must be 0 (auto), 1 (fp32) or 2 (tcgen05)");
   return DP_OK;
 }
 
@@ -335,6 +376,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   if (e->trace_enabled) CK(cudaMemsetAsync(e->d_trace, 0, (size_t)e->max_clips * e->trace_iters * 52 * 4, st));
   DpFrameArgs a{};
   a.model = e->d_model;
+  a.model_tc = e->d_model_tc;
   a.n_clips = e->n_clips;
   a.latent = e->d_latent; a.gpos = e->d_gpos; a.grot = e->d_grot;
   a.latent_buf = e->d_latent_buf; a.disp_buf = e->d_disp_buf; a.height_buf = e->d_height_buf;
@@ -351,7 +393,12 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.trace = e->trace_enabled ? e->d_trace : nullptr;
   a.trace_iters = e->trace_iters;
   if (e->profiling) CK(cudaEventRecord(ev[1], st));
-  CK(dp_frame_simt_launch(a, e->num_sms, st));
+  // auto: tensor-core decoder once a batch fills a fair share of the SMs with 32-clip tiles; the fp32 warp-per-clip
+  // kernel is the low-latency path for small batches (B = 1 streaming)
+  const bool use_tc = p->decoder_path == 2 || (p->decoder_path == 0 && e->n_clips >= 1024);
+  if (use_tc) CK(dp_frame_tc_launch(a, st));
+  else CK(dp_frame_simt_launch(a, e->num_sms, st));
+  e->last_path = use_tc ? 2 : 1;
   ++e->launches;
   if (e->profiling) {
     CK(cudaEventRecord(ev[2], st));
@@ -471,7 +518,6 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
     return fail(DP_ERR_ARG, "dp_engine_eval_gradient: null argument");
   if (!e->has_pose) return fail(DP_ERR_STATE, "pose model not set");
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
-  if (decoder_path == 2) return fail(DP_ERR_UNSUPPORTED, "tcgen05 decoder path not built in this version");
   CK(cudaSetDevice(e->device));
   CK(cudaDeviceSynchronize());
   const size_t N = (size_t)n, S = (size_t)ee_stride, nj = shared ? S : N * S;
@@ -491,14 +537,15 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   CK(cudaMemcpy(d_tr, tgt_rot, N * S * 36, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_adam, 0, 8));
   DpFrameArgs a{};
-  a.model = e->d_model; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
+  a.model = e->d_model; a.model_tc = e->d_model_tc; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
   a.target_buf = d_t; a.target_rows = 1; a.target_index = 0;
   a.n_ee = d_ne; a.joints = d_j; a.weights = d_w; a.shared_trackers = shared; a.tgt_pos = d_tp; a.tgt_rot = d_tr;
   a.ee_stride = ee_stride;
   a.eps_pos = -1.0; a.eps_rot = -1.0; a.min_incr = -std::numeric_limits<double>::infinity();
   a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
   a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
-  CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
+  if (decoder_path == 2) CK(dp_frame_tc_launch(a, e->stream));
+  else CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
   ++e->launches;
   CK(cudaStreamSynchronize(e->stream));
   if (grad) CK(cudaMemcpy(grad, d_grad, N * DP_L * 4, cudaMemcpyDeviceToHost));
@@ -605,3 +652,5 @@ extern "C" int dp_engine_set_predictor_path(dp_engine* e, int path) {
   e->predictor_path = path;
   return DP_OK;
 }
+
+extern "C" int dp_engine_last_decoder_path(const dp_engine* e) { return e ? e->last_path : 0; }

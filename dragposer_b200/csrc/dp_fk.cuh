@@ -1,0 +1,182 @@
+// dp_fk.cuh -- forward kinematics + masked tracker loss + reverse-mode adjoint for ONE clip per warp
+// (lane == joint), shared by the fp32 CUDA-core frame kernel and the tcgen05 frame kernel.
+// Arithmetic: SURVEY.md appendix B, i.e. the closed form of python/src/utils.py:80-149 and
+// python/src/drag_pose.py:66-194.  `M` only needs the statistics / skeleton-table members.
+#pragma once
+#include "dp_common.cuh"
+
+struct ClipTrackers {   // per-clip, per-lane(joint) tracker row in shared memory
+  float4 pw;            // tp.xyz, w_pos
+  float4 r0;            // TR row 0, w_rot
+  float4 r1;            // TR row 1, -
+  float4 r2;            // TR row 2, -
+};
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.0f ? x : 0.2f * x; }
+
+struct FkOut {
+  float lp, lr;        // weighted position loss, lambda-scaled rotation loss (warp-uniform)
+};
+
+// Forward kinematics + masked tracker loss (+ adjoint) for ONE clip; lane == joint.
+// y / ybar alias the same 96-float shared buffer (all reads of y precede the writes).
+template <bool ADJOINT, bool EPILOGUE, class MODEL>
+__device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybuf, const ClipTrackers* __restrict__ trk,
+                                         const float g[4], float inv3e, float lrot9e, int lane,
+                                         // epilogue outputs
+                                         float q_out[4], float r_out[4], float p_out[3], float d_out[3]) {
+  const bool is_joint = lane < DP_J;
+  const bool is_root = lane == 0;
+  const float4 yv = is_joint ? reinterpret_cast<const float4*>(ybuf)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 yd = reinterpret_cast<const float4*>(ybuf)[DP_J];
+  const float4 mq = is_joint ? reinterpret_cast<const float4*>(M.mean_q)[lane] : make_float4(1.f, 0.f, 0.f, 0.f);
+  const float4 sq = is_joint ? reinterpret_cast<const float4*>(M.std_q)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  float u[4] = {fmaf(yv.x, sq.x, mq.x), fmaf(yv.y, sq.y, mq.y), fmaf(yv.z, sq.z, mq.z), fmaf(yv.w, sq.w, mq.w)};
+  const float n = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
+  const float inv = 1.0f / (n + 1e-8f);
+  float q[4] = {u[0] * inv, u[1] * inv, u[2] * inv, u[3] * inv};
+  float q0[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q0[i] = __shfl_sync(0xffffffffu, q[i], 0);
+  float r[4];
+  quat_mul(g, q0, r);  // world root rotation (drag_pose.py:88-92)
+  float R0[9], Mj[9], R[9];
+  quat_to_mat(r, R0);
+  {
+    const float ident[4] = {1.f, 0.f, 0.f, 0.f};
+    quat_to_mat(is_root ? ident : q, Mj);
+  }
+  mat_mul(R0, Mj, R);  // closed form of utils.py:80-149: R_j = R_0 M(q_j)
+  const float d[3] = {fmaf(yd.x, M.std_d[0], M.mean_d[0]), fmaf(yd.y, M.std_d[1], M.mean_d[1]),
+                      fmaf(yd.z, M.std_d[2], M.mean_d[2])};
+  float p0[3];
+  mat_vec(R0, d, p0);  // == quat.mul_vec(world_rotation, displacement) (drag_pose.py:102)
+  // c_j = R_parent o_j ; p_j = sum of c over the ancestor chain (log-step pointer jumping)
+  const int par = M.parent[lane];
+  float Rp[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rp[i] = __shfl_sync(0xffffffffu, R[i], par);
+  const float4 off = *reinterpret_cast<const float4*>(M.off[lane]);
+  const float ov[3] = {off.x, off.y, off.z};
+  float p[3];
+  mat_vec(Rp, ov, p);
+  if (is_root) { p[0] = p0[0]; p[1] = p0[1]; p[2] = p0[2]; }
+#pragma unroll
+  for (int rd = 0; rd < DP_JUMP_ROUNDS; ++rd) {
+    const int a = M.jump[rd][lane];
+    const int src = a >= 0 ? a : lane;
+    const float t0 = __shfl_sync(0xffffffffu, p[0], src);
+    const float t1 = __shfl_sync(0xffffffffu, p[1], src);
+    const float t2 = __shfl_sync(0xffffffffu, p[2], src);
+    if (a >= 0) { p[0] += t0; p[1] += t1; p[2] += t2; }
+  }
+  // masked tracker loss (drag_pose.py:116-124); untracked lanes carry zero weights
+  const ClipTrackers tk = trk[lane];
+  const float ep[3] = {p[0] - tk.pw.x, p[1] - tk.pw.y, p[2] - tk.pw.z};
+  const float wp = tk.pw.w, wr = tk.r0.w;
+  float eR[9] = {R[0] - tk.r0.x, R[1] - tk.r0.y, R[2] - tk.r0.z, R[3] - tk.r1.x, R[4] - tk.r1.y,
+                 R[5] - tk.r1.z, R[6] - tk.r2.x, R[7] - tk.r2.y, R[8] - tk.r2.z};
+  float sp = ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2];
+  float sr = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) sr = fmaf(eR[i], eR[i], sr);
+  sp *= wp;
+  sr *= wr;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+  }
+  FkOut out;
+  out.lp = sp * inv3e;
+  out.lr = sr * lrot9e;
+  if (EPILOGUE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q_out[i] = q[i]; r_out[i] = r[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p_out[i] = p[i]; d_out[i] = d[i]; }
+  }
+  if (ADJOINT) {
+    // seeds
+    const float kp = 2.0f * wp * inv3e, kr = 2.0f * wr * lrot9e;
+    float pb[3] = {ep[0] * kp, ep[1] * kp, ep[2] * kp};
+    float Rb[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb[i] = eR[i] * kr;
+    // subtree sums of pbar over the pre-order numbering: inclusive scan, then a range difference
+    float P[3] = {pb[0], pb[1], pb[2]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t0 = __shfl_up_sync(0xffffffffu, P[0], o);
+      const float t1 = __shfl_up_sync(0xffffffffu, P[1], o);
+      const float t2 = __shfl_up_sync(0xffffffffu, P[2], o);
+      if (lane >= o) { P[0] += t0; P[1] += t1; P[2] += t2; }
+    }
+    const int last = M.last[lane];
+    float cb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float hi = __shfl_sync(0xffffffffu, P[i], last);
+      float lo = __shfl_up_sync(0xffffffffu, P[i], 1);
+      if (lane == 0) lo = 0.0f;
+      cb[i] = hi - lo;  // cbar_j = sum of pbar over subtree(j)
+    }
+    // Rbar_j += sum_children cbar_c o_c^T   (p_c = p_j + R_j o_c)
+#pragma unroll
+    for (int k = 0; k < DP_MAX_CHILD; ++k) {
+      const int ch = M.child[k][lane];
+      const int src = ch >= 0 ? ch : lane;
+      const float t0 = __shfl_sync(0xffffffffu, cb[0], src);
+      const float t1 = __shfl_sync(0xffffffffu, cb[1], src);
+      const float t2 = __shfl_sync(0xffffffffu, cb[2], src);
+      if (ch >= 0) {
+        const float4 co = *reinterpret_cast<const float4*>(M.coff[k][lane]);
+        Rb[0] = fmaf(t0, co.x, Rb[0]); Rb[1] = fmaf(t0, co.y, Rb[1]); Rb[2] = fmaf(t0, co.z, Rb[2]);
+        Rb[3] = fmaf(t1, co.x, Rb[3]); Rb[4] = fmaf(t1, co.y, Rb[4]); Rb[5] = fmaf(t1, co.z, Rb[5]);
+        Rb[6] = fmaf(t2, co.x, Rb[6]); Rb[7] = fmaf(t2, co.y, Rb[7]); Rb[8] = fmaf(t2, co.z, Rb[8]);
+      }
+    }
+    if (is_root) {  // p_0 = R_0 d
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Rb[3 * i + j] = fmaf(cb[i], d[j], Rb[3 * i + j]);
+    }
+    // every joint contributes Rbar_j M_j^T to Rbar_0 (M_0 = I); reduce in quaternion space (4 values, not 9)
+    float X[9], rbp[4];
+    mat_mul_bt(Rb, Mj, X);
+    mat_bar_to_quat(r, X, rbp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rbp[i] += __shfl_xor_sync(0xffffffffu, rbp[i], o);
+    }
+    float qb[4];
+    if (is_root) {
+      const float gc[4] = {g[0], -g[1], -g[2], -g[3]};
+      quat_mul(gc, rbp, qb);  // r = g (x) q_0  ->  q0bar = conj(g) (x) rbar
+    } else {
+      float G[9];
+      mat_mul_at(R0, Rb, G);
+      mat_bar_to_quat(q, G, qb);
+    }
+    // adjoint of q = u / (|u| + 1e-8)
+    const float dt = u[0] * qb[0] + u[1] * qb[1] + u[2] * qb[2] + u[3] * qb[3];
+    const float kk = dt * inv * inv / n;
+    float4 yb;
+    yb.x = (qb[0] * inv - u[0] * kk) * sq.x;
+    yb.y = (qb[1] * inv - u[1] * kk) * sq.y;
+    yb.z = (qb[2] * inv - u[2] * kk) * sq.z;
+    yb.w = (qb[3] * inv - u[3] * kk) * sq.w;
+    if (is_joint) reinterpret_cast<float4*>(ybuf)[lane] = yb;
+    if (is_root) {
+      float db[3];
+      mat_t_vec(R0, cb, db);
+      reinterpret_cast<float4*>(ybuf)[DP_J] = make_float4(db[0] * M.std_d[0], db[1] * M.std_d[1], db[2] * M.std_d[2], 0.0f);
+    }
+    __syncwarp();
+  }
+  return out;
+}
+

@@ -86,7 +86,77 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const SelftestArg
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- clean issue-rate probe: one converged warp, elect.sync lane, 64 fully unrolled MMAs with precomputed descriptors
+template <int KIND, bool TS, int NACC>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int reps, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.0f;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 1) {
+    const uint32_t idesc = KIND ? umma_idesc_bf16(128, N, 0, 0) : umma_idesc_tf32(128, N, 0, 0);
+    const UmmaDescBase da = umma_desc_base(smem_u32(smem), 128, 1024);
+    const UmmaDescBase db = umma_desc_base(smem_u32(smem) + 16384, 128 * (N / 8), 128);
+    long long t0 = 0;
+    uint32_t phase = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (r == 1) t0 = clock64();
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const uint32_t d = tmem + (uint32_t)((i % NACC) * 64);
+          const uint32_t boff = (uint32_t)((i % 8) * 256);
+          if (TS) umma_tf32_ts_c<true>(d, tmem + 384u + 8u * (i % 8), umma_desc_at(db, boff), idesc);
+          else if (KIND) umma_bf16_ss(d, umma_desc_at(da, boff), umma_desc_at(db, boff), idesc, 1u);
+          else umma_tf32_ss(d, umma_desc_at(da, boff), umma_desc_at(db, boff), idesc, 1u);
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    if (elect_one()) *cycles = (clock64() - t0) / ((reps - 1) * 64);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
+
+extern "C" __attribute__((visibility("default"))) long long dp_selftest_umma_rate(int kind, int ts, int nacc, int N) {
+  long long* dc = nullptr;
+  long long h = -1;
+  if (cudaMalloc(&dc, 8) != cudaSuccess) return -1;
+  const size_t smem = 64 * 1024;
+#define DP_RATE(K, T, A)                                                                              \
+  {                                                                                                   \
+    cudaFuncSetAttribute(umma_rate_kernel<K, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    umma_rate_kernel<K, T, A><<<1, 128, smem>>>(N, 9, dc);                                            \
+  }
+  if (kind == 0 && !ts && nacc == 1) DP_RATE(0, false, 1)
+  else if (kind == 0 && !ts) DP_RATE(0, false, 2)
+  else if (kind == 0 && ts && nacc == 1) DP_RATE(0, true, 1)
+  else if (kind == 0 && ts) DP_RATE(0, true, 2)
+  else if (nacc == 1) DP_RATE(1, false, 1)
+  else DP_RATE(1, false, 2)
+#undef DP_RATE
+  if (cudaDeviceSynchronize() == cudaSuccess) cudaMemcpy(&h, dc, 8, cudaMemcpyDeviceToHost);
+  cudaFree(dc);
+  return h;
+}
 
 extern "C" __attribute__((visibility("default"))) int dp_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img,
                                                                         uint32_t b_bytes, uint32_t a_lbo, uint32_t a_sbo,

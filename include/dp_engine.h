@@ -155,6 +155,10 @@ int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const floa
  * current ring buffers, as drag_pose.py:246-290 does when current_index == 0. */
 int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
 
+/* Decoder path the last frame actually ran: 1 = fp32 CUDA-core kernel, 2 = tcgen05 kernel (0 = none yet).
+ * dp_run_params.decoder_path = 0 picks tcgen05 for batches >= 1024 clips and fp32 below. */
+int dp_engine_last_decoder_path(const dp_engine* e);
+
 /* Feed-forward GEMMs of the predictor: 0 = tcgen05 tensor cores, 3xTF32 (default);
  * 1 = fp32 CUDA-core kernel (kept as an on-device cross-check, same results to ~1e-6). */
 int dp_engine_set_predictor_path(dp_engine* e, int path);

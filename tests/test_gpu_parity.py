@@ -32,7 +32,8 @@ def pose_positions(pw, pose_std, root_pos=None):
     return pos.numpy()
 
 
-def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_weights):
+@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
     eng = engine_factory(512)
     worst_rel, worst_f64 = 0.0, 0.0
@@ -45,7 +46,7 @@ def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_w
                 args = dict(global_rot=np.tile(g[f"{tag}_grot"][t, c], (n, 1)), tgt_latent=np.tile(g[f"{tag}_tgt_latent"][t, c], (n, 1)),
                             tgt_pos=np.tile(g["tgt_pos"][t, c], (n, 1, 1)), tgt_rot=np.tile(g["tgt_rot"][t, c], (n, 1, 1, 1)),
                             joints=g["joints"], weights=g["weights"], lambda_rot=1.0, lambda_temporal=0.02)
-                r = eng.eval_gradient(lat, **args)
+                r = eng.eval_gradient(lat, decoder_path=path, **args)
                 ref = g[f"{tag}_grad"][t, c, :n]
                 err = np.linalg.norm(r["grad"] - ref, axis=1)
                 bound = GRAD_REL * np.linalg.norm(ref, axis=1) + GRAD_FLOOR
@@ -65,8 +66,9 @@ def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_w
     print(f"worst grad rel err vs reference fp32 {worst_rel:.2e}, vs float64 truth {worst_f64:.2e}")
 
 
-def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_model, model_npz):
-    """20 random states (like SURVEY's probe): relative error <= 1e-4 with no floor."""
+@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_model, model_npz, path):
+    """20 random states (like SURVEY's probe): relative error <= 1e-4 with no floor, for both decoder paths."""
     rng = np.random.default_rng(11)
     n = 20
     cfg = synthetic.config_6_trackers()
@@ -77,18 +79,19 @@ def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_mode
     tl = rng.standard_normal((n, 24)).astype(np.float32) * 0.3
     eng = engine_factory(512)
     r = eng.eval_gradient(lat, grot, tl, wl["tgt_pos"][0], wl["tgt_rot"][0], wl["joints"], wl["weights"], lambda_rot=1.0,
-                          lambda_temporal=0.02)
+                          lambda_temporal=0.02, decoder_path=path)
     pw64 = port.PortWeights(model_npz, dtype=torch.float64)
     t64 = port.loss_and_grad(pw64, lat, grot, wl["tgt_pos"][0], wl["tgt_rot"][0], tl, wl["joints"], wl["weights"],
                              lambda_rot=1.0, lambda_temporal=0.02, dtype=torch.float64)
     rel = np.linalg.norm(r["grad"] - t64["grad"], axis=1) / np.linalg.norm(t64["grad"], axis=1)
-    print("random-state grad rel err: max %.2e median %.2e" % (rel.max(), np.median(rel)))
+    print("decoder path %d random-state grad rel err: max %.2e median %.2e" % (path, rel.max(), np.median(rel)))
     assert rel.max() <= GRAD_REL
     np.testing.assert_allclose(r["pos"], t64["pos"], atol=2e-6)
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
 @pytest.mark.parametrize("tag,opt,n_frames", [("fixed", FIXED, 2), ("early", EARLY, 6)])
-def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights, tag, opt, n_frames):
+def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights, tag, opt, n_frames, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
     cfg = synthetic.config_6_trackers()
     eng = engine_factory(512)
@@ -98,7 +101,9 @@ def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights
     for t in range(n_frames):
         pose, gpos = eng.run(g["tgt_pos"][t], g["tgt_rot"][t], g["joints"], g["weights"], lambda_rot=1,
                              lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window,
-                             joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight, **opt)
+                             joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight,
+                             decoder_path=path, **opt)
+        assert eng.last_decoder_path() == path
         iters, losses = eng.frame_stats()
         ref_iters = g[f"{tag}_iters"][t]
         if tag == "fixed":
@@ -139,7 +144,8 @@ def test_temporal_predictor_vs_reference(golden_dir, engine_factory):
         assert err <= 2e-5
 
 
-def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory, port_weights):
+@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_frames_3trk.npz"))
     cfg = synthetic.config_3_trackers()
     eng = engine_factory(512)
@@ -149,7 +155,8 @@ def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory
     for t in range(T):
         pose, gpos = eng.run(g["tgt_pos"][t], g["tgt_rot"][t], g["joints_tb"][t], g["weights_tb"][t], n_ee=g["n_ee"][t],
                              lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window,
-                             joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight, **EARLY)
+                             joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight,
+                             decoder_path=path, **EARLY)
         iters, _ = eng.frame_stats()
         dpos = np.abs(pose_positions(port_weights, pose) - pose_positions(port_weights, g["pose"][t])).max()
         dg = np.abs(gpos - g["gpos"][t]).max()
@@ -160,7 +167,8 @@ def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory
     np.testing.assert_allclose(tb[:, :16], g["target_buf"][:, :16], atol=5e-4)
 
 
-def test_batch_256_clips_vs_oracle(engine_factory, pose_model, model_npz, port_weights, temporal_model):
+@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+def test_batch_256_clips_vs_oracle(engine_factory, pose_model, model_npz, port_weights, temporal_model, path):
     """BASELINE config 2: 256 synthetic clips, 6 trackers, against the CPU oracle (batched port)."""
     B, T = 256, 2
     cfg = synthetic.config_6_trackers()
@@ -169,14 +177,15 @@ def test_batch_256_clips_vs_oracle(engine_factory, pose_model, model_npz, port_w
     eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
     ora = port.PortDragPose(port_weights, temporal_model.sd)
     ora.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
-    opt = dict(FIXED, max_iter=40)
+    opt = dict(FIXED, max_iter=40, decoder_path=path)
+    oopt = dict(FIXED, max_iter=40)
     for t in range(T):
         pose, gpos = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], lambda_rot=1,
                              lambda_temporal=cfg.lambda_temporal, temporal_future_window=0,
                              joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight, **opt)
         op, og = ora.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], lambda_rot=1.0,
                          lambda_temporal=cfg.lambda_temporal, temporal_future_window=0, joint_adjustment=cfg.joint_adjustment,
-                         joint_adjustment_weight=cfg.joint_adjustment_weight, **opt)
+                         joint_adjustment_weight=cfg.joint_adjustment_weight, **oopt)
         dpos = np.abs(pose_positions(port_weights, pose) - pose_positions(port_weights, op.numpy())).max()
         dg = np.abs(gpos - og.numpy()).max()
         print(f"256 clips frame {t}: max joint diff {dpos*1e3:.4f} mm, root diff {dg*1e3:.4f} mm")
