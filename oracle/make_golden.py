@@ -259,12 +259,63 @@ def golden_rundrag(ref):
                         tgt_quat=rot, result_pose=res_pose, result_gpos=res_gpos)
 
 
+def golden_eval_bvh(ref, n_frames=48):
+    """Config #1 of BASELINE.json on an excerpt: the evaluation loop of python/src/eval_drag.py:62-224 (the reference's own
+    TestMotionData / from_root_quat / pymotion-fk / DragPose.run calls) on the first frames of example.bvh with
+    config/6_trackers_config.json.  Also writes the BVH excerpt itself (data: CC BY-SA 4.0, LICENSE_data)."""
+    rh.activate()
+    import train
+    from motion_data import TestMotionData
+    from pymotion.ops.forward_kinematics_torch import fk
+    from utils import from_root_quat
+
+    src = open(rh.EXAMPLE_BVH).read().split("\n")
+    m = src.index("MOTION")
+    excerpt = src[: m + 1] + [f"Frames: {n_frames}", src[m + 2]] + src[m + 3 : m + 3 + n_frames]
+    with open(os.path.join(OUT, "example_48f.bvh"), "w") as fh:
+        fh.write("\n".join(excerpt) + "\n")
+    cfg = ref.load_config("6_trackers_config.json")
+    mask = torch.tensor(cfg["mask"])
+    weights = torch.tensor(cfg["weights"], dtype=torch.float32)
+    ds = TestMotionData(train.param, train.scale, "cpu", height_indices=[0, 4, 8, 13, 17, 21])
+    ds.set_means_stds(ref.means, ref.stds)
+    ds.add_motion(ref.offsets_np, ref.pos[:n_frames, 0, :], ref.rots[:n_frames], ref.parents, ref.bvh, "example_48f.bvh")
+    ds.normalize()
+    nm = ds.get_item(0)
+    mask_indices = torch.nonzero(mask).squeeze()
+    weights = weights[mask_indices]
+    drag = ref.new_drag()
+    inp = nm["dqs"].unsqueeze(0).permute(0, 2, 1)
+    gpos, grot, heights = nm["global_pos"], nm["global_rot"], nm["heights"]
+    torch.manual_seed(4242)
+    drag.set_initial_pose(torch.tile(inp[..., 0:1], (1, 1, 1)), gpos[..., 0:1], grot[..., 0:1], heights[0])
+    latent0 = drag.latent.detach().numpy()[0].copy()
+    poses, gps, its = [], [], []
+    rec = Recorder(drag)
+    for i in range(n_frames):
+        tq = inp[..., i : i + 1].clone().reshape((1, -1, 8, 1))[..., :4, :].flatten(1, 2)
+        tq = tq * drag.stds_dqs + drag.means_dqs
+        tq[:, :4, :] = grot[..., i : i + 1]
+        loc = from_root_quat(tq.permute(0, 2, 1).reshape((1, 1, -1, 4)), drag.parents)
+        disp = (gpos[..., i : i + 1] - drag.current_global_pos.detach().clone()).permute(0, 2, 1)
+        p, R = fk(loc, disp, ref.offsets, drag.parents)
+        pose, gp = drag.run(target_ee_pos=p[0, 0, mask_indices, :], target_ee_rot=R[0, 0, mask_indices, :, :], mask_joints=mask_indices,
+                            weights_joints=weights, offsets=ref.offsets, stop_eps_pos=0.01 * 0.01, stop_eps_rot=0.01, max_iter=100,
+                            min_loss_incr=0.00001, learning_rate=1e-2, lambda_rot=1, lambda_temporal=cfg["lambda_temporal"],
+                            temporal_future_window=cfg["temporal_future_window"], height_indices=[0, 4, 8, 13, 17, 21],
+                            joint_adjustment_indices=tuple(cfg["joint_adjustment_indices"]), joint_adjustment_weight=cfg["joint_adjustment_weight"])
+        poses.append(pose.detach().numpy().copy())
+        gps.append(gp.detach().numpy().copy())
+        its.append(len(rec.take()))
+    np.savez_compressed(os.path.join(OUT, "ref_eval_bvh.npz"), latent0=latent0, pose=np.stack(poses), gpos=np.stack(gps), iters=np.asarray(its, np.int32))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = build()
     pm = save_model_fixture(ref)
-    which = sys.argv[1:] or ["trace", "frames3", "temporal", "rundrag"]
+    which = sys.argv[1:] or ["trace", "frames3", "temporal", "rundrag", "evalbvh"]
     if "trace" in which:
         golden_iter_traces(ref, pm)
     if "frames3" in which:
@@ -273,4 +324,6 @@ if __name__ == "__main__":
         golden_temporal(ref)
     if "rundrag" in which:
         golden_rundrag(ref)
+    if "evalbvh" in which:
+        golden_eval_bvh(ref)
     print("golden fixtures written to", OUT)
