@@ -174,6 +174,28 @@ __device__ __forceinline__ void mat_t_vec(const float a[9], const float v[3], fl
   for (int i = 0; i < 3; ++i) r[i] = a[i] * v[0] + a[3 + i] * v[1] + a[6 + i] * v[2];
 }
 
+// fast reciprocal / square root (MUFU, <= 2 ulp): used where the reference's own fp32 noise is orders of magnitude larger
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sum of 4 per-lane values over the warp with 6 shuffles instead of 20: halve the value set while halving the lane set.
+// Afterwards lane (8*c) holds the total of component c (c = 0..3); other lanes hold totals of their own component.
+__device__ __forceinline__ float warp_sum4_scatter(const float (&a)[4], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8;
+  float k0 = b4 ? a[2] : a[0], k1 = b4 ? a[3] : a[1];
+  k0 += __shfl_xor_sync(0xffffffffu, b4 ? a[0] : a[2], 16);
+  k1 += __shfl_xor_sync(0xffffffffu, b4 ? a[1] : a[3], 16);
+  float k = b3 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

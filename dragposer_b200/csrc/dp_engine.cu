@@ -193,6 +193,7 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     I.height_slot[j] = -1;
   }
   for (int s = 0; s < DP_NH; ++s) I.height_slot[height_joints[s]] = s;
+  int max_depth = 0, max_children = 0;
   for (int j = 0; j < DP_J; ++j) {
     I.parent[j] = par[j];
     I.last[j] = last[j];
@@ -203,6 +204,8 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
       I.child[nchild[p]][p] = j;
       for (int i = 0; i < 3; ++i) I.coff[nchild[p]][p][i] = m->offsets[3 * j + i];
       ++nchild[p];
+      if (nchild[p] > max_children) max_children = nchild[p];
+      if (depth[j] > max_depth) max_depth = depth[j];
       int a = j;
       for (int r = 0, dist = 1; r < DP_JUMP_ROUNDS; ++r, dist <<= 1) {
         // ancestor at distance 2^r, if the chain is that long
@@ -215,6 +218,9 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
       (void)a;
     }
   }
+  I.pad[0] = 0;
+  while ((1 << I.pad[0]) <= max_depth) ++I.pad[0];  // pointer-jumping rounds: smallest r with 2^r > max depth
+  I.pad[1] = max_children;
   CK(cudaMemcpy(e->d_model, raw.data(), raw.size(), cudaMemcpyHostToDevice));
   {  // tcgen05 image: bf16 split pieces of the same matrices + the same statistics / skeleton tables
     std::vector<unsigned char> raw_tc(sizeof(DpModelImageTC), 0);
@@ -252,6 +258,7 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     memcpy(T.off, I.off, sizeof(I.off)); memcpy(T.coff, I.coff, sizeof(I.coff)); memcpy(T.child, I.child, sizeof(I.child));
     memcpy(T.jump, I.jump, sizeof(I.jump)); memcpy(T.parent, I.parent, sizeof(I.parent)); memcpy(T.last, I.last, sizeof(I.last));
     memcpy(T.height_slot, I.height_slot, sizeof(I.height_slot));
+    memcpy(T.pad, I.pad, sizeof(I.pad));
     CK(cudaMemcpy(e->d_model_tc, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
   }
   e->has_pose = true;
@@ -320,7 +327,7 @@ static int ensure_adam(dp_engine* e, int max_iter, float lr) {
   const double lrd = (double)lr;
   for (int k = 1; k <= max_iter; ++k) {
     tab[k - 1] = (float)(lrd / (1.0 - std::pow(0.9, (double)k)));
-    tab[max_iter + k - 1] = (float)std::pow(1.0 - std::pow(0.999, (double)k), 0.5);
+    tab[max_iter + k - 1] = (float)(1.0 / std::pow(1.0 - std::pow(0.999, (double)k), 0.5));  // kernels multiply by the reciprocal
   }
   if (e->adam_iters != max_iter) {
     cudaFree(e->d_adam);

@@ -33,8 +33,8 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
   const float4 sq = is_joint ? reinterpret_cast<const float4*>(M.std_q)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   float u[4] = {fmaf(yv.x, sq.x, mq.x), fmaf(yv.y, sq.y, mq.y), fmaf(yv.z, sq.z, mq.z), fmaf(yv.w, sq.w, mq.w)};
-  const float n = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
-  const float inv = 1.0f / (n + 1e-8f);
+  const float n = fast_sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
+  const float inv = fast_rcp(n + 1e-8f);
   float q[4] = {u[0] * inv, u[1] * inv, u[2] * inv, u[3] * inv};
   float q0[4];
 #pragma unroll
@@ -63,7 +63,10 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
   mat_vec(Rp, ov, p);
   if (is_root) { p[0] = p0[0]; p[1] = p0[1]; p[2] = p0[2]; }
 #pragma unroll
+  const int n_jump = M.pad[0], n_child = M.pad[1];  // rounds this skeleton needs (3 and 3 for the 22-joint body)
+#pragma unroll
   for (int rd = 0; rd < DP_JUMP_ROUNDS; ++rd) {
+    if (rd >= n_jump) break;
     const int a = M.jump[rd][lane];
     const int src = a >= 0 ? a : lane;
     const float t0 = __shfl_sync(0xffffffffu, p[0], src);
@@ -83,10 +86,14 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
   for (int i = 0; i < 9; ++i) sr = fmaf(eR[i], eR[i], sr);
   sp *= wp;
   sr *= wr;
+  {  // two warp sums with 6 shuffles: lanes 0-15 finish the position sum, lanes 16-31 the rotation sum, then swap
+    const bool hi = lane & 16;
+    float k = (hi ? sr : sp) + __shfl_xor_sync(0xffffffffu, hi ? sp : sr, 16);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sp += __shfl_xor_sync(0xffffffffu, sp, o);
-    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    for (int o = 8; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    const float other = __shfl_xor_sync(0xffffffffu, k, 16);
+    sp = hi ? other : k;
+    sr = hi ? k : other;
   }
   FkOut out;
   out.lp = sp * inv3e;
@@ -125,6 +132,7 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
     // Rbar_j += sum_children cbar_c o_c^T   (p_c = p_j + R_j o_c)
 #pragma unroll
     for (int k = 0; k < DP_MAX_CHILD; ++k) {
+      if (k >= n_child) break;
       const int ch = M.child[k][lane];
       const int src = ch >= 0 ? ch : lane;
       const float t0 = __shfl_sync(0xffffffffu, cb[0], src);
@@ -147,10 +155,12 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
     float X[9], rbp[4];
     mat_mul_bt(Rb, Mj, X);
     mat_bar_to_quat(r, X, rbp);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rbp[i] += __shfl_xor_sync(0xffffffffu, rbp[i], o);
+    {  // only lane 0 needs the four totals: 6-shuffle scatter reduction, then lane 0 collects from lanes 0, 8, 16, 24
+      const float k = warp_sum4_scatter(rbp, lane);
+      rbp[0] = k;
+      rbp[1] = __shfl_sync(0xffffffffu, k, 8);
+      rbp[2] = __shfl_sync(0xffffffffu, k, 16);
+      rbp[3] = __shfl_sync(0xffffffffu, k, 24);
     }
     float qb[4];
     if (is_root) {
@@ -163,7 +173,7 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
     }
     // adjoint of q = u / (|u| + 1e-8)
     const float dt = u[0] * qb[0] + u[1] * qb[1] + u[2] * qb[2] + u[3] * qb[3];
-    const float kk = dt * inv * inv / n;
+    const float kk = dt * inv * inv * fast_rcp(n);
     float4 yb;
     yb.x = (qb[0] * inv - u[0] * kk) * sq.x;
     yb.y = (qb[1] * inv - u[1] * kk) * sq.y;

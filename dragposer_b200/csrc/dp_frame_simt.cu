@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(512, 1) dp_frame_simt_kernel(const __grid_cons
     __syncwarp();
     dense_pairs<CPW, DP_H0, DP_L>(M.W0, nullptr, sb, acc, lane);
     // temporal term, loss bookkeeping, Adam (torch/optim/adam.py single-tensor path)
-    const float step_size = A.adam_tab[it], bc2s = A.adam_tab[A.max_iter + it];
+    const float step_size = A.adam_tab[it], inv_bc2s = A.adam_tab[A.max_iter + it];  // lr/(1-b1^k), 1/sqrt(1-b2^k)
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
       const float dx = z[c].x - tl[c].x, dy = z[c].y - tl[c].y;
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(512, 1) dp_frame_simt_kernel(const __grid_cons
         am[c].y = fmaf(0.1f, gy - am[c].y, am[c].y);
         av[c].x = av[c].x * 0.999f + (0.001f * gx) * gx;
         av[c].y = av[c].y * 0.999f + (0.001f * gy) * gy;
-        z[c].x += (-step_size * am[c].x) / (sqrtf(av[c].x) / bc2s + 1e-8f);
-        z[c].y += (-step_size * am[c].y) / (sqrtf(av[c].y) / bc2s + 1e-8f);
+        z[c].x += __fdividef(-step_size * am[c].x, fmaf(fast_sqrt(av[c].x), inv_bc2s, 1e-8f));
+        z[c].y += __fdividef(-step_size * am[c].y, fmaf(fast_sqrt(av[c].y), inv_bc2s, 1e-8f));
       }
       if (active[c]) {
         lp[c] = nlp[c];
