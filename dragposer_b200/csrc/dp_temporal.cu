@@ -102,25 +102,40 @@ __device__ __forceinline__ void project_feature(const float (*x)[TP_D], int t0, 
   }
 }
 
+template <int MT>
+struct MhaSmem {
+  float xq[MT][TP_D], xkv[MT][TP_D];
+  float q[MT][TP_D], k[MT][TP_D + 1], v[MT][TP_D], o[MT][TP_D];
+  float sc[MT][TP_H][MT + 1];  // attention scores / probabilities
+};
+
+// One CTA per clip; MT (16 or 32) bounds the token counts so that up to 9 CTAs fit on an SM.  Every phase uses all 160
+// threads: projections are register tiled per output feature, the T x H x S score matrix is spread over the CTA.
+template <int MT>
 __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __restrict__ blob, TpAttn A, TpNorm N,
                                                                 const float* __restrict__ xq_g, int T, int q_stride,
                                                                 const float* __restrict__ xkv_g, int S, int kv_stride,
                                                                 float* __restrict__ out_g) {
-  __shared__ __align__(16) float xq[TP_MAXT][TP_D], xkv[TP_MAXT][TP_D];
-  __shared__ __align__(16) float q[TP_MAXT][TP_D], k[TP_MAXT][TP_D + 1], v[TP_MAXT][TP_D], o[TP_MAXT][TP_D];
+  extern __shared__ __align__(16) unsigned char mha_raw[];
+  MhaSmem<MT>& M = *reinterpret_cast<MhaSmem<MT>*>(mha_raw);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float (*xq)[TP_D] = M.xq;
+  float (*xkv)[TP_D] = M.xkv;
+  float (*q)[TP_D] = M.q;
+  float (*k)[TP_D + 1] = M.k;
+  float (*v)[TP_D] = M.v;
+  float (*o)[TP_D] = M.o;
   for (int idx = tid; idx < T * TP_D / 4; idx += MHA_THREADS)
     reinterpret_cast<float4*>(&xq[0][0])[idx] = reinterpret_cast<const float4*>(xq_g + (size_t)b * q_stride * TP_D)[idx];
   for (int idx = tid; idx < S * TP_D / 4; idx += MHA_THREADS)
     reinterpret_cast<float4*>(&xkv[0][0])[idx] = reinterpret_cast<const float4*>(xkv_g + (size_t)b * kv_stride * TP_D)[idx];
   __syncthreads();
   const float* Win = blob + A.w_in;
-  const float* bin = blob + A.b_in;
   if (tid < 3 * TP_D) {  // feature tid of [q | k | v]
     const bool is_q = tid < TP_D;
     const int n_tok = is_q ? T : S;
     const float (*src)[TP_D] = is_q ? xq : xkv;
-    const float bias = bin[tid];
+    const float bias = blob[A.b_in + tid];
     const float scale = is_q ? rsqrtf((float)TP_HD) : 1.0f;
     for (int t0 = 0; t0 < n_tok; t0 += MHA_TT) {
       float acc[MHA_TT];
@@ -136,45 +151,47 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < T * TP_H; idx += MHA_THREADS) {
-    const int t = idx / TP_H, h = idx % TP_H;
-    float sc[TP_MAXT];
-    float mx = -3.0e38f;
-    for (int s = 0; s < S; ++s) {
-      float a = 0.0f;
+  for (int idx = tid; idx < T * TP_H * S; idx += MHA_THREADS) {  // scores
+    const int s = idx % S, h = (idx / S) % TP_H, t = idx / (S * TP_H);
+    float a = 0.0f;
 #pragma unroll
-      for (int d = 0; d < TP_HD; ++d) a = fmaf(q[t][h * TP_HD + d], k[s][h * TP_HD + d], a);
-      sc[s] = a;
-      mx = fmaxf(mx, a);
-    }
-    float den = 0.0f;
-    for (int s = 0; s < S; ++s) {
-      sc[s] = expf(sc[s] - mx);
-      den += sc[s];
-    }
-    const float inv = 1.0f / den;
-#pragma unroll
-    for (int d = 0; d < TP_HD; ++d) {
-      float a = 0.0f;
-      for (int s = 0; s < S; ++s) a = fmaf(sc[s], v[s][h * TP_HD + d], a);
-      o[t][h * TP_HD + d] = a * inv;
-    }
+    for (int d = 0; d < TP_HD; ++d) a = fmaf(q[t][h * TP_HD + d], k[s][h * TP_HD + d], a);
+    M.sc[t][h][s] = a;
   }
   __syncthreads();
-  // output projection + residual, register tiled the same way (48 features x up to 3 token groups), then LayerNorm per token
-  const float* Wo = blob + A.w_out;
-  const float* bo = blob + A.b_out;
-  {
-    const int f = tid % TP_D, grp = tid / TP_D;  // 3 groups of 48 threads take interleaved token blocks
+  for (int idx = tid; idx < T * TP_H; idx += MHA_THREADS) {  // softmax rows (max-subtracted, like torch)
+    float* row = M.sc[idx / TP_H][idx % TP_H];
+    float mx = -3.0e38f;
+    for (int s = 0; s < S; ++s) mx = fmaxf(mx, row[s]);
+    float den = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      const float e = expf(row[s] - mx);
+      row[s] = e;
+      den += e;
+    }
+    const float inv = 1.0f / den;
+    for (int s = 0; s < S; ++s) row[s] *= inv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < T * TP_D; idx += MHA_THREADS) {  // weighted values
+    const int f = idx % TP_D, t = idx / TP_D;
+    const float* row = M.sc[t][f / TP_HD];
+    float a = 0.0f;
+    for (int s = 0; s < S; ++s) a = fmaf(row[s], v[s][f], a);
+    o[t][f] = a;
+  }
+  __syncthreads();
+  {  // output projection + residual, register tiled (48 features x 3 token groups); q is dead: reuse it for the sums
+    const int f = tid % TP_D, grp = tid / TP_D;
     if (grp < 3) {
       const int per = (T + 2) / 3;
       const int t0 = grp * per, nt = max(0, min(per, T - t0));
       if (nt > 0) {
-        float acc[11];  // ceil(TP_MAXT / 3)
-        project_feature<11>(o, t0, nt, Wo, TP_D, f, bo[f], acc);
+        float acc[11];  // ceil(32 / 3)
+        project_feature<11>(o, t0, nt, blob + A.w_out, TP_D, f, blob[A.b_out + f], acc);
 #pragma unroll
         for (int t = 0; t < 11; ++t)
-          if (t < nt) q[t0 + t][f] = acc[t] + xq[t0 + t][f];  // q is dead: reuse it for the residual sums
+          if (t < nt) q[t0 + t][f] = acc[t] + xq[t0 + t][f];
       }
     }
   }
@@ -187,6 +204,19 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
     dst[lane] = r0;
     if (has1) dst[lane + 32] = r1;
   }
+}
+
+static cudaError_t launch_mha(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
+                              int S, int kv_stride, float* out, int B, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tp_mha_ln_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MhaSmem<32>));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (T <= 16 && S <= 16) tp_mha_ln_kernel<16><<<B, MHA_THREADS, sizeof(MhaSmem<16>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out);
+  else tp_mha_ln_kernel<32><<<B, MHA_THREADS, sizeof(MhaSmem<32>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out);
+  return cudaGetLastError();
 }
 
 // ---- out = LN(x + W2 relu(W1 x + b1) + b2) [then an optional second LayerNorm]; 64 tokens per CTA.
@@ -318,13 +348,15 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
                             long long* launches) {
   cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
   if (err != cudaSuccess) return err;
+
   tp_embed_kernel<<<B, 128, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
   ++*launches;
   float* e = w.enc;
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
   for (int l = 0; l < TP_NENC; ++l) {
-    tp_mha_ln_kernel<<<B, MHA_THREADS, 0, st>>>(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2);
+    err = launch_mha(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2, B, st);
+    if (err != cudaSuccess) return err;
     if (fftiles) {
       err = dp_ff_tc_launch(fftiles + (size_t)l * FFT_LAYER_BYTES, blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm, l == TP_NENC - 1, e2,
                             enc_rows, TP_S, TP_S, e, st);
@@ -343,8 +375,10 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     float* d2 = w.dec2;
     const int rows = B * T;
     for (int l = 0; l < TP_NDEC; ++l) {
-      tp_mha_ln_kernel<<<B, MHA_THREADS, 0, st>>>(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2);
-      tp_mha_ln_kernel<<<B, MHA_THREADS, 0, st>>>(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d);
+      err = launch_mha(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2, B, st);
+      if (err != cudaSuccess) return err;
+      err = launch_mha(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d, B, st);
+      if (err != cudaSuccess) return err;
       if (fftiles) {
         err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
                               l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, st);

@@ -14,6 +14,7 @@
 // chunk is ONE contiguous bulk-TMA copy (cp.async.bulk); chunks are double buffered and the
 // MMA of chunk c+1 is issued behind MMA2 of chunk c so the tensor pipe stays busy while the
 // 8 epilogue warps convert the next H tile.
+#include <cstdlib>
 #include <cstring>
 
 #include "dp_internal.h"
@@ -32,7 +33,7 @@ static_assert(kPart1 + kPart2 == FFT_CHUNK_BYTES, "chunk size");
 // shared-memory operand geometry (bytes), see dp_umma.cuh
 constexpr uint32_t kW1_LBO = 128 * (kHC / 8), kW2_LBO = 128 * (TP_D / 8), kB_SBO = 128;
 
-constexpr int kW1Stages = 4, kW2Stages = 3;
+constexpr int kW1Stages = 4, kW2Stages = 4;
 struct Smem {
   unsigned char w1[kW1Stages][kPart1];
   unsigned char w2[kW2Stages][kPart2];
@@ -102,7 +103,7 @@ constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 32;  // 8 epilogue war
 
 __global__ void __launch_bounds__(kThreads, 1)
 tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2,
-                const float* __restrict__ x_g, int n_rows, int T, int row_stride, float* __restrict__ out_g) {
+                const float* __restrict__ x_g, int n_rows, int T, int row_stride, float* __restrict__ out_g, int dbg) {
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& S = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -119,7 +120,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  if (warp == 8 && elect_one()) {  // weight pipeline prologue (bulk TMA): W1 chunks 0..3, W2 chunks 0..2
+  if (warp == 8 && elect_one()) {  // weight pipeline prologue (bulk TMA): W1 chunks 0..3, W2 chunks 0..3
     for (int c = 0; c < kW1Stages; ++c) load_w1(S, wtiles, c);
     for (int c = 0; c < kW2Stages; ++c) load_w2(S, wtiles, c);
   }
@@ -165,16 +166,20 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
       mbar_wait(&S.hready[b], (c >> 1) & 1);  // all epilogue threads converted H(c) (and finished chunk c-1)
       tc_fence_after();
       if (elect_one()) {
-        if (c >= 1 && c + 3 < kChunks) load_w1(S, wtiles, c + 3);   // stage of chunk c-1: MMA1(c-1) retired, b1(c-1) consumed
-        if (c >= 2 && c + 1 < kChunks) load_w2(S, wtiles, c + 1);   // stage of chunk c-2: MMA2(c-2) retired
+        // refill two chunks ahead of use: stage of chunk c (MMA1(c) retired, b1(c) consumed by the epilogue) and stage of
+        // chunk c-2 (MMA2(c-2) retired -- the epilogue could only signal after seeing the commit that covered it)
+        if (c + kW1Stages < kChunks) load_w1(S, wtiles, c + kW1Stages);
+        if (c >= 2 && c - 2 + kW2Stages < kChunks) load_w2(S, wtiles, c - 2 + kW2Stages);
       }
       __syncwarp();
       mbar_wait(&S.w2full[c % kW2Stages], (c / kW2Stages) & 1);
       if (c + 2 < kChunks) mbar_wait(&S.w1full[(c + 2) % kW1Stages], ((c + 2) / kW1Stages) & 1);
       if (elect_one()) {
-        if (c == 0) issue_mma2<true>(S, c % kW2Stages, tmem, hcol, lcol);
-        else issue_mma2<false>(S, c % kW2Stages, tmem, hcol, lcol);
-        if (c + 2 < kChunks) issue_mma1(S, (c + 2) % kW1Stages, tmem, hcol);
+        if (!(dbg & 2)) {
+          if (c == 0) issue_mma2<true>(S, c % kW2Stages, tmem, hcol, lcol);
+          else issue_mma2<false>(S, c % kW2Stages, tmem, hcol, lcol);
+        }
+        if (c + 2 < kChunks && !(dbg & 1)) issue_mma1(S, (c + 2) % kW1Stages, tmem, hcol);
         umma_commit(&S.hfull[b]);
       }
       __syncwarp();
@@ -188,15 +193,14 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
       tc_fence_after();
       mbar_wait(&S.w1full[c % kW1Stages], (c / kW1Stages) & 1);  // acquire the TMA-written b1 slice
       const float* b1 = reinterpret_cast<const float*>(S.w1[c % kW1Stages] + 2 * kW1Bytes) + chalf * 32;
-#pragma unroll
-      for (int j0 = 0; j0 < 32; j0 += 16) {
-        float v[16], lo[16];
-        tmem_ld16(tmem + lane_base + hcol + (uint32_t)(chalf * 32 + j0), v);
+      if (!(dbg & 4)) {  // one 32-column load, one wait, all the math, two 32-column stores, one wait
+        float v[32], lo[32];
+        tmem_ld32(tmem + lane_base + hcol + (uint32_t)(chalf * 32), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) split_tf32(fmaxf(v[j] + b1[j0 + j], 0.f), v[j], lo[j]);
-        tmem_st16(tmem + lane_base + hcol + (uint32_t)(chalf * 32 + j0), v);
-        tmem_st16(tmem + lane_base + lcol + (uint32_t)(chalf * 32 + j0), lo);
+        for (int j = 0; j < 32; ++j) split_tf32(fmaxf(v[j] + b1[j], 0.f), v[j], lo[j]);
+        tmem_st32(tmem + lane_base + hcol + (uint32_t)(chalf * 32), v);
+        tmem_st32(tmem + lane_base + lcol + (uint32_t)(chalf * 32), lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -285,6 +289,7 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wtiles, const float* blob, cons
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  tp_ff_tc_kernel<<<(n_rows + kTM - 1) / kTM, kThreads, smem, st>>>(wtiles, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out);
+  static int dbg = getenv("DP_FF_DBG") ? atoi(getenv("DP_FF_DBG")) : 0;
+  tp_ff_tc_kernel<<<(n_rows + kTM - 1) / kTM, kThreads, smem, st>>>(wtiles, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, dbg);
   return cudaGetLastError();
 }
