@@ -112,6 +112,7 @@ struct DpFrameArgs {
   float* out_losses;  // (B,3)
   float* trace;       // (B,trace_iters,52) or null
   int trace_iters;
+  int clips_per_cta;  // tcgen05 kernel: real clips per 32-column tile (<= 32), chosen so that the grid covers every SM
   // teacher-forced evaluation (dp_engine_eval_gradient)
   int eval_only;
   float* eval_grad;   // (B,24)

@@ -403,7 +403,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   // auto: tensor-core decoder once a batch fills a fair share of the SMs with 32-clip tiles; the fp32 warp-per-clip
   // kernel is the low-latency path for small batches (B = 1 streaming)
   const bool use_tc = p->decoder_path == 2 || (p->decoder_path == 0 && e->n_clips >= 1024);
-  if (use_tc) CK(dp_frame_tc_launch(a, st));
+  if (use_tc) CK(dp_frame_tc_launch(a, e->num_sms, st));
   else CK(dp_frame_simt_launch(a, e->num_sms, st));
   e->last_path = use_tc ? 2 : 1;
   ++e->launches;
@@ -551,7 +551,7 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   a.eps_pos = -1.0; a.eps_rot = -1.0; a.min_incr = -std::numeric_limits<double>::infinity();
   a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
   a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
-  if (decoder_path == 2) CK(dp_frame_tc_launch(a, e->stream));
+  if (decoder_path == 2) CK(dp_frame_tc_launch(a, e->num_sms, e->stream));
   else CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
   ++e->launches;
   CK(cudaStreamSynchronize(e->stream));

@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
   }
   Ctx ctx{&S, S.tmem_base, warp, lane, 0u};
   constexpr int CPW = NC / kWarps;  // 2 clips per warp in the per-clip phases
-  const int n0 = warp * CPW;        // local clip index of this warp's first clip
-  const int clip0 = blockIdx.x * NC + n0;
+  const int n0 = warp * CPW;        // local clip index (tile column) of this warp's first clip
+  const int clip0 = blockIdx.x * A.clips_per_cta + n0;
 
   // ---- per-clip frame inputs (same as the fp32 kernel)
   bool valid[CPW];
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
 #pragma unroll
   for (int c = 0; c < CPW; ++c) {
     const int clip = clip0 + c;
-    valid[c] = clip < A.n_clips;
+    valid[c] = clip < A.n_clips && n0 + c < A.clips_per_cta;
     const int cc = valid[c] ? clip : 0;
     const int ne = A.n_ee ? A.n_ee[cc] : A.ee_stride;
     inv3e[c] = 1.0f / (3.0f * (float)ne);
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
 
 }  // namespace
 
-cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, cudaStream_t stream) {
+cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(SmemTC) + 1024;
   if (!configured) {
@@ -480,7 +480,13 @@ cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int grid = (args.n_clips + NC - 1) / NC;
-  dp_frame_tc_kernel<<<grid, kWarps * 32, smem, stream>>>(args);
+  // 4096 clips: 28 real clips per 32-column tile -> 147 CTAs, one per SM, instead of 128 CTAs of 32
+  DpFrameArgs a = args;
+  int cpc = (args.n_clips + num_sms - 1) / num_sms;
+  cpc = cpc < 1 ? 1 : (cpc > NC ? NC : cpc);
+  if (args.n_clips > num_sms * NC) cpc = NC;  // several waves anyway: use full tiles
+  a.clips_per_cta = cpc;
+  const int grid = (args.n_clips + cpc - 1) / cpc;
+  dp_frame_tc_kernel<<<grid, kWarps * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
