@@ -280,8 +280,9 @@ def run_ours(args):
             "metric": "clip-frames/sec (fixed 100 opt iters)", "value": value, "unit": "clip-frames/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, cfg, n_total),
-            "roofline": {"bound": "tensor", "kernel": ("dp_frame_tc_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, bf16x3 split)"
-                                                       if eng.last_decoder_path() == 2 else
+            "roofline": {"bound": "tensor", "kernel": ("dp_frame_tc_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, %s split)"
+                                                       % ("fp16x2" if eng.last_decoder_path() == 3 else "bf16x3")
+                                                       if eng.last_decoder_path() >= 2 else
                                                        "dp_frame_simt_kernel (persistent per-frame loop; fp32 CUDA-core decoder)"),
                          "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf32_peak,
                          "traffic": None, "peak_source": which, "kernel_ms_per_launch": frame_ms,
@@ -309,7 +310,7 @@ def main():
     ap.add_argument("--clips", type=int, default=4096, help="clips per GPU (weak scaling)")
     ap.add_argument("--trackers", default="6", choices=["6", "3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decoder-path", type=int, default=0, choices=[0, 1, 2], help="0 auto, 1 fp32 CUDA-core decoder, 2 tcgen05 decoder")
+    ap.add_argument("--decoder-path", type=int, default=0, choices=[0, 1, 2, 3], help="0 auto, 1 fp32 CUDA-core decoder, 2 tcgen05 bf16x3, 3 tcgen05 fp16x2")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

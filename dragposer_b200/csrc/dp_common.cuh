@@ -77,7 +77,8 @@ static_assert(sizeof(DpModelImageTC) % 16 == 0, "bulk copy needs a multiple of 1
 
 struct DpFrameArgs {
   const DpModelImage* model;
-  const DpModelImageTC* model_tc;
+  const DpModelImageTC* model_tc;    // bf16x3 pieces
+  const DpModelImageTC* model_tc16;  // fp16x2 pieces of 16 W (w[2] unused)
   int n_clips;
   // carried state (HBM)
   float* latent;        // (B,24) latent after the last Adam step (seeds the next frame)

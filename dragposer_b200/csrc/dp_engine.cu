@@ -4,6 +4,7 @@
 // clip's rows with coalesced, vectorised accesses), the model images, pinned staging
 // buffers for the host-pointer entry points, and launches the persistent frame kernel
 // (and, when the reference would, the temporal predictor first).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -16,6 +17,7 @@
 #include "../../include/dp_engine.h"
 #include "dp_internal.h"
 
+#define DP_AUTO_TC_PATH 3  // tensor-core variant picked by decoder_path = 0 for batches
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -32,6 +34,7 @@ struct dp_engine {
   bool has_pose = false, has_temporal = false;
   DpModelImage* d_model = nullptr;
   DpModelImageTC* d_model_tc = nullptr;
+  DpModelImageTC* d_model_tc16 = nullptr;
   float* d_tblob = nullptr;
   unsigned char* d_fftiles = nullptr;  // pre-tiled 3xTF32 FF weights of the 6 predictor layers
   int predictor_path = 0;              // 0 = tcgen05 FF (default), 1 = fp32 CUDA-core FF
@@ -90,6 +93,7 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&e->d_model, sizeof(DpModelImage)));
   CK(cudaMalloc(&e->d_model_tc, sizeof(DpModelImageTC)));
+  CK(cudaMalloc(&e->d_model_tc16, sizeof(DpModelImageTC)));
   CK(cudaMalloc(&e->d_latent, B * DP_L * 4));
   CK(cudaMalloc(&e->d_gpos, B * 3 * 4));
   CK(cudaMalloc(&e->d_grot, B * 4 * 4));
@@ -128,7 +132,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_stage(e);
-  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam);
@@ -260,6 +264,22 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     memcpy(T.height_slot, I.height_slot, sizeof(I.height_slot));
     memcpy(T.pad, I.pad, sizeof(I.pad));
     CK(cudaMemcpy(e->d_model_tc, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
+    // fp16x2 variant: two fp16 pieces of 16 W in the same layout (third piece unused)
+    memset(T.w, 0, sizeof(T.w));
+    for (int l = 0; l < 3; ++l) {
+      const int K = dims[l], N = dims[l + 1];
+      for (int o = 0; o < N; ++o)
+        for (int i = 0; i < K; ++i) {
+          float r = 16.0f * A[l][o * K + i];
+          const uint32_t at = woff[l] + (o / 8) * 128 * (kin[l] / 8) + (i / 8) * 128 + (o % 8) * 16 + (i % 8) * 2;
+          for (int p = 0; p < 2; ++p) {
+            const __half h = __float2half_rn(r);
+            memcpy(&T.w[p][at], &h, 2);
+            r -= __half2float(h);
+          }
+        }
+    }
+    CK(cudaMemcpy(e->d_model_tc16, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
   }
   e->has_pose = true;
   return DP_OK;
@@ -351,7 +371,8 @@ static int check_params(const dp_engine* e, const dp_run_params* p, int ee_strid
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
   if (p->joint_adjust_joint >= DP_JOINTS || (p->joint_adjust_joint >= 0 && (p->joint_adjust_slot < 0 || p->joint_adjust_slot >= ee_stride)))
     return fail(DP_ERR_ARG, "joint adjustment indices out of range");
-  if (p->decoder_path < 0 || p->decoder_path > 2) return fail(DP_ERR_ARG, "decoder_path must be 0 (auto), 1 (fp32) or 2 (tcgen05)");
+  if (p->decoder_path < 0 || p->decoder_path > 3)
+    return fail(DP_ERR_ARG, "decoder_path must be 0 (auto), 1 (fp32), 2 (tcgen05 bf16x3) or 3 (tcgen05 fp16x2)");
   return DP_OK;
 }
 
@@ -384,6 +405,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   DpFrameArgs a{};
   a.model = e->d_model;
   a.model_tc = e->d_model_tc;
+  a.model_tc16 = e->d_model_tc16;
   a.n_clips = e->n_clips;
   a.latent = e->d_latent; a.gpos = e->d_gpos; a.grot = e->d_grot;
   a.latent_buf = e->d_latent_buf; a.disp_buf = e->d_disp_buf; a.height_buf = e->d_height_buf;
@@ -402,10 +424,10 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   if (e->profiling) CK(cudaEventRecord(ev[1], st));
   // auto: tensor-core decoder once a batch fills a fair share of the SMs with 32-clip tiles; the fp32 warp-per-clip
   // kernel is the low-latency path for small batches (B = 1 streaming)
-  const bool use_tc = p->decoder_path == 2 || (p->decoder_path == 0 && e->n_clips >= 1024);
-  if (use_tc) CK(dp_frame_tc_launch(a, e->num_sms, st));
+  const int path = p->decoder_path ? p->decoder_path : (e->n_clips >= 1024 ? DP_AUTO_TC_PATH : 1);
+  if (path >= 2) CK(dp_frame_tc_launch(a, e->num_sms, path == 3, st));
   else CK(dp_frame_simt_launch(a, e->num_sms, st));
-  e->last_path = use_tc ? 2 : 1;
+  e->last_path = path;
   ++e->launches;
   if (e->profiling) {
     CK(cudaEventRecord(ev[2], st));
@@ -544,14 +566,14 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   CK(cudaMemcpy(d_tr, tgt_rot, N * S * 36, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_adam, 0, 8));
   DpFrameArgs a{};
-  a.model = e->d_model; a.model_tc = e->d_model_tc; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
+  a.model = e->d_model; a.model_tc = e->d_model_tc; a.model_tc16 = e->d_model_tc16; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
   a.target_buf = d_t; a.target_rows = 1; a.target_index = 0;
   a.n_ee = d_ne; a.joints = d_j; a.weights = d_w; a.shared_trackers = shared; a.tgt_pos = d_tp; a.tgt_rot = d_tr;
   a.ee_stride = ee_stride;
   a.eps_pos = -1.0; a.eps_rot = -1.0; a.min_incr = -std::numeric_limits<double>::infinity();
   a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
   a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
-  if (decoder_path == 2) CK(dp_frame_tc_launch(a, e->num_sms, e->stream));
+  if (decoder_path >= 2) CK(dp_frame_tc_launch(a, e->num_sms, decoder_path == 3, e->stream));
   else CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
   ++e->launches;
   CK(cudaStreamSynchronize(e->stream));

@@ -62,7 +62,6 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
   float p[3];
   mat_vec(Rp, ov, p);
   if (is_root) { p[0] = p0[0]; p[1] = p0[1]; p[2] = p0[2]; }
-#pragma unroll
   const int n_jump = M.pad[0], n_child = M.pad[1];  // rounds this skeleton needs (3 and 3 for the 22-joint body)
 #pragma unroll
   for (int rd = 0; rd < DP_JUMP_ROUNDS; ++rd) {

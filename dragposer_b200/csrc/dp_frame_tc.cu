@@ -8,12 +8,12 @@
 //
 // * transposed mapping: the WEIGHTS are the 128-row A operand, the CTA's 32 clips are the N dimension, so
 //   4096 clips occupy 128 SMs (clips-as-M would fill only 32).
-// * precision: bf16 split products.  x = x1 + x2 (two bf16 pieces, 16 mantissa bits), products
-//   W1.X2 + W2.X1 + W1.X1 accumulated in fp32: measured 5e-6 relative per GEMM on B200 (plain TF32: 7.7e-4,
-//   which breaks the 1e-4 gradient bar); kTerms = 6 adds the third piece (1.3e-7, better than an fp32 GEMM).
-//   bf16 rather than tf32 because kind::tf32 produces zeros for MN-major operands in the no-swizzle layout
-//   (measured) while kind::f16 accepts them: ONE weight image serves the forward GEMM (A K-major) and the
-//   transposed backward GEMM (A MN-major), 42 KB instead of 155 KB of shared memory.
+// * precision: split products on kind::f16 (see PREC below): fp16x2 (default) or bf16x3, both ~fp32-exact
+//   (gradient 2.5e-6 / 3.0e-6 relative vs 1.8e-6 for the fp32 kernel; plain TF32 would be 1.8e-3 and bf16x2
+//   1e-4 -- both break the 1e-4 bar).  kind::f16 rather than kind::tf32 because tf32 produces zeros for
+//   MN-major operands in the no-swizzle layout (measured) while f16/bf16 accept them: ONE weight image
+//   serves the forward GEMM (A K-major) and the transposed backward GEMM (A MN-major), 42 KB instead of
+//   155 KB of shared memory.
 // * activations never leave the SM: epilogue warps read the accumulator with tcgen05.ld (lane == feature),
 //   apply bias / LeakyReLU (slope bits stay in registers for the backward pass), split to bf16 pieces and
 //   write the next layer's B operand (MN-major image, one STS.128 per 8 clips).
@@ -32,7 +32,13 @@ constexpr int kIssueWarp = 8;
 constexpr uint32_t kB_LBO = 128 * (NC / 8);  // activation image: K 8-groups 512 B apart, clip 8-groups 128 B apart
 constexpr uint32_t kB_SBO = 128;
 constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // per bf16 piece
-constexpr int kPieces = 3;        // x = x1 + x2 + x3; six products W1X1 W1X2 W2X1 W1X3 W2X2 W3X1 (fp32-exact to 1.3e-7)
+constexpr int kPieces = 3;        // buffers are sized for three pieces
+// PREC 0: bf16x3 -- x = x1 + x2 + x3 (bf16), six products (3,1)(2,2)(1,3)(2,1)(1,2)(1,1): 1.3e-7 relative per GEMM.
+// PREC 1: fp16x2 -- x = x1 + x2 (fp16, 22 mantissa bits), three products (2,1)(1,2)(1,1): ~5e-7 relative per GEMM at half the
+//         tensor and epilogue work.  fp16's narrow exponent is handled by exact power-of-two scalings: the weight image stores
+//         16 W (undone in every epilogue), and the backward pass carries dL/dy scaled per clip so that its largest component
+//         is in [16, 32) (undone when dL/dz is written); forward activations (|a| < 2^6 here) need no scaling.
+constexpr float kWScale = 16.0f;
 
 struct SmemTC {
   DpModelImageTC M;
@@ -40,13 +46,14 @@ struct SmemTC {
   __align__(16) unsigned char pong[kPieces][kPongBytes];  // [piece]  a0 (40) / dL/dy (92) / dL/dh0 (40)
   __align__(16) float ybuf[NC][96];                 // y, then dL/dy in place (fp32, one row per clip)
   float zgrad[NC][25];                              // dL/dz from the decoder (fp32)
+  float bscale[NC];                                 // fp16 path: 1 / (per-clip power-of-two scale of dL/dy)
   __align__(16) ClipTrackers trk[NC][32];
   uint64_t bar_w, bar_mma;
   uint32_t tmem_base;
 };
 
 template <bool ACC>
-__device__ __forceinline__ void umma_bf16_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+__device__ __forceinline__ void umma_f16_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
   if (ACC)
     asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
                  "l"(a_desc), "l"(b_desc), "r"(idesc));
@@ -57,15 +64,34 @@ __device__ __forceinline__ void umma_bf16_c(uint32_t d_tmem, uint64_t a_desc, ui
 
 // layer geometry (DpModelImageTC): input width padded to 16, output rows padded to 16, both zero filled
 template <int L> struct Lay;
-template <> struct Lay<0> { static constexpr int kin = 32, kout = 48, rows = DP_H0, cols = DP_L; static constexpr uint32_t off = DP_TC_W0_OFF; };
-template <> struct Lay<1> { static constexpr int kin = 48, kout = 64, rows = DP_H1, cols = DP_H0; static constexpr uint32_t off = DP_TC_W1_OFF; };
-template <> struct Lay<2> { static constexpr int kin = 64, kout = 96, rows = DP_Y, cols = DP_H1; static constexpr uint32_t off = DP_TC_W2_OFF; };
+template <> struct Lay<0> { static constexpr int kin = 32, kout = 48; static constexpr uint32_t off = DP_TC_W0_OFF; };
+template <> struct Lay<1> { static constexpr int kin = 48, kout = 64; static constexpr uint32_t off = DP_TC_W1_OFF; };
+template <> struct Lay<2> { static constexpr int kin = 64, kout = 96; static constexpr uint32_t off = DP_TC_W2_OFF; };
+
+// the split products of one K step, smallest first
+template <int PREC>
+__device__ __forceinline__ void issue_terms(uint32_t tmem, const UmmaDescBase (&a)[kPieces], const UmmaDescBase (&b)[kPieces], uint32_t ao,
+                                            uint32_t bo, uint32_t idesc, bool first) {
+  if (PREC == 0) {  // (3,1) (2,2) (1,3) | (2,1) (1,2) | (1,1)
+    if (first) umma_f16_c<false>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
+    else umma_f16_c<true>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
+    umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[1], bo), idesc);
+    umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[2], bo), idesc);
+    umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
+  } else {          // (2,1) | (1,2) | (1,1)
+    if (first) umma_f16_c<false>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
+    else umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
+  }
+  umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[1], bo), idesc);
+  umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[0], bo), idesc);
+}
 
 // forward layer L: A = W_L (K-major: LBO 128 between input 8-groups, SBO between output-row 8-groups)
-template <int L>
+template <int L, int PREC>
 __device__ __forceinline__ void issue_fwd(const SmemTC& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
   constexpr uint32_t sbo = 128 * (Lay<L>::kin / 8);
-  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);  // bf16, B MN-major
+  constexpr uint32_t fmt = PREC ? 0u : 1u;  // kind::f16 operand format: 0 = fp16, 1 = bf16
+  constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);  // B MN-major
   UmmaDescBase a[kPieces], b[kPieces];
 #pragma unroll
   for (int p = 0; p < kPieces; ++p) {
@@ -75,21 +101,15 @@ __device__ __forceinline__ void issue_fwd(const SmemTC& S, uint32_t tmem, const 
 #pragma unroll
   for (int k = 0; k < Lay<L>::kin / 16; ++k) {
     const uint32_t ao = k * 256, bo = k * 2 * kB_LBO;
-    // smallest products first: (3,1) (2,2) (1,3) | (2,1) (1,2) | (1,1)
-    if (k == 0) umma_bf16_c<false>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
-    else umma_bf16_c<true>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[1], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[2], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[1], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[0], bo), idesc);
+    issue_terms<PREC>(tmem, a, b, ao, bo, idesc, k == 0);
   }
 }
 // backward of layer L: the SAME weight image read MN-major (M = inputs, K = outputs): LBO / SBO swap roles
-template <int L>
+template <int L, int PREC>
 __device__ __forceinline__ void issue_bwd(const SmemTC& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
   constexpr uint32_t wsbo = 128 * (Lay<L>::kin / 8);
-  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
+  constexpr uint32_t fmt = PREC ? 0u : 1u;
+  constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
   UmmaDescBase a[kPieces], b[kPieces];
 #pragma unroll
   for (int p = 0; p < kPieces; ++p) {
@@ -99,13 +119,7 @@ __device__ __forceinline__ void issue_bwd(const SmemTC& S, uint32_t tmem, const 
 #pragma unroll
   for (int k = 0; k < Lay<L>::kout / 16; ++k) {
     const uint32_t ao = k * 2 * wsbo, bo = k * 2 * kB_LBO;
-    if (k == 0) umma_bf16_c<false>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
-    else umma_bf16_c<true>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[1], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[2], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[1], bo), idesc);
-    umma_bf16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[0], bo), idesc);
+    issue_terms<PREC>(tmem, a, b, ao, bo, idesc, k == 0);
   }
 }
 
@@ -114,7 +128,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
   return p;
 }
-// 16 fp32 values (feature k, clips 16*half .. +15) -> three bf16 pieces in an MN-major activation image
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t p;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
+  return p;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t p, float& lo_elem, float& hi_elem) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo_elem), "=f"(hi_elem) : "r"(p));
+}
+// 16 fp32 values (feature k, clips 16*half .. +15) -> split pieces in an MN-major activation image
+template <int PREC>
 __device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_stride, int k, int half, const float (&v)[16]) {
   unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (2 * half) * kB_SBO;
 #pragma unroll
@@ -123,28 +146,45 @@ __device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float x0 = v[8 * g + 2 * i], x1 = v[8 * g + 2 * i + 1];
-      p1[i] = pack_bf16x2(x0, x1);
-      const float r0 = x0 - __uint_as_float(p1[i] << 16), r1 = x1 - __uint_as_float(p1[i] & 0xffff0000u);
-      p2[i] = pack_bf16x2(r0, r1);
-      const float s0 = r0 - __uint_as_float(p2[i] << 16), s1 = r1 - __uint_as_float(p2[i] & 0xffff0000u);
-      p3[i] = pack_bf16x2(s0, s1);
+      if (PREC == 0) {
+        p1[i] = pack_bf16x2(x0, x1);
+        const float r0 = x0 - __uint_as_float(p1[i] << 16), r1 = x1 - __uint_as_float(p1[i] & 0xffff0000u);
+        p2[i] = pack_bf16x2(r0, r1);
+        const float s0 = r0 - __uint_as_float(p2[i] << 16), s1 = r1 - __uint_as_float(p2[i] & 0xffff0000u);
+        p3[i] = pack_bf16x2(s0, s1);
+      } else {
+        p1[i] = pack_f16x2(x0, x1);
+        float h0, h1;
+        unpack_f16x2(p1[i], h0, h1);
+        p2[i] = pack_f16x2(x0 - h0, x1 - h1);
+      }
     }
     *reinterpret_cast<uint4*>(dst + g * kB_SBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
     *reinterpret_cast<uint4*>(dst + piece_stride + g * kB_SBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-    *reinterpret_cast<uint4*>(dst + 2 * piece_stride + g * kB_SBO) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+    if (PREC == 0) *reinterpret_cast<uint4*>(dst + 2 * piece_stride + g * kB_SBO) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
   }
 }
-// a single fp32 value (feature k, clip n) -> the three pieces (used by the Adam lanes for the latent)
+// a single fp32 value (feature k, clip n) -> its pieces (used by the Adam lanes for the latent)
+template <int PREC>
 __device__ __forceinline__ void store_piece_scalar(unsigned char* img, uint32_t piece_stride, int k, int n, float x) {
-  const uint32_t p = pack_bf16x2(x, 0.0f);
-  const float r = x - __uint_as_float(p << 16);
-  const uint32_t q = pack_bf16x2(r, 0.0f);
-  const float s = r - __uint_as_float(q << 16);
-  const uint32_t t = pack_bf16x2(s, 0.0f);
   unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (n >> 3) * kB_SBO + (n & 7) * 2;
-  *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
-  *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
-  *reinterpret_cast<unsigned short*>(dst + 2 * piece_stride) = (unsigned short)(t & 0xffffu);
+  if (PREC == 0) {
+    const uint32_t p = pack_bf16x2(x, 0.0f);
+    const float r = x - __uint_as_float(p << 16);
+    const uint32_t q = pack_bf16x2(r, 0.0f);
+    const float s = r - __uint_as_float(q << 16);
+    const uint32_t t = pack_bf16x2(s, 0.0f);
+    *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
+    *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
+    *reinterpret_cast<unsigned short*>(dst + 2 * piece_stride) = (unsigned short)(t & 0xffffu);
+  } else {
+    const uint32_t p = pack_f16x2(x, 0.0f);
+    float h0, h1;
+    unpack_f16x2(p, h0, h1);
+    const uint32_t q = pack_f16x2(x - h0, 0.0f);
+    *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
+    *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
+  }
 }
 
 struct Ctx {
@@ -155,14 +195,14 @@ struct Ctx {
 };
 
 // one dense layer on the tensor pipe + its epilogue; every thread of the CTA calls this (ends with __syncthreads)
-template <int L, bool FWD, class Epi>
+template <int L, bool FWD, int PREC, class Epi>
 __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
   SmemTC& S = *c.S;
   if (c.warp == kIssueWarp) {
     tc_fence_after();
     if (elect_one()) {
-      if (FWD) issue_fwd<L>(S, c.tmem, src, src_stride);
-      else issue_bwd<L>(S, c.tmem, src, src_stride);
+      if (FWD) issue_fwd<L, PREC>(S, c.tmem, src, src_stride);
+      else issue_bwd<L, PREC>(S, c.tmem, src, src_stride);
       umma_commit(&S.bar_mma);
     }
     __syncwarp();
@@ -185,6 +225,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint3
   __syncthreads();
 }
 
+template <int PREC>
 __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __grid_constant__ DpFrameArgs A) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemTC& S = *reinterpret_cast<SmemTC*>(smem_raw);
@@ -206,7 +247,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
     constexpr uint32_t kChunk = 32768;
     mbar_expect_tx(&S.bar_w, kBytes);
     for (uint32_t o = 0; o < kBytes; o += kChunk)
-      tma_bulk_g2s(reinterpret_cast<unsigned char*>(&S.M) + o, reinterpret_cast<const unsigned char*>(A.model_tc) + o, min(kChunk, kBytes - o), &S.bar_w);
+      tma_bulk_g2s(reinterpret_cast<unsigned char*>(&S.M) + o, reinterpret_cast<const unsigned char*>(PREC ? A.model_tc16 : A.model_tc) + o, min(kChunk, kBytes - o), &S.bar_w);
   }
   Ctx ctx{&S, S.tmem_base, warp, lane, 0u};
   constexpr int CPW = NC / kWarps;  // 2 clips per warp in the per-clip phases
@@ -250,33 +291,34 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
     }
     S.trk[n0 + c][lane] = row;
     if (lane < DP_L / 2) {  // latent -> B operand of the first layer
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z[c].x);
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z[c].y);
+      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z[c].x);
+      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z[c].y);
     }
   }
   fence_proxy_async();
   mbar_wait(&S.bar_w, 0);  // model image (weights, statistics, skeleton tables) has landed
 
+  constexpr float wsc = PREC ? 1.0f / kWScale : 1.0f;  // undoes the weight-image scaling of the fp16 path
   unsigned neg0 = 0, neg1 = 0;  // LeakyReLU slope bits of (feature k, this thread's 16 clips) for the backward pass
   auto forward = [&]() {
-    tc_layer<0, true>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[16]) {
+    tc_layer<0, true, PREC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[16]) {
       const float b = M.b0[k];
       neg0 = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] += b; neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces(&S.pong[0][0], kPongBytes, k, half, v);
+      for (int i = 0; i < 16; ++i) { v[i] = fmaf(v[i], wsc, b); neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces<PREC>(&S.pong[0][0], kPongBytes, k, half, v);
     });
-    tc_layer<1, true>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[16]) {
+    tc_layer<1, true, PREC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[16]) {
       const float b = M.b1[k];
       neg1 = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] += b; neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces(&S.ping[0][0], kPingBytes, k, half, v);
+      for (int i = 0; i < 16; ++i) { v[i] = fmaf(v[i], wsc, b); neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces<PREC>(&S.ping[0][0], kPingBytes, k, half, v);
     });
-    tc_layer<2, true>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[16]) {
+    tc_layer<2, true, PREC>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[16]) {
       const float b = M.b2[k];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) S.ybuf[16 * half + i][k] = v[i] + b;
+      for (int i = 0; i < 16; ++i) S.ybuf[16 * half + i][k] = fmaf(v[i], wsc, b);
     });
   };
   auto backward = [&]() {
@@ -286,24 +328,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = S.ybuf[16 * half + i][k];
-        store_pieces(&S.pong[0][0], kPongBytes, k, half, v);
+        store_pieces<PREC>(&S.pong[0][0], kPongBytes, k, half, v);
       }
       fence_proxy_async();
     }
     __syncthreads();
-    tc_layer<2, false>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[16]) {
+    tc_layer<2, false, PREC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[16]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f : 1.0f;
-      store_pieces(&S.ping[0][0], kPingBytes, k, half, v);
+      for (int i = 0; i < 16; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
+      store_pieces<PREC>(&S.ping[0][0], kPingBytes, k, half, v);
     });
-    tc_layer<1, false>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[16]) {
+    tc_layer<1, false, PREC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[16]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f : 1.0f;
-      store_pieces(&S.pong[0][0], kPongBytes, k, half, v);
+      for (int i = 0; i < 16; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f * wsc : wsc;
+      store_pieces<PREC>(&S.pong[0][0], kPongBytes, k, half, v);
     });
-    tc_layer<0, false>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[16]) {
+    tc_layer<0, false, PREC>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[16]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) S.zgrad[16 * half + i][k] = v[i];
+      for (int i = 0; i < 16; ++i) S.zgrad[16 * half + i][k] = v[i] * (PREC ? wsc * S.bscale[16 * half + i] : 1.0f);
     });
   };
 
@@ -343,6 +385,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
                                              nullptr, nullptr);
         nlp[c] = o.lp;
         nlr[c] = o.lr;
+        if (PREC) {  // bring the largest |dL/dy| component of this clip into [16, 32) with an exact power of two
+          float4* row = reinterpret_cast<float4*>(&S.ybuf[n0 + c][0]);
+          float4 yb = lane < 23 ? row[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+          float mx = fmaxf(fmaxf(fabsf(yb.x), fabsf(yb.y)), fmaxf(fabsf(yb.z), fabsf(yb.w)));
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+          int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;  // floor(log2(mx)) for normal mx
+          e = mx > 0.f ? max(-100, min(100, e)) : 4;
+          const float sc = __uint_as_float((uint32_t)(127 + 4 - e) << 23), isc = __uint_as_float((uint32_t)(127 - 4 + e) << 23);
+          if (lane < 23) row[lane] = make_float4(yb.x * sc, yb.y * sc, yb.z * sc, yb.w * sc);
+          if (lane == 0) S.bscale[n0 + c] = isc;
+          __syncwarp();
+        }
       }
     }
     __syncthreads();
@@ -381,8 +436,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
       // EVERY clip (stopped and padding clips included) so that no column ever feeds back on its own garbage -- a
       // non-finite value in a K-padding row would poison the column through 0 x NaN
       if (lane < DP_L / 2) {
-        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z[c].x);
-        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z[c].y);
+        store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z[c].x);
+        store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z[c].y);
       }
       if (active[c]) {
         lp[c] = nlp[c];
@@ -401,8 +456,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
 #pragma unroll
   for (int c = 0; c < CPW; ++c)
     if (lane < DP_L / 2) {
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zlast[c].x);
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zlast[c].y);
+      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zlast[c].x);
+      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zlast[c].y);
     }
   fence_proxy_async();
   __syncthreads();
@@ -472,11 +527,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
 
 }  // namespace
 
-cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream) {
+cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream) {
   static bool configured = false;
   const size_t smem = sizeof(SmemTC) + 1024;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dp_frame_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -487,6 +543,7 @@ cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_
   if (args.n_clips > num_sms * NC) cpc = NC;  // several waves anyway: use full tiles
   a.clips_per_cta = cpc;
   const int grid = (args.n_clips + cpc - 1) / cpc;
-  dp_frame_tc_kernel<<<grid, kWarps * 32, smem, stream>>>(a);
+  if (fp16) dp_frame_tc_kernel<1><<<grid, kWarps * 32, smem, stream>>>(a);
+  else dp_frame_tc_kernel<0><<<grid, kWarps * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

@@ -12,7 +12,7 @@ struct TpWork {
 };
 
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
-cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
+cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream);
 // fftiles: (TP_NENC + TP_NDEC) x FFT_LAYER_BYTES pre-tiled 3xTF32 FF weights (encoder layers first), or null
 // to run the fp32 CUDA-core FF kernel.
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,

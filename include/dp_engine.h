@@ -61,7 +61,7 @@ typedef struct {
   int32_t joint_adjust_joint;       /* -1 = joint adjustment off */
   int32_t joint_adjust_slot;        /* end-effector slot the joint is snapped towards */
   float joint_adjust_weight;
-  int32_t decoder_path;             /* 0 = auto, 1 = fp32 CUDA-core decoder, 2 = tcgen05 3xTF32 decoder */
+  int32_t decoder_path;             /* 0 = auto, 1 = fp32 CUDA-core decoder, 2 = tcgen05 bf16x3, 3 = tcgen05 fp16x2 */
 } dp_run_params;
 
 /* Pose-VAE decoder folded to three dense layers + statistics + skeleton.
@@ -155,7 +155,7 @@ int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const floa
  * current ring buffers, as drag_pose.py:246-290 does when current_index == 0. */
 int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
 
-/* Decoder path the last frame actually ran: 1 = fp32 CUDA-core kernel, 2 = tcgen05 kernel (0 = none yet).
+/* Decoder path the last frame actually ran: 1 = fp32 CUDA-core kernel, 2 / 3 = tcgen05 kernel (bf16x3 / fp16x2), 0 = none yet.
  * dp_run_params.decoder_path = 0 picks tcgen05 for batches >= 1024 clips and fp32 below. */
 int dp_engine_last_decoder_path(const dp_engine* e);
 

@@ -18,7 +18,7 @@ tl = rng.standard_normal((n, 24)).astype(np.float32) * 0.3
 eng = BatchedDragPose(pm, npz["offsets"], tm, 4096)
 pw64 = port.PortWeights(npz, dtype=torch.float64)
 t64 = port.loss_and_grad(pw64, lat, grot, wl["tgt_pos"][0], wl["tgt_rot"][0], tl, wl["joints"], wl["weights"], lambda_rot=1.0, lambda_temporal=0.02, dtype=torch.float64)
-for path in (1, 2):
+for path in (1, 2, 3):
     r = eng.eval_gradient(lat, grot, tl, wl["tgt_pos"][0], wl["tgt_rot"][0], wl["joints"], wl["weights"], lambda_rot=1.0, lambda_temporal=0.02, decoder_path=path)
     rel = np.linalg.norm(r["grad"] - t64["grad"], axis=1) / np.linalg.norm(t64["grad"], axis=1)
     print(f"path {path}: grad rel err max {rel.max():.2e} median {np.median(rel):.2e}; pos err {np.abs(r['pos'] - t64['pos']).max():.2e}; lp err {np.abs(r['lp']-t64['lp']).max():.2e}")
@@ -26,7 +26,7 @@ for path in (1, 2):
 B, T = 64, 3
 wl = synthetic.make_workload(pm, npz["offsets"], cfg, B, T)
 outs = {}
-for path in (1, 2):
+for path in (1, 2, 3):
     eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1., 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
     res = []
     for t in range(T):
@@ -43,5 +43,6 @@ def positions(pose):
     pos, _ = port.fk_chain(port.root_to_local(q, pw.parents), torch.zeros(q.shape[0], 3), pw.offsets, pw.parents)
     return pos.numpy()
 for t in range(T):
-    d = np.abs(positions(outs[1][t][0]) - positions(outs[2][t][0])).max()
-    print(f"frame {t}: TC vs fp32 max joint diff {d*1e3:.4f} mm, root diff {np.abs(outs[1][t][1]-outs[2][t][1]).max()*1e3:.4f} mm")
+    for pth in (2, 3):
+        d = np.abs(positions(outs[1][t][0]) - positions(outs[pth][t][0])).max()
+        print(f"frame {t}: path {pth} vs fp32 max joint diff {d*1e3:.4f} mm, root diff {np.abs(outs[1][t][1]-outs[pth][t][1]).max()*1e3:.4f} mm")

@@ -32,7 +32,7 @@ def pose_positions(pw, pose_std, root_pos=None):
     return pos.numpy()
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
     eng = engine_factory(512)
@@ -66,7 +66,7 @@ def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_w
     print(f"worst grad rel err vs reference fp32 {worst_rel:.2e}, vs float64 truth {worst_f64:.2e}")
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_model, model_npz, path):
     """20 random states (like SURVEY's probe): relative error <= 1e-4 with no floor, for both decoder paths."""
     rng = np.random.default_rng(11)
@@ -89,7 +89,7 @@ def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_mode
     np.testing.assert_allclose(r["pos"], t64["pos"], atol=2e-6)
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 @pytest.mark.parametrize("tag,opt,n_frames", [("fixed", FIXED, 2), ("early", EARLY, 6)])
 def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights, tag, opt, n_frames, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
@@ -144,7 +144,7 @@ def test_temporal_predictor_vs_reference(golden_dir, engine_factory):
         assert err <= 2e-5
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_frames_3trk.npz"))
     cfg = synthetic.config_3_trackers()
@@ -167,7 +167,7 @@ def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory
     np.testing.assert_allclose(tb[:, :16], g["target_buf"][:, :16], atol=5e-4)
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 def test_batch_256_clips_vs_oracle(engine_factory, pose_model, model_npz, port_weights, temporal_model, path):
     """BASELINE config 2: 256 synthetic clips, 6 trackers, against the CPU oracle (batched port)."""
     B, T = 256, 2
