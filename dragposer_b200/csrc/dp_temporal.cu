@@ -102,38 +102,46 @@ __device__ __forceinline__ void project_feature(const float (*x)[TP_D], int t0, 
   }
 }
 
-template <int MT>
+template <int MQ, int MKV>
 struct MhaSmem {
-  float xq[MT][TP_D], xkv[MT][TP_D];
-  float q[MT][TP_D], k[MT][TP_D + 1], v[MT][TP_D], o[MT][TP_D];
-  float sc[MT][TP_H][MT + 1];  // attention scores / probabilities
+  float xq[MQ][TP_D], q[MQ][TP_D], o[MQ][TP_D];
+  float xkv[MKV][TP_D], k[MKV][TP_D + 1], v[MKV][TP_D];
+  float sc[MQ][TP_H][TP_MAXT + 1];  // attention scores / probabilities of a query row against its own clip's keys
 };
 
-// One CTA per clip; MT (16 or 32) bounds the token counts so that up to 9 CTAs fit on an SM.  Every phase uses all 160
-// threads: projections are register tiled per output feature, the T x H x S score matrix is spread over the CTA.
-template <int MT>
+// One CTA handles G clips: their G*T query rows and G*S key/value rows are projected together (register tiled per output
+// feature), attention stays per clip.  Short sequences (decoder steps with T = 1..5) would otherwise launch 4096 CTAs that
+// each have almost nothing to do; G packs them.  Every phase uses all 160 threads.
+template <int MQ, int MKV>
 __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __restrict__ blob, TpAttn A, TpNorm N,
                                                                 const float* __restrict__ xq_g, int T, int q_stride,
                                                                 const float* __restrict__ xkv_g, int S, int kv_stride,
-                                                                float* __restrict__ out_g) {
+                                                                float* __restrict__ out_g, int n_clips, int G) {
   extern __shared__ __align__(16) unsigned char mha_raw[];
-  MhaSmem<MT>& M = *reinterpret_cast<MhaSmem<MT>*>(mha_raw);
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  MhaSmem<MQ, MKV>& M = *reinterpret_cast<MhaSmem<MQ, MKV>*>(mha_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = blockIdx.x * G;
+  const int g_here = min(G, n_clips - b0);
+  const int RQ = g_here * T, RK = g_here * S;  // rows in this CTA
   float (*xq)[TP_D] = M.xq;
   float (*xkv)[TP_D] = M.xkv;
   float (*q)[TP_D] = M.q;
   float (*k)[TP_D + 1] = M.k;
   float (*v)[TP_D] = M.v;
   float (*o)[TP_D] = M.o;
-  for (int idx = tid; idx < T * TP_D / 4; idx += MHA_THREADS)
-    reinterpret_cast<float4*>(&xq[0][0])[idx] = reinterpret_cast<const float4*>(xq_g + (size_t)b * q_stride * TP_D)[idx];
-  for (int idx = tid; idx < S * TP_D / 4; idx += MHA_THREADS)
-    reinterpret_cast<float4*>(&xkv[0][0])[idx] = reinterpret_cast<const float4*>(xkv_g + (size_t)b * kv_stride * TP_D)[idx];
+  for (int idx = tid; idx < RQ * (TP_D / 4); idx += MHA_THREADS) {
+    const int r = idx / (TP_D / 4), c4 = idx % (TP_D / 4);
+    reinterpret_cast<float4*>(&xq[r][0])[c4] = reinterpret_cast<const float4*>(xq_g + ((size_t)(b0 + r / T) * q_stride + r % T) * TP_D)[c4];
+  }
+  for (int idx = tid; idx < RK * (TP_D / 4); idx += MHA_THREADS) {
+    const int r = idx / (TP_D / 4), c4 = idx % (TP_D / 4);
+    reinterpret_cast<float4*>(&xkv[r][0])[c4] = reinterpret_cast<const float4*>(xkv_g + ((size_t)(b0 + r / S) * kv_stride + r % S) * TP_D)[c4];
+  }
   __syncthreads();
   const float* Win = blob + A.w_in;
   if (tid < 3 * TP_D) {  // feature tid of [q | k | v]
     const bool is_q = tid < TP_D;
-    const int n_tok = is_q ? T : S;
+    const int n_tok = is_q ? RQ : RK;
     const float (*src)[TP_D] = is_q ? xq : xkv;
     const float bias = blob[A.b_in + tid];
     const float scale = is_q ? rsqrtf((float)TP_HD) : 1.0f;
@@ -151,15 +159,16 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < T * TP_H * S; idx += MHA_THREADS) {  // scores
-    const int s = idx % S, h = (idx / S) % TP_H, t = idx / (S * TP_H);
+  for (int idx = tid; idx < RQ * TP_H * S; idx += MHA_THREADS) {  // scores of query row r against the S keys of its clip
+    const int s = idx % S, h = (idx / S) % TP_H, r = idx / (S * TP_H);
+    const float* kr = k[(r / T) * S + s];
     float a = 0.0f;
 #pragma unroll
-    for (int d = 0; d < TP_HD; ++d) a = fmaf(q[t][h * TP_HD + d], k[s][h * TP_HD + d], a);
-    M.sc[t][h][s] = a;
+    for (int d = 0; d < TP_HD; ++d) a = fmaf(q[r][h * TP_HD + d], kr[h * TP_HD + d], a);
+    M.sc[r][h][s] = a;
   }
   __syncthreads();
-  for (int idx = tid; idx < T * TP_H; idx += MHA_THREADS) {  // softmax rows (max-subtracted, like torch)
+  for (int idx = tid; idx < RQ * TP_H; idx += MHA_THREADS) {  // softmax rows (max-subtracted, like torch)
     float* row = M.sc[idx / TP_H][idx % TP_H];
     float mx = -3.0e38f;
     for (int s = 0; s < S; ++s) mx = fmaxf(mx, row[s]);
@@ -173,19 +182,20 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
     for (int s = 0; s < S; ++s) row[s] *= inv;
   }
   __syncthreads();
-  for (int idx = tid; idx < T * TP_D; idx += MHA_THREADS) {  // weighted values
-    const int f = idx % TP_D, t = idx / TP_D;
-    const float* row = M.sc[t][f / TP_HD];
+  for (int idx = tid; idx < RQ * TP_D; idx += MHA_THREADS) {  // weighted values
+    const int f = idx % TP_D, r = idx / TP_D;
+    const float* row = M.sc[r][f / TP_HD];
+    const int kv0 = (r / T) * S;
     float a = 0.0f;
-    for (int s = 0; s < S; ++s) a = fmaf(row[s], v[s][f], a);
-    o[t][f] = a;
+    for (int s = 0; s < S; ++s) a = fmaf(row[s], v[kv0 + s][f], a);
+    o[r][f] = a;
   }
   __syncthreads();
-  {  // output projection + residual, register tiled (48 features x 3 token groups); q is dead: reuse it for the sums
+  {  // output projection + residual, register tiled (48 features x 3 row groups); q is dead: reuse it for the sums
     const int f = tid % TP_D, grp = tid / TP_D;
     if (grp < 3) {
-      const int per = (T + 2) / 3;
-      const int t0 = grp * per, nt = max(0, min(per, T - t0));
+      const int per = (RQ + 2) / 3;
+      const int t0 = grp * per, nt = max(0, min(per, RQ - t0));
       if (nt > 0) {
         float acc[11];  // ceil(32 / 3)
         project_feature<11>(o, t0, nt, blob + A.w_out, TP_D, f, blob[A.b_out + f], acc);
@@ -196,27 +206,39 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
     }
   }
   __syncthreads();
-  for (int t = warp; t < T; t += MHA_THREADS / 32) {
+  for (int r = warp; r < RQ; r += MHA_THREADS / 32) {
     const bool has1 = lane + 32 < TP_D;
     float r0, r1;
-    layer_norm_row(q[t][lane], has1 ? q[t][lane + 32] : 0.0f, has1, blob + N.w, blob + N.b, lane, r0, r1);
-    float* dst = out_g + ((size_t)b * q_stride + t) * TP_D;
+    layer_norm_row(q[r][lane], has1 ? q[r][lane + 32] : 0.0f, has1, blob + N.w, blob + N.b, lane, r0, r1);
+    float* dst = out_g + ((size_t)(b0 + r / T) * q_stride + r % T) * TP_D;
     dst[lane] = r0;
     if (has1) dst[lane + 32] = r1;
   }
 }
 
-static cudaError_t launch_mha(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
-                              int S, int kv_stride, float* out, int B, cudaStream_t st) {
+template <int MQ, int MKV>
+static cudaError_t launch_mha_t(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
+                                int S, int kv_stride, float* out, int B, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tp_mha_ln_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MhaSmem<32>));
+    cudaError_t e = cudaFuncSetAttribute(tp_mha_ln_kernel<MQ, MKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MhaSmem<MQ, MKV>));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (T <= 16 && S <= 16) tp_mha_ln_kernel<16><<<B, MHA_THREADS, sizeof(MhaSmem<16>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out);
-  else tp_mha_ln_kernel<32><<<B, MHA_THREADS, sizeof(MhaSmem<32>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out);
+  int G = MQ / T < MKV / S ? MQ / T : MKV / S;
+  G = G < 1 ? 1 : G;
+  tp_mha_ln_kernel<MQ, MKV><<<(B + G - 1) / G, MHA_THREADS, sizeof(MhaSmem<MQ, MKV>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, G);
   return cudaGetLastError();
+}
+
+static cudaError_t launch_mha(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
+                              int S, int kv_stride, float* out, int B, cudaStream_t st) {
+  // (query rows, key rows) per CTA: short decoder self-attention packs 16/T clips, cross-attention min(16/T, 4) clips,
+  // the 14-token encoder 2 clips; long decoder sequences fall back to one clip per CTA
+  const bool cross = xq != xkv;
+  if (cross && T <= 16) return launch_mha_t<16, 64>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st);
+  if (!cross && T <= 8) return launch_mha_t<16, 16>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st);
+  return launch_mha_t<32, 32>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st);
 }
 
 // ---- out = LN(x + W2 relu(W1 x + b1) + b2) [then an optional second LayerNorm]; 64 tokens per CTA.
