@@ -41,7 +41,19 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const SelftestArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  if (T.a_tmem) {  // A given row-major [128][8*ksteps] fp32: row m -> TMEM lane m, columns 256..
+  if (T.a_tmem == 2) {  // A given row-major [128][16*ksteps] 16-bit: row m -> TMEM lane m, two K elements per 32-bit column
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(T.a_img) + (size_t)tid * 8 * T.ksteps;
+    for (int c0 = 0; c0 < 8 * T.ksteps; c0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (c0 + i < 8 * T.ksteps) ? __uint_as_float(arow[c0 + i]) : 0.f;
+      tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 256u + (uint32_t)c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  } else if (T.a_tmem) {  // A given row-major [128][8*ksteps] fp32: row m -> TMEM lane m, columns 256..
     const float* arow = reinterpret_cast<const float*>(T.a_img) + (size_t)tid * 8 * T.ksteps;
     for (int c0 = 0; c0 < 8 * T.ksteps; c0 += 16) {
       float v[16];
@@ -57,7 +69,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const SelftestArg
   long long t0 = 0;
   if (tid == 0) {
     t0 = clock64();
-    const uint32_t idesc = T.kind ? umma_idesc_bf16(128, T.N, T.a_mn, T.b_mn) : umma_idesc_tf32(128, T.N, T.a_mn, T.b_mn);
+    uint32_t idesc = T.kind ? umma_idesc_bf16(128, T.N, T.a_mn, T.b_mn) : umma_idesc_tf32(128, T.N, T.a_mn, T.b_mn);
+    if (T.kind == 2) idesc &= ~((1u << 7) | (1u << 10));  // fp16 operands (format 0)
     for (int p = 0; p < T.passes; ++p)  // passes > 1 re-accumulates the same product (tests the accumulate flag)
       for (int k = 0; k < T.ksteps; ++k) {
         const uint64_t da = umma_smem_desc(smem_u32(sa) + k * T.a_kstep, T.a_lbo, T.a_sbo);
@@ -65,7 +78,10 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const SelftestArg
         // nacc > 1: rotate over independent accumulators (timing probe only; results of accumulators 1.. are discarded)
         const uint32_t dcol = tmem_base + (T.nacc > 1 ? (uint32_t)(((p * T.ksteps + k) % T.nacc) * 32) : 0u);
         const uint32_t acc = T.nacc > 1 ? ((p * T.ksteps + k) >= T.nacc ? 1u : 0u) : ((p | k) ? 1u : 0u);
-        if (T.a_tmem) umma_tf32_ts(dcol, tmem_base + 256u + 8u * k, db, idesc, acc);
+        if (T.a_tmem == 2) {
+          if (acc) umma_f16_ts_c<true>(dcol, tmem_base + 256u + 8u * k, db, idesc);
+          else umma_f16_ts_c<false>(dcol, tmem_base + 256u + 8u * k, db, idesc);
+        } else if (T.a_tmem) umma_tf32_ts(dcol, tmem_base + 256u + 8u * k, db, idesc, acc);
         else if (T.kind) umma_bf16_ss(dcol, da, db, idesc, acc);
         else umma_tf32_ss(dcol, da, db, idesc, acc);
       }

@@ -20,7 +20,7 @@
 #define TP_NENC 3
 #define TP_NDEC 3
 #define FFT_HC 64                 // hidden units per tensor-core FF chunk
-#define FFT_CHUNK_BYTES 49408     // W1c hi|lo (2 x 12288) + b1c (256) + W2c hi|lo (2 x 12288)
+#define FFT_CHUNK_BYTES 24832     // W1c pieces (2 x 6144 fp16) + b1c (256 fp32) + W2c pieces (2 x 6144 fp16)
 #define FFT_LAYER_BYTES ((TP_FF / FFT_HC) * FFT_CHUNK_BYTES)
 
 struct TpAttn {   // offsets (floats) into the blob

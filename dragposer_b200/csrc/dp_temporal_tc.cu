@@ -5,15 +5,22 @@
 // dim_feedforward 2048; python/src/temporal_transformer.py:26-33).  These two GEMMs are 95%
 // of the predictor's FLOPs.  One CTA owns a tile of 128 tokens (the UMMA M dimension) and
 // walks the 2048 hidden units in chunks of 64:
-//   MMA1  H[128x64]  = X[128x48]  . W1c^T      (tf32, K = 48)       accumulator in TMEM
-//   epi   H -> +b1, relu, hi/lo split -> shared memory (UMMA A-operand layout)
-//   MMA2  O[128x48] += H[128x64]  . W2c^T      (tf32, K = 64)       accumulator in TMEM
-// Precision: 3xTF32 error compensation (x = hi + lo; lo.hi + hi.lo + hi.hi, fp32 accumulate)
-// -- measured 2.7e-7 relative on B200, the same as an fp32 GEMM; plain TF32 gives 7.7e-4.
-// Weights are pre-split and pre-tiled on the host into the exact shared-memory image, so a
-// chunk is ONE contiguous bulk-TMA copy (cp.async.bulk); chunks are double buffered and the
-// MMA of chunk c+1 is issued behind MMA2 of chunk c so the tensor pipe stays busy while the
-// 8 epilogue warps convert the next H tile.
+//   MMA1  H[128x64]  = X[128x48]  . W1c^T      (K = 48)       accumulator in TMEM
+//   epi   H -> +b1, relu, split -> TENSOR MEMORY (A operand of MMA2, two K elements per column)
+//   MMA2  O[128x48] += H[128x64]  . W2c^T      (K = 64)       accumulator in TMEM
+// Precision: fp16x2 split products on kind::f16 -- every fp32 value is two fp16 pieces (22 mantissa bits),
+// three products (2,1)(1,2)(1,1) accumulate in fp32; the weight image stores 64 W (exact power of two, undone in
+// the epilogues) so that the second piece of the small FF weights stays a normal fp16.  Measured on B200: same
+// predictor output error as the fp32 CUDA-core kernel to ~1e-6; plain TF32 would be 7.7e-4 per GEMM.
+// (History: 3xTF32 on kind::tf32 needed twice the MMAs and twice the weight bytes for the same accuracy.)
+// A operands live in tensor memory (TS mode: ~N/2 cycles per MMA instead of the ~45-cycle shared-memory A fetch):
+// X is split once into TMEM, the 8 epilogue warps read the H accumulator with one tcgen05.ld.x32 and write the
+// packed pieces back with tcgen05.st, so activations never touch shared memory.  Weights are pre-split and
+// pre-tiled on the host into the exact shared-memory operand image, so a chunk is ONE contiguous bulk-TMA copy
+// (cp.async.bulk) through a 4+4 stage mbarrier pipeline; a dedicated issuer warp (elect.sync lane) feeds the tensor
+// pipe -- MMA2(c) then MMA1(c+2) per commit -- while the epilogue warps convert chunk c+1.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -25,12 +32,13 @@ namespace {
 constexpr int kTM = 128;
 constexpr int kHC = FFT_HC;                    // 64 hidden units per chunk
 constexpr int kChunks = TP_FF / kHC;           // 32
-constexpr uint32_t kW1Bytes = kHC * TP_D * 4;  // 12288: one tf32 image of W1c [64][48]
-constexpr uint32_t kW2Bytes = TP_D * kHC * 4;  // 12288: one tf32 image of W2c [48][64]
-constexpr uint32_t kPart1 = 2 * kW1Bytes + kHC * 4;  // W1 hi | W1 lo | b1 chunk
-constexpr uint32_t kPart2 = 2 * kW2Bytes;            // W2 hi | W2 lo
+constexpr float kFfWScale = 64.0f;             // weight image holds 64 W
+constexpr uint32_t kW1Bytes = kHC * TP_D * 2;  // 6144: one fp16 image of W1c [64][48]
+constexpr uint32_t kW2Bytes = TP_D * kHC * 2;  // 6144: one fp16 image of W2c [48][64]
+constexpr uint32_t kPart1 = 2 * kW1Bytes + kHC * 4;  // W1 piece 1 | W1 piece 2 | b1 chunk (fp32)
+constexpr uint32_t kPart2 = 2 * kW2Bytes;            // W2 piece 1 | W2 piece 2
 static_assert(kPart1 + kPart2 == FFT_CHUNK_BYTES, "chunk size");
-// shared-memory operand geometry (bytes), see dp_umma.cuh
+// shared-memory B-operand geometry (bytes), K-major no-swizzle fp16: element (n,k) at (n/8)*128 + (k/8)*LBO + (n%8)*16 + (k%8)*2
 constexpr uint32_t kW1_LBO = 128 * (kHC / 8), kW2_LBO = 128 * (TP_D / 8), kB_SBO = 128;
 
 constexpr int kW1Stages = 4, kW2Stages = 4;
@@ -40,39 +48,55 @@ struct Smem {
   uint64_t w1full[kW1Stages], w2full[kW2Stages], hfull[2], hready[2];
   uint32_t tmem_base;
 };
-// tensor-memory columns (fp32 words per lane; lane = token row)
-constexpr uint32_t kT_XHI = 0, kT_XLO = 48, kT_H0 = 96, kT_H1 = 160, kT_L0 = 224, kT_L1 = 288, kT_OUT = 352, kT_COLS = 512;
+// tensor-memory columns (32-bit words per lane; lane = token row; fp16 operands hold two K elements per word)
+constexpr uint32_t kT_X1 = 0, kT_X2 = 24, kT_H0 = 48, kT_H1 = 112, kT_P0 = 176, kT_P1 = 240, kT_OUT = 304, kT_COLS = 512;
+// kT_P{b}: pieces of relu(H) for buffer b: piece 1 at +0 (32 words), piece 2 at +32
+constexpr uint32_t kIdescF16 = (1u << 4);  // fp32 accumulate, fp16 A/B, both K-major; N and M added below
 
-// H(c)[128x64] = X . W1c^T : A = X from tensor memory (hi | lo), B = W1c from shared memory
+// H(c)[128x64] = X . W1c^T : A = X pieces from tensor memory, B = W1c pieces from shared memory
 __device__ __forceinline__ void issue_mma1(const Smem& S, int stage, uint32_t tmem, uint32_t d_col) {
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kHC >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
-  const UmmaDescBase wh = umma_desc_base(smem_u32(S.w1[stage]), kW1_LBO, kB_SBO);
-  const UmmaDescBase wl = umma_desc_base(smem_u32(S.w1[stage]) + kW1Bytes, kW1_LBO, kB_SBO);
-  const uint32_t d = tmem + d_col, xh = tmem + kT_XHI, xl = tmem + kT_XLO;
+  constexpr uint32_t idesc = kIdescF16 | ((uint32_t)(kHC >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+  const UmmaDescBase w1 = umma_desc_base(smem_u32(S.w1[stage]), kW1_LBO, kB_SBO);
+  const UmmaDescBase w2 = umma_desc_base(smem_u32(S.w1[stage]) + kW1Bytes, kW1_LBO, kB_SBO);
+  const uint32_t d = tmem + d_col, x1 = tmem + kT_X1, x2 = tmem + kT_X2;
 #pragma unroll
-  for (int k = 0; k < TP_D / 8; ++k) {
+  for (int k = 0; k < TP_D / 16; ++k) {
     const uint32_t bo = k * 2 * kW1_LBO;
-    if (k == 0) umma_tf32_ts_c<false>(d, xl + 8 * k, umma_desc_at(wh, bo), idesc);
-    else umma_tf32_ts_c<true>(d, xl + 8 * k, umma_desc_at(wh, bo), idesc);
-    umma_tf32_ts_c<true>(d, xh + 8 * k, umma_desc_at(wl, bo), idesc);
-    umma_tf32_ts_c<true>(d, xh + 8 * k, umma_desc_at(wh, bo), idesc);
+    if (k == 0) umma_f16_ts_c<false>(d, x2 + 8 * k, umma_desc_at(w1, bo), idesc);
+    else umma_f16_ts_c<true>(d, x2 + 8 * k, umma_desc_at(w1, bo), idesc);
+    umma_f16_ts_c<true>(d, x1 + 8 * k, umma_desc_at(w2, bo), idesc);
+    umma_f16_ts_c<true>(d, x1 + 8 * k, umma_desc_at(w1, bo), idesc);
   }
 }
-// O[128x48] += H(c) . W2c^T : A = relu(H) hi (in place of the accumulator) | lo from tensor memory
+// O[128x48] += relu(H(c)) . W2c^T : A = pieces of relu(H) from tensor memory
 template <bool FIRST>
-__device__ __forceinline__ void issue_mma2(const Smem& S, int stage, uint32_t tmem, uint32_t hi_col, uint32_t lo_col) {
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TP_D >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
-  const UmmaDescBase wh = umma_desc_base(smem_u32(S.w2[stage]), kW2_LBO, kB_SBO);
-  const UmmaDescBase wl = umma_desc_base(smem_u32(S.w2[stage]) + kW2Bytes, kW2_LBO, kB_SBO);
-  const uint32_t d = tmem + kT_OUT, hh = tmem + hi_col, hl = tmem + lo_col;
+__device__ __forceinline__ void issue_mma2(const Smem& S, int stage, uint32_t tmem, uint32_t p_col) {
+  constexpr uint32_t idesc = kIdescF16 | ((uint32_t)(TP_D >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+  const UmmaDescBase w1 = umma_desc_base(smem_u32(S.w2[stage]), kW2_LBO, kB_SBO);
+  const UmmaDescBase w2 = umma_desc_base(smem_u32(S.w2[stage]) + kW2Bytes, kW2_LBO, kB_SBO);
+  const uint32_t d = tmem + kT_OUT, h1 = tmem + p_col, h2 = tmem + p_col + 32;
 #pragma unroll
-  for (int k = 0; k < kHC / 8; ++k) {
+  for (int k = 0; k < kHC / 16; ++k) {
     const uint32_t bo = k * 2 * kW2_LBO;
-    if (FIRST && k == 0) umma_tf32_ts_c<false>(d, hl + 8 * k, umma_desc_at(wh, bo), idesc);
-    else umma_tf32_ts_c<true>(d, hl + 8 * k, umma_desc_at(wh, bo), idesc);
-    umma_tf32_ts_c<true>(d, hh + 8 * k, umma_desc_at(wl, bo), idesc);
-    umma_tf32_ts_c<true>(d, hh + 8 * k, umma_desc_at(wh, bo), idesc);
+    if (FIRST && k == 0) umma_f16_ts_c<false>(d, h2 + 8 * k, umma_desc_at(w1, bo), idesc);
+    else umma_f16_ts_c<true>(d, h2 + 8 * k, umma_desc_at(w1, bo), idesc);
+    umma_f16_ts_c<true>(d, h1 + 8 * k, umma_desc_at(w2, bo), idesc);
+    umma_f16_ts_c<true>(d, h1 + 8 * k, umma_desc_at(w1, bo), idesc);
   }
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {  // lower 16 bits <- lo_elem (the even K index)
+  uint32_t p;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
+  return p;
+}
+// two fp32 values -> packed first pieces and packed second pieces
+__device__ __forceinline__ void split_h2(float a, float b, float& p1, float& p2) {
+  const uint32_t w = pack_h2(a, b);
+  float ha, hb;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(ha), "=f"(hb) : "r"(w));
+  p1 = __uint_as_float(w);
+  p2 = __uint_as_float(pack_h2(a - ha, b - hb));
 }
 
 __device__ __forceinline__ void ln48(float (&v)[TP_D], const float* __restrict__ w, const float* __restrict__ b) {
@@ -129,20 +153,18 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
   const int chalf = warp >> 2;                   // which 32 of a chunk's 64 hidden columns
   const int row = row0 + m;
   const size_t g = row < n_rows ? ((size_t)(row / T) * row_stride + row % T) * TP_D : 0;
-  // X tile -> tensor memory as the A operand (hi | lo); warps 0-3 take columns 0..23, warps 4-7 columns 24..47
-  if (warp < 8) {
-    float h[24], l[24];
+  // X tile -> tensor memory as the A operand (two fp16 pieces, two K elements per word); warps 0-3 own the 128 rows
+  if (warp < 4) {
+    float p1[24], p2[24];
 #pragma unroll
-    for (int j = 0; j < 24; j += 4) {
+    for (int j = 0; j < TP_D; j += 4) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < n_rows) v = *reinterpret_cast<const float4*>(x_g + g + chalf * 24 + j);
-      split_tf32(v.x, h[j], l[j]); split_tf32(v.y, h[j + 1], l[j + 1]);
-      split_tf32(v.z, h[j + 2], l[j + 2]); split_tf32(v.w, h[j + 3], l[j + 3]);
+      if (row < n_rows) v = *reinterpret_cast<const float4*>(x_g + g + j);
+      split_h2(v.x, v.y, p1[j / 2], p2[j / 2]);
+      split_h2(v.z, v.w, p1[j / 2 + 1], p2[j / 2 + 1]);
     }
-    tmem_st8(tmem + lane_base + kT_XHI + chalf * 24, h + 0); tmem_st8(tmem + lane_base + kT_XHI + chalf * 24 + 8, h + 8);
-    tmem_st8(tmem + lane_base + kT_XHI + chalf * 24 + 16, h + 16);
-    tmem_st8(tmem + lane_base + kT_XLO + chalf * 24, l + 0); tmem_st8(tmem + lane_base + kT_XLO + chalf * 24 + 8, l + 8);
-    tmem_st8(tmem + lane_base + kT_XLO + chalf * 24 + 16, l + 16);
+    tmem_st8(tmem + lane_base + kT_X1, p1 + 0); tmem_st8(tmem + lane_base + kT_X1 + 8, p1 + 8); tmem_st8(tmem + lane_base + kT_X1 + 16, p1 + 16);
+    tmem_st8(tmem + lane_base + kT_X2, p2 + 0); tmem_st8(tmem + lane_base + kT_X2 + 8, p2 + 8); tmem_st8(tmem + lane_base + kT_X2 + 16, p2 + 16);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -162,7 +184,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
     __syncwarp();
     for (int c = 0; c < kChunks; ++c) {
       const int b = c & 1;
-      const uint32_t hcol = b ? kT_H1 : kT_H0, lcol = b ? kT_L1 : kT_L0;
+      const uint32_t hcol = b ? kT_H1 : kT_H0, pcol = b ? kT_P1 : kT_P0;
       mbar_wait(&S.hready[b], (c >> 1) & 1);  // all epilogue threads converted H(c) (and finished chunk c-1)
       tc_fence_after();
       if (elect_one()) {
@@ -176,8 +198,8 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
       if (c + 2 < kChunks) mbar_wait(&S.w1full[(c + 2) % kW1Stages], ((c + 2) / kW1Stages) & 1);
       if (elect_one()) {
         if (!(dbg & 2)) {
-          if (c == 0) issue_mma2<true>(S, c % kW2Stages, tmem, hcol, lcol);
-          else issue_mma2<false>(S, c % kW2Stages, tmem, hcol, lcol);
+          if (c == 0) issue_mma2<true>(S, c % kW2Stages, tmem, pcol);
+          else issue_mma2<false>(S, c % kW2Stages, tmem, pcol);
         }
         if (c + 2 < kChunks && !(dbg & 1)) issue_mma1(S, (c + 2) % kW1Stages, tmem, hcol);
         umma_commit(&S.hfull[b]);
@@ -185,22 +207,23 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
       __syncwarp();
     }
   } else {
-    // ===== epilogue warps: H(c) accumulator -> relu(H + b1) -> hi (in place) | lo, all inside tensor memory
+    // ===== epilogue warps: H(c) accumulator -> relu(H / 64 + b1) -> two packed fp16 pieces, all inside tensor memory
     for (int c = 0; c < kChunks; ++c) {
       const int b = c & 1;
-      const uint32_t hcol = b ? kT_H1 : kT_H0, lcol = b ? kT_L1 : kT_L0;
+      const uint32_t hcol = b ? kT_H1 : kT_H0, pcol = b ? kT_P1 : kT_P0;
       mbar_wait(&S.hfull[b], (c >> 1) & 1);  // H(c) accumulated; MMA2(c-2) has released this buffer pair
       tc_fence_after();
       mbar_wait(&S.w1full[c % kW1Stages], (c / kW1Stages) & 1);  // acquire the TMA-written b1 slice
       const float* b1 = reinterpret_cast<const float*>(S.w1[c % kW1Stages] + 2 * kW1Bytes) + chalf * 32;
-      if (!(dbg & 4)) {  // one 32-column load, one wait, all the math, two 32-column stores, one wait
-        float v[32], lo[32];
+      if (!(dbg & 4)) {  // one 32-column load, bias + relu, split into packed fp16 pieces, two 16-word stores
+        float v[32], p1[16], p2[16];
         tmem_ld32(tmem + lane_base + hcol + (uint32_t)(chalf * 32), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) split_tf32(fmaxf(v[j] + b1[j], 0.f), v[j], lo[j]);
-        tmem_st32(tmem + lane_base + hcol + (uint32_t)(chalf * 32), v);
-        tmem_st32(tmem + lane_base + lcol + (uint32_t)(chalf * 32), lo);
+        for (int j = 0; j < 32; j += 2)
+          split_h2(fmaxf(fmaf(v[j], 1.0f / kFfWScale, b1[j]), 0.f), fmaxf(fmaf(v[j + 1], 1.0f / kFfWScale, b1[j + 1]), 0.f), p1[j / 2], p2[j / 2]);
+        tmem_st16(tmem + lane_base + pcol + (uint32_t)(chalf * 16), p1);
+        tmem_st16(tmem + lane_base + pcol + 32u + (uint32_t)(chalf * 16), p2);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -226,7 +249,8 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
 #pragma unroll
       for (int j = 0; j < TP_D; j += 4) {
         const float4 xv = *reinterpret_cast<const float4*>(x_g + g + j);
-        o[j] += b2[j] + xv.x; o[j + 1] += b2[j + 1] + xv.y; o[j + 2] += b2[j + 2] + xv.z; o[j + 3] += b2[j + 3] + xv.w;
+        o[j] = fmaf(o[j], 1.0f / kFfWScale, b2[j] + xv.x); o[j + 1] = fmaf(o[j + 1], 1.0f / kFfWScale, b2[j + 1] + xv.y);
+        o[j + 2] = fmaf(o[j + 2], 1.0f / kFfWScale, b2[j + 2] + xv.z); o[j + 3] = fmaf(o[j + 3], 1.0f / kFfWScale, b2[j + 3] + xv.w);
       }
       ln48(o, blob + N1.w, blob + N1.b);
       if (has_n2) ln48(o, blob + N2.w, blob + N2.b);
@@ -244,38 +268,30 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
 // Host: build the pre-split, pre-tiled weight image of one FF block (kChunks x FFT_CHUNK_BYTES).
 // w1t is [48][2048] (in, out), w2t is [2048][48] (in, out) -- the transposed layout of the blob.
 void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned char* dst) {
-  auto tf32_hi = [](float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;  // round-to-nearest (ties away) to 10 explicit mantissa bits == cvt.rna.tf32
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-  };
   for (int c = 0; c < kChunks; ++c) {
     unsigned char* base = dst + (size_t)c * FFT_CHUNK_BYTES;
-    float* w1hi = reinterpret_cast<float*>(base);
-    float* w1lo = reinterpret_cast<float*>(base + kW1Bytes);
+    __half* w1p[2] = {reinterpret_cast<__half*>(base), reinterpret_cast<__half*>(base + kW1Bytes)};
     float* bb = reinterpret_cast<float*>(base + 2 * kW1Bytes);
-    float* w2hi = reinterpret_cast<float*>(base + kPart1);
-    float* w2lo = reinterpret_cast<float*>(base + kPart1 + kW2Bytes);
+    __half* w2p[2] = {reinterpret_cast<__half*>(base + kPart1), reinterpret_cast<__half*>(base + kPart1 + kW2Bytes)};
     for (int n = 0; n < kHC; ++n) {      // W1c as B operand [N = hidden][K = 48]
       bb[n] = b1[c * kHC + n];
       for (int k = 0; k < TP_D; ++k) {
-        const float w = w1t[(size_t)k * TP_FF + c * kHC + n];
-        const uint32_t off = ((n >> 3) * kB_SBO + (k >> 2) * kW1_LBO + (n & 7) * 16 + (k & 3) * 4) / 4;
-        const float h = tf32_hi(w);
-        w1hi[off] = h;
-        w1lo[off] = w - h;
+        float r = kFfWScale * w1t[(size_t)k * TP_FF + c * kHC + n];
+        const uint32_t off = ((n >> 3) * kB_SBO + (k >> 3) * kW1_LBO + (n & 7) * 16 + (k & 7) * 2) / 2;
+        for (int p = 0; p < 2; ++p) {
+          w1p[p][off] = __float2half_rn(r);
+          r -= __half2float(w1p[p][off]);
+        }
       }
     }
     for (int n = 0; n < TP_D; ++n)       // W2c as B operand [N = out 48][K = hidden chunk]
       for (int k = 0; k < kHC; ++k) {
-        const float w = w2t[(size_t)(c * kHC + k) * TP_D + n];
-        const uint32_t off = ((n >> 3) * kB_SBO + (k >> 2) * kW2_LBO + (n & 7) * 16 + (k & 3) * 4) / 4;
-        const float h = tf32_hi(w);
-        w2hi[off] = h;
-        w2lo[off] = w - h;
+        float r = kFfWScale * w2t[(size_t)(c * kHC + k) * TP_D + n];
+        const uint32_t off = ((n >> 3) * kB_SBO + (k >> 3) * kW2_LBO + (n & 7) * 16 + (k & 7) * 2) / 2;
+        for (int p = 0; p < 2; ++p) {
+          w2p[p][off] = __float2half_rn(r);
+          r -= __half2float(w2p[p][off]);
+        }
       }
   }
 }
