@@ -49,8 +49,10 @@ struct Smem {
   uint32_t tmem_base;
 };
 // tensor-memory columns (32-bit words per lane; lane = token row; fp16 operands hold two K elements per word)
-constexpr uint32_t kT_X1 = 0, kT_X2 = 24, kT_H0 = 48, kT_H1 = 112, kT_P0 = 176, kT_P1 = 240, kT_OUT = 304, kT_COLS = 512;
-// kT_P{b}: pieces of relu(H) for buffer b: piece 1 at +0 (32 words), piece 2 at +32
+constexpr uint32_t kT_X1 = 0, kT_X2 = 24, kT_H0 = 48, kT_H1 = 112, kT_OUT = 176, kT_COLS = 256;
+// The packed pieces of relu(H) overwrite the accumulator they came from: the epilogue thread that owns hidden columns
+// [32h, 32h+32) of a chunk writes piece 1 to words [32h, 32h+16) and piece 2 to [32h+16, 32h+32) of the same buffer.
+// 256 columns per CTA -> two CTAs share an SM (and its tensor pipe), one converting while the other multiplies.
 constexpr uint32_t kIdescF16 = (1u << 4);  // fp32 accumulate, fp16 A/B, both K-major; N and M added below
 
 // H(c)[128x64] = X . W1c^T : A = X pieces from tensor memory, B = W1c pieces from shared memory
@@ -74,14 +76,15 @@ __device__ __forceinline__ void issue_mma2(const Smem& S, int stage, uint32_t tm
   constexpr uint32_t idesc = kIdescF16 | ((uint32_t)(TP_D >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
   const UmmaDescBase w1 = umma_desc_base(smem_u32(S.w2[stage]), kW2_LBO, kB_SBO);
   const UmmaDescBase w2 = umma_desc_base(smem_u32(S.w2[stage]) + kW2Bytes, kW2_LBO, kB_SBO);
-  const uint32_t d = tmem + kT_OUT, h1 = tmem + p_col, h2 = tmem + p_col + 32;
+  const uint32_t d = tmem + kT_OUT;
 #pragma unroll
   for (int k = 0; k < kHC / 16; ++k) {
     const uint32_t bo = k * 2 * kW2_LBO;
-    if (FIRST && k == 0) umma_f16_ts_c<false>(d, h2 + 8 * k, umma_desc_at(w1, bo), idesc);
-    else umma_f16_ts_c<true>(d, h2 + 8 * k, umma_desc_at(w1, bo), idesc);
-    umma_f16_ts_c<true>(d, h1 + 8 * k, umma_desc_at(w2, bo), idesc);
-    umma_f16_ts_c<true>(d, h1 + 8 * k, umma_desc_at(w1, bo), idesc);
+    const uint32_t h1 = tmem + p_col + (k >> 1) * 32 + (k & 1) * 8, h2 = h1 + 16;
+    if (FIRST && k == 0) umma_f16_ts_c<false>(d, h2, umma_desc_at(w1, bo), idesc);
+    else umma_f16_ts_c<true>(d, h2, umma_desc_at(w1, bo), idesc);
+    umma_f16_ts_c<true>(d, h1, umma_desc_at(w2, bo), idesc);
+    umma_f16_ts_c<true>(d, h1, umma_desc_at(w1, bo), idesc);
   }
 }
 
@@ -125,7 +128,7 @@ __device__ __forceinline__ void load_w2(Smem& S, const unsigned char* wtiles, in
 
 constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 32;  // 8 epilogue warps + 1 MMA/TMA issuer warp
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2,
                 const float* __restrict__ x_g, int n_rows, int T, int row_stride, float* __restrict__ out_g, int dbg) {
   extern __shared__ __align__(1024) unsigned char raw[];
@@ -184,7 +187,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
     __syncwarp();
     for (int c = 0; c < kChunks; ++c) {
       const int b = c & 1;
-      const uint32_t hcol = b ? kT_H1 : kT_H0, pcol = b ? kT_P1 : kT_P0;
+      const uint32_t hcol = b ? kT_H1 : kT_H0, pcol = hcol;
       mbar_wait(&S.hready[b], (c >> 1) & 1);  // all epilogue threads converted H(c) (and finished chunk c-1)
       tc_fence_after();
       if (elect_one()) {
@@ -210,7 +213,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
     // ===== epilogue warps: H(c) accumulator -> relu(H / 64 + b1) -> two packed fp16 pieces, all inside tensor memory
     for (int c = 0; c < kChunks; ++c) {
       const int b = c & 1;
-      const uint32_t hcol = b ? kT_H1 : kT_H0, pcol = b ? kT_P1 : kT_P0;
+      const uint32_t hcol = b ? kT_H1 : kT_H0, pcol = hcol;
       mbar_wait(&S.hfull[b], (c >> 1) & 1);  // H(c) accumulated; MMA2(c-2) has released this buffer pair
       tc_fence_after();
       mbar_wait(&S.w1full[c % kW1Stages], (c / kW1Stages) & 1);  // acquire the TMA-written b1 slice
@@ -222,8 +225,8 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wtiles, const float* __restric
 #pragma unroll
         for (int j = 0; j < 32; j += 2)
           split_h2(fmaxf(fmaf(v[j], 1.0f / kFfWScale, b1[j]), 0.f), fmaxf(fmaf(v[j + 1], 1.0f / kFfWScale, b1[j + 1]), 0.f), p1[j / 2], p2[j / 2]);
-        tmem_st16(tmem + lane_base + pcol + (uint32_t)(chalf * 16), p1);
-        tmem_st16(tmem + lane_base + pcol + 32u + (uint32_t)(chalf * 16), p2);
+        tmem_st16(tmem + lane_base + pcol + (uint32_t)(chalf * 32), p1);
+        tmem_st16(tmem + lane_base + pcol + (uint32_t)(chalf * 32) + 16u, p2);
       }
       tmem_st_wait();
       tc_fence_before();
