@@ -67,6 +67,7 @@ SIGNATURES = {
     "dp_engine_last_decoder_path": (C.c_int, [_VP]),
     "dp_engine_set_predictor_path": (C.c_int, [_VP, C.c_int]),
     "dp_engine_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "dp_engine_get_phase_cycles": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),
     "dp_engine_get_profile": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 

@@ -56,7 +56,6 @@ static_assert(sizeof(DpModelImage) % 16 == 0, "bulk copy needs a multiple of 16 
 #define DP_TC_W_BYTES 21504u  // W2: 96 x 64 x 2 B = 12288
 #define DP_TC_PIECES 3
 struct __align__(16) DpModelImageTC {
-  unsigned char w[DP_TC_PIECES][DP_TC_W_BYTES];
   float b0[DP_H0];
   float b1[DP_H1];
   float b2[DP_Y];
@@ -72,7 +71,10 @@ struct __align__(16) DpModelImageTC {
   int32_t last[32];
   int32_t height_slot[32];
   int32_t pad[32];
+  // LAST member: a kernel that uses only the first n pieces copies (and reserves shared memory for) a prefix of the image
+  __align__(16) unsigned char w[DP_TC_PIECES][DP_TC_W_BYTES];
 };
+#define DP_TC_IMAGE_BYTES(n_pieces) (sizeof(DpModelImageTC) - (DP_TC_PIECES - (n_pieces)) * DP_TC_W_BYTES)
 static_assert(sizeof(DpModelImageTC) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
 
 struct DpFrameArgs {
@@ -118,6 +120,8 @@ struct DpFrameArgs {
   int eval_only;
   float* eval_grad;   // (B,24)
   float* eval_pos;    // (B,22,3)
+  // optional phase clock of CTA 0 (tcgen05 kernel), 8 counters, see dp_engine_get_phase_cycles
+  unsigned long long* phase_cycles;
 };
 
 // ---------------------------------------------------------------- small math helpers

@@ -66,6 +66,7 @@ struct dp_engine {
   long long launches = 0;
   // optional device-side timing of the two kernel groups (bench roofline)
   int profiling = 0;
+  unsigned long long* d_phase = nullptr;  // 8 phase-cycle counters of the tcgen05 frame kernel (profiling level 2 only)
   std::vector<cudaEvent_t> prof_events;  // triples: before predictor, before frame kernel, after frame kernel
 };
 
@@ -135,7 +136,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
-  cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam);
+  cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
   cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat);
   cudaFree(e->d_pose); cudaFree(e->d_gp); cudaFreeHost(e->h_pose); cudaFreeHost(e->h_gp);
   cudaStreamDestroy(e->stream);
@@ -264,7 +265,7 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     memcpy(T.height_slot, I.height_slot, sizeof(I.height_slot));
     memcpy(T.pad, I.pad, sizeof(I.pad));
     CK(cudaMemcpy(e->d_model_tc, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
-    // fp16x2 variant: two fp16 pieces of 16 W in the same layout (third piece unused)
+    // fp16x2 variant: two fp16 pieces of 16 W in the same layout (third piece unused; the kernel copies a prefix)
     memset(T.w, 0, sizeof(T.w));
     for (int l = 0; l < 3; ++l) {
       const int K = dims[l], N = dims[l + 1];
@@ -421,6 +422,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.out_pose = out_pose; a.out_gpos = out_gpos; a.out_iters = e->d_iters; a.out_losses = e->d_losses;
   a.trace = e->trace_enabled ? e->d_trace : nullptr;
   a.trace_iters = e->trace_iters;
+  a.phase_cycles = e->profiling >= 2 ? e->d_phase : nullptr;
   if (e->profiling) CK(cudaEventRecord(ev[1], st));
   // auto: tensor-core decoder once a batch fills a fair share of the SMs with 32-clip tiles; the fp32 warp-per-clip
   // kernel is the low-latency path for small batches (B = 1 streaming)
@@ -654,7 +656,19 @@ extern "C" int dp_engine_set_profiling(dp_engine* e, int enable) {
   CK(cudaDeviceSynchronize());
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   e->prof_events.clear();
-  e->profiling = enable ? 1 : 0;
+  e->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+  if (enable >= 2) {
+    if (!e->d_phase) CK(cudaMalloc(&e->d_phase, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_phase, 0, 8 * sizeof(unsigned long long)));
+  }
+  return DP_OK;
+}
+
+extern "C" int dp_engine_get_phase_cycles(dp_engine* e, unsigned long long* cycles8) {
+  if (!e || !cycles8) return fail(DP_ERR_ARG, "null argument");
+  if (!e->d_phase) return fail(DP_ERR_STATE, "profiling was never enabled");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(cycles8, e->d_phase, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return DP_OK;
 }
 

@@ -1,0 +1,297 @@
+// dp_fk2.cuh -- forward kinematics + masked tracker loss + reverse-mode adjoint for TWO clips per warp
+// (lane == joint), the two clips travelling in the halves of packed fp32x2 registers (FFMA2 / FMUL2 / FADD2,
+// sm_100).  Same arithmetic as fk_loss in dp_fk.cuh (python/src/utils.py:80-149,
+// python/src/drag_pose.py:66-194), written with explicit fused multiply-adds.
+//
+// Why: the phase clock of the tcgen05 frame kernel showed the kinematics phase latency bound -- a warp walked its
+// two clips one after the other, ~1000 dependent-ish instructions each at ~4.5 cycles per instruction.  Packing
+// halves the instruction stream of the pair (one FFMA2 does both clips) instead of merely interleaving it.
+// FFMA2 has the same fp32 FLOP rate as FFMA (measured: scripts/ubench/ffma2_rate.cu, 114 vs 120 FMA/clk/SM), so
+// this buys issue slots and latency, not arithmetic throughput.
+#pragma once
+#include "dp_fk.cuh"
+
+struct P2 {
+  float2 v;  // .x = first clip of the warp, .y = second clip
+};
+#define DP_DI __device__ __forceinline__
+DP_DI P2 mk2(float a, float b) { P2 r; r.v = make_float2(a, b); return r; }
+DP_DI P2 splat(float a) { return mk2(a, a); }
+DP_DI P2 operator-(P2 a) { return mk2(-a.v.x, -a.v.y); }  // folds into the operand modifier of the consumer
+DP_DI P2 operator+(P2 a, P2 b) { P2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+DP_DI P2 operator-(P2 a, P2 b) { P2 r; r.v = __fadd2_rn(a.v, (-b).v); return r; }
+DP_DI P2 operator*(P2 a, P2 b) { P2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+DP_DI P2 operator*(float s, P2 a) { return splat(s) * a; }
+DP_DI P2 mad(P2 a, P2 b, P2 c) { P2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }   // a b + c
+DP_DI P2 mad(float s, P2 b, P2 c) { return mad(splat(s), b, c); }
+DP_DI P2 shfl(P2 a, int src) { return mk2(__shfl_sync(0xffffffffu, a.v.x, src), __shfl_sync(0xffffffffu, a.v.y, src)); }
+DP_DI P2 shfl_up(P2 a, int d) { return mk2(__shfl_up_sync(0xffffffffu, a.v.x, d), __shfl_up_sync(0xffffffffu, a.v.y, d)); }
+DP_DI P2 sel(bool c, P2 a, P2 b) { return mk2(c ? a.v.x : b.v.x, c ? a.v.y : b.v.y); }
+// MUFU without the denormal range-extension sequence: the arguments here are quaternion norms (~1)
+DP_DI float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DP_DI float sqrt_ftz(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DP_DI P2 rcp2(P2 a) { return mk2(rcp_ftz(a.v.x), rcp_ftz(a.v.y)); }
+DP_DI P2 sqrt2(P2 a) { return mk2(sqrt_ftz(a.v.x), sqrt_ftz(a.v.y)); }
+
+DP_DI void quat_mul(const P2 a[4], const P2 b[4], P2 r[4]) {
+  r[0] = mad(-a[3], b[3], mad(-a[2], b[2], mad(-a[1], b[1], a[0] * b[0])));
+  r[1] = mad(-a[3], b[2], mad(a[2], b[3], mad(a[1], b[0], a[0] * b[1])));
+  r[2] = mad(a[3], b[1], mad(a[2], b[0], mad(-a[1], b[3], a[0] * b[2])));
+  r[3] = mad(a[3], b[0], mad(-a[2], b[1], mad(a[1], b[2], a[0] * b[3])));
+}
+// python/src/utils.py:34-76 (no normalisation, 1 - 2(yy+zz) form), row-major 3x3
+DP_DI void quat_to_mat(const P2 q[4], P2 m[9]) {
+  const P2 w = q[0], x = q[1], y = q[2], z = q[3], one = splat(1.0f);
+  const P2 x2 = x + x, y2 = y + y, z2 = z + z;
+  const P2 xx = x * x2, yy = y * y2, zz = z * z2;
+  const P2 xy = x * y2, yz = y * z2, xz = x * z2;
+  m[0] = one - (yy + zz); m[1] = mad(-w, z2, xy);  m[2] = mad(w, y2, xz);
+  m[3] = mad(w, z2, xy);  m[4] = one - (xx + zz);  m[5] = mad(-w, x2, yz);
+  m[6] = mad(-w, y2, xz); m[7] = mad(w, x2, yz);   m[8] = one - (xx + yy);
+}
+// adjoint of quat_to_mat: G = dL/dM -> dL/dq (Mbar2q), as differences of G entries
+DP_DI void mat_bar_to_quat(const P2 q[4], const P2 G[9], P2 qb[4]) {
+  const P2 w = q[0], x = q[1], y = q[2], z = q[3];
+  const P2 a = G[7] - G[5], b = G[2] - G[6], c = G[3] - G[1];  // antisymmetric part (multiplies w)
+  const P2 d = G[1] + G[3], e = G[2] + G[6], f = G[5] + G[7];  // symmetric part
+  const P2 g0 = G[0] + G[0], g4 = G[4] + G[4], g8 = G[8] + G[8];
+  const P2 two = splat(2.0f);
+  qb[0] = two * mad(z, c, mad(y, b, x * a));
+  qb[1] = two * mad(-x, g4 + g8, mad(w, a, mad(z, e, y * d)));
+  qb[2] = two * mad(-y, g0 + g8, mad(w, b, mad(z, f, x * d)));
+  qb[3] = two * mad(-z, g0 + g4, mad(w, c, mad(y, f, x * e)));
+}
+DP_DI void mat_mul(const P2 a[9], const P2 b[9], P2 c[9]) {  // c = a b
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = mad(a[3 * i + 2], b[6 + j], mad(a[3 * i + 1], b[3 + j], a[3 * i] * b[j]));
+}
+DP_DI void mat_mul_bt(const P2 a[9], const P2 b[9], P2 c[9]) {  // c = a b^T
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = mad(a[3 * i + 2], b[3 * j + 2], mad(a[3 * i + 1], b[3 * j + 1], a[3 * i] * b[3 * j]));
+}
+DP_DI void mat_mul_at(const P2 a[9], const P2 b[9], P2 c[9]) {  // c = a^T b
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = mad(a[6 + i], b[6 + j], mad(a[3 + i], b[3 + j], a[i] * b[j]));
+}
+DP_DI void mat_vec(const P2 a[9], const P2 v[3], P2 r[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = mad(a[3 * i + 2], v[2], mad(a[3 * i + 1], v[1], a[3 * i] * v[0]));
+}
+DP_DI void mat_t_vec(const P2 a[9], const P2 v[3], P2 r[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = mad(a[6 + i], v[2], mad(a[3 + i], v[1], a[i] * v[0]));
+}
+// Sum of 8 per-lane values over the warp with 9 shuffles: halve the value set while halving the lane set.
+// Afterwards lane 4c holds the total of component c (c = 0..7).
+DP_DI float warp_sum8_scatter(const float (&a)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float k[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) k[i] = (b4 ? a[4 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a[i] : a[4 + i], 16);
+  float m[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) m[i] = (b3 ? k[2 + i] : k[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k[i] : k[2 + i], 8);
+  float s = (b2 ? m[1] : m[0]) + __shfl_xor_sync(0xffffffffu, b2 ? m[0] : m[1], 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return s;
+}
+
+struct FkOut2 {
+  P2 lp, lr;  // weighted position loss, lambda-scaled rotation loss of the two clips (warp-uniform)
+};
+
+// ybuf* / trk*: the two clips' 96-float y rows (dL/dy is written in place) and tracker rows; groot: their previous world
+// root rotations, 2 x 4 floats in shared memory (re-read where needed instead of held in registers); scr: 16 float2 of
+// per-pair scratch for the warp-uniform R_0, r and d, parked in shared memory between the forward and the adjoint half.
+template <bool ADJOINT, bool EPILOGUE, class MODEL>
+DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restrict__ ybuf_b, const ClipTrackers* __restrict__ trk_a,
+                      const ClipTrackers* __restrict__ trk_b, const float* __restrict__ groot, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
+                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3]) {
+  const bool is_joint = lane < DP_J;
+  const bool is_root = lane == 0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 ya = is_joint ? reinterpret_cast<const float4*>(ybuf_a)[lane] : zero4;
+  const float4 yb = is_joint ? reinterpret_cast<const float4*>(ybuf_b)[lane] : zero4;
+  const float4 da = reinterpret_cast<const float4*>(ybuf_a)[DP_J], db = reinterpret_cast<const float4*>(ybuf_b)[DP_J];
+  const float4 mq = is_joint ? reinterpret_cast<const float4*>(M.mean_q)[lane] : make_float4(1.f, 0.f, 0.f, 0.f);
+  const float4 sq = is_joint ? reinterpret_cast<const float4*>(M.std_q)[lane] : zero4;
+  __syncwarp();
+  const P2 u[4] = {mad(sq.x, mk2(ya.x, yb.x), splat(mq.x)), mad(sq.y, mk2(ya.y, yb.y), splat(mq.y)),
+                   mad(sq.z, mk2(ya.z, yb.z), splat(mq.z)), mad(sq.w, mk2(ya.w, yb.w), splat(mq.w))};
+  const P2 n = sqrt2(mad(u[3], u[3], mad(u[2], u[2], mad(u[1], u[1], u[0] * u[0]))));
+  const P2 inv = rcp2(n + splat(1e-8f));
+  const P2 q[4] = {u[0] * inv, u[1] * inv, u[2] * inv, u[3] * inv};
+  P2 q0[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q0[i] = shfl(q[i], 0);
+  P2 r[4];
+  {
+    const float4 ga = reinterpret_cast<const float4*>(groot)[0], gb = reinterpret_cast<const float4*>(groot)[1];
+    const P2 g[4] = {mk2(ga.x, gb.x), mk2(ga.y, gb.y), mk2(ga.z, gb.z), mk2(ga.w, gb.w)};
+    quat_mul(g, q0, r);  // world root rotation (drag_pose.py:88-92)
+  }
+  P2 R0[9], Mj[9], R[9];
+  quat_to_mat(r, R0);
+  {
+    const P2 qj[4] = {sel(is_root, splat(1.f), q[0]), sel(is_root, splat(0.f), q[1]), sel(is_root, splat(0.f), q[2]),
+                      sel(is_root, splat(0.f), q[3])};
+    quat_to_mat(qj, Mj);
+  }
+  mat_mul(R0, Mj, R);  // closed form of utils.py:80-149: R_j = R_0 M(q_j)
+  const P2 d[3] = {mad(M.std_d[0], mk2(da.x, db.x), splat(M.mean_d[0])), mad(M.std_d[1], mk2(da.y, db.y), splat(M.mean_d[1])),
+                   mad(M.std_d[2], mk2(da.z, db.z), splat(M.mean_d[2]))};
+  // c_j = R_parent o_j ; p_j = sum of c over the ancestor chain (log-step pointer jumping); p_0 = R_0 d (drag_pose.py:102)
+  const int par = is_root ? 0 : M.parent[lane];
+  const float4 off = *reinterpret_cast<const float4*>(M.off[lane]);
+  P2 p[3];
+  {
+    P2 Rp[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rp[i] = shfl(R[i], par);
+    const P2 ov[3] = {sel(is_root, d[0], splat(off.x)), sel(is_root, d[1], splat(off.y)), sel(is_root, d[2], splat(off.z))};
+    mat_vec(Rp, ov, p);  // the root's parent entry is itself: R_0 d
+  }
+  if (ADJOINT && is_root) {  // warp-uniform values the adjoint needs again: park them (every lane holds the same numbers)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scr[i] = R0[i].v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) scr[9 + i] = r[i].v;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) scr[13 + i] = d[i].v;
+  }
+  const int n_jump = M.pad[0], n_child = M.pad[1];  // rounds this skeleton needs (3 and 3 for the 22-joint body)
+#pragma unroll
+  for (int rd = 0; rd < DP_JUMP_ROUNDS; ++rd) {
+    if (rd >= n_jump) break;
+    const int a = M.jump[rd][lane];
+    const int src = a >= 0 ? a : lane;
+    const P2 t0 = shfl(p[0], src), t1 = shfl(p[1], src), t2 = shfl(p[2], src);
+    if (a >= 0) { p[0] = p[0] + t0; p[1] = p[1] + t1; p[2] = p[2] + t2; }
+  }
+  // masked tracker loss (drag_pose.py:116-124); untracked lanes carry zero weights
+  const ClipTrackers ta = trk_a[lane], tb = trk_b[lane];
+  const P2 ep[3] = {p[0] - mk2(ta.pw.x, tb.pw.x), p[1] - mk2(ta.pw.y, tb.pw.y), p[2] - mk2(ta.pw.z, tb.pw.z)};
+  const P2 wp = mk2(ta.pw.w, tb.pw.w), wr = mk2(ta.r0.w, tb.r0.w);
+  const P2 eR[9] = {R[0] - mk2(ta.r0.x, tb.r0.x), R[1] - mk2(ta.r0.y, tb.r0.y), R[2] - mk2(ta.r0.z, tb.r0.z),
+                    R[3] - mk2(ta.r1.x, tb.r1.x), R[4] - mk2(ta.r1.y, tb.r1.y), R[5] - mk2(ta.r1.z, tb.r1.z),
+                    R[6] - mk2(ta.r2.x, tb.r2.x), R[7] - mk2(ta.r2.y, tb.r2.y), R[8] - mk2(ta.r2.z, tb.r2.z)};
+  P2 sp = mad(ep[2], ep[2], mad(ep[1], ep[1], ep[0] * ep[0]));
+  P2 sr = eR[0] * eR[0];
+#pragma unroll
+  for (int i = 1; i < 9; ++i) sr = mad(eR[i], eR[i], sr);
+  sp = sp * wp;
+  sr = sr * wr;
+  {  // four warp sums with 6 + 4 shuffles
+    const float four[4] = {sp.v.x, sp.v.y, sr.v.x, sr.v.y};
+    const float k = warp_sum4_scatter(four, lane);
+    sp = mk2(__shfl_sync(0xffffffffu, k, 0), __shfl_sync(0xffffffffu, k, 8));
+    sr = mk2(__shfl_sync(0xffffffffu, k, 16), __shfl_sync(0xffffffffu, k, 24));
+  }
+  FkOut2 out;
+  out.lp = sp * inv3e;
+  out.lr = sr * lrot9e;
+  if (EPILOGUE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q_out[i] = q[i]; r_out[i] = r[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p_out[i] = p[i]; d_out[i] = d[i]; }
+  }
+  if (ADJOINT) {
+    __syncwarp();  // scratch visible; from here R0 / r / d are re-read from shared memory
+    auto ld2 = [&](int i) { P2 t; t.v = scr[i]; return t; };
+    // seeds
+    const P2 kp = (wp + wp) * inv3e, kr = (wr + wr) * lrot9e;
+    P2 Rb[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb[i] = eR[i] * kr;
+    // subtree sums of pbar over the pre-order numbering: inclusive scan, then a range difference
+    P2 P[3] = {ep[0] * kp, ep[1] * kp, ep[2] * kp};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const P2 t0 = shfl_up(P[0], o), t1 = shfl_up(P[1], o), t2 = shfl_up(P[2], o);
+      if (lane >= o) { P[0] = P[0] + t0; P[1] = P[1] + t1; P[2] = P[2] + t2; }
+    }
+    const int last = M.last[lane];
+    P2 cb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const P2 hi = shfl(P[i], last);
+      P2 lo = shfl_up(P[i], 1);
+      if (lane == 0) lo = splat(0.0f);
+      cb[i] = hi - lo;  // cbar_j = sum of pbar over subtree(j)
+    }
+    // Rbar_j += sum_children cbar_c o_c^T   (p_c = p_j + R_j o_c)
+#pragma unroll
+    for (int k = 0; k < DP_MAX_CHILD; ++k) {
+      if (k >= n_child) break;
+      const int ch = M.child[k][lane];
+      const int src = ch >= 0 ? ch : lane;
+      const P2 t0 = shfl(cb[0], src), t1 = shfl(cb[1], src), t2 = shfl(cb[2], src);
+      if (ch >= 0) {
+        const float4 co = *reinterpret_cast<const float4*>(M.coff[k][lane]);
+        Rb[0] = mad(co.x, t0, Rb[0]); Rb[1] = mad(co.y, t0, Rb[1]); Rb[2] = mad(co.z, t0, Rb[2]);
+        Rb[3] = mad(co.x, t1, Rb[3]); Rb[4] = mad(co.y, t1, Rb[4]); Rb[5] = mad(co.z, t1, Rb[5]);
+        Rb[6] = mad(co.x, t2, Rb[6]); Rb[7] = mad(co.y, t2, Rb[7]); Rb[8] = mad(co.z, t2, Rb[8]);
+      }
+    }
+    if (is_root) {  // p_0 = R_0 d
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Rb[3 * i + j] = mad(cb[i], ld2(13 + j), Rb[3 * i + j]);
+    }
+    // every joint contributes Rbar_j M_j^T to Rbar_0 (M_0 = I); reduce in quaternion space (4 values per clip, not 9)
+    P2 rbp[4];
+    {
+      P2 X[9], t[4];
+      mat_mul_bt(Rb, Mj, X);
+      const P2 rr[4] = {ld2(9), ld2(10), ld2(11), ld2(12)};
+      mat_bar_to_quat(rr, X, t);
+      // only lane 0 needs the eight totals: 9-shuffle scatter reduction, then lane 0 collects from lanes 4c
+      const float eight[8] = {t[0].v.x, t[0].v.y, t[1].v.x, t[1].v.y, t[2].v.x, t[2].v.y, t[3].v.x, t[3].v.y};
+      const float k = warp_sum8_scatter(eight, lane);
+      rbp[0] = mk2(k, __shfl_sync(0xffffffffu, k, 4));
+      rbp[1] = mk2(__shfl_sync(0xffffffffu, k, 8), __shfl_sync(0xffffffffu, k, 12));
+      rbp[2] = mk2(__shfl_sync(0xffffffffu, k, 16), __shfl_sync(0xffffffffu, k, 20));
+      rbp[3] = mk2(__shfl_sync(0xffffffffu, k, 24), __shfl_sync(0xffffffffu, k, 28));
+    }
+    P2 qb[4];
+    if (is_root) {
+      const float4 ga = reinterpret_cast<const float4*>(groot)[0], gb = reinterpret_cast<const float4*>(groot)[1];
+      const P2 gc[4] = {mk2(ga.x, gb.x), mk2(-ga.y, -gb.y), mk2(-ga.z, -gb.z), mk2(-ga.w, -gb.w)};
+      quat_mul(gc, rbp, qb);  // r = g (x) q_0  ->  q0bar = conj(g) (x) rbar
+    } else {
+      P2 G[9], R0s[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R0s[i] = ld2(i);
+      mat_mul_at(R0s, Rb, G);
+      mat_bar_to_quat(q, G, qb);
+    }
+    // adjoint of q = u / (|u| + 1e-8)
+    const P2 dt = mad(u[3], qb[3], mad(u[2], qb[2], mad(u[1], qb[1], u[0] * qb[0])));
+    const P2 kk = dt * inv * inv * rcp2(n);
+    const P2 o0 = sq.x * mad(-u[0], kk, qb[0] * inv), o1 = sq.y * mad(-u[1], kk, qb[1] * inv);
+    const P2 o2 = sq.z * mad(-u[2], kk, qb[2] * inv), o3 = sq.w * mad(-u[3], kk, qb[3] * inv);
+    if (is_joint) {
+      reinterpret_cast<float4*>(ybuf_a)[lane] = make_float4(o0.v.x, o1.v.x, o2.v.x, o3.v.x);
+      reinterpret_cast<float4*>(ybuf_b)[lane] = make_float4(o0.v.y, o1.v.y, o2.v.y, o3.v.y);
+    }
+    if (is_root) {
+      P2 dbar[3], R0s[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R0s[i] = ld2(i);
+      mat_t_vec(R0s, cb, dbar);
+      reinterpret_cast<float4*>(ybuf_a)[DP_J] = make_float4(dbar[0].v.x * M.std_d[0], dbar[1].v.x * M.std_d[1], dbar[2].v.x * M.std_d[2], 0.0f);
+      reinterpret_cast<float4*>(ybuf_b)[DP_J] = make_float4(dbar[0].v.y * M.std_d[0], dbar[1].v.y * M.std_d[1], dbar[2].v.y * M.std_d[2], 0.0f);
+    }
+    __syncwarp();
+  }
+  return out;
+}

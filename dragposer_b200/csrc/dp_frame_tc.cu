@@ -19,37 +19,58 @@
 //   write the next layer's B operand (MN-major image, one STS.128 per 8 clips).
 // * kinematics, loss, adjoint, Adam, early stopping and the frame epilogue are the warp-per-clip code shared
 //   with the fp32 kernel (dp_fk.cuh).
-#include "dp_fk.cuh"
+#include "dp_fk2.cuh"
 #include "dp_internal.h"
 #include "dp_umma.cuh"
 
 namespace {
 
-constexpr int NC = DP_TC_CLIPS;   // 32 clips per CTA == UMMA N
-constexpr int kWarps = 16;
-constexpr int kEpiWarps = 8;      // warps 0..7: TMEM lane quarter = warp % 4, clip half = warp / 4
-constexpr int kIssueWarp = 8;
-constexpr uint32_t kB_LBO = 128 * (NC / 8);  // activation image: K 8-groups 512 B apart, clip 8-groups 128 B apart
+// Tile geometry.  NC clips (the UMMA N dimension) per CTA, two clips per warp in the per-clip phases, eight epilogue warps
+// (TMEM lane quarter = warp % 4, clip half = warp / 4).  Two instantiations:
+//   NC = 32, 16 warps, one CTA per SM   (bf16x3: its three-piece image does not fit twice)
+//   NC = 16,  8 warps, TWO CTAs per SM  (fp16x2, default): while one CTA waits for the tensor pipe or sits in a block barrier
+//   the other one runs its kinematics -- the phase clock (dp_engine_get_phase_cycles) showed the single-CTA kernel spending
+//   46 % of an iteration in tensor/epilogue/Adam phases with the CUDA cores mostly idle.
+template <int NC>
+struct Geo {
+  static constexpr int kWarps = NC / 2;
+  static constexpr int EC = NC / 2;                      // clips per epilogue thread
+  static constexpr int kIssueWarp = kWarps > 8 ? 8 : 0;  // a non-epilogue warp when there is one
+  static constexpr uint32_t kB_LBO = 128 * (NC / 8);     // activation image: K 8-groups LBO apart, clip 8-groups 128 B apart
+  static constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // per 16-bit piece
+};
+constexpr int kEpiWarps = 8;
 constexpr uint32_t kB_SBO = 128;
-constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // per bf16 piece
-constexpr int kPieces = 3;        // buffers are sized for three pieces
 // PREC 0: bf16x3 -- x = x1 + x2 + x3 (bf16), six products (3,1)(2,2)(1,3)(2,1)(1,2)(1,1): 1.3e-7 relative per GEMM.
 // PREC 1: fp16x2 -- x = x1 + x2 (fp16, 22 mantissa bits), three products (2,1)(1,2)(1,1): ~5e-7 relative per GEMM at half the
 //         tensor and epilogue work.  fp16's narrow exponent is handled by exact power-of-two scalings: the weight image stores
 //         16 W (undone in every epilogue), and the backward pass carries dL/dy scaled per clip so that its largest component
 //         is in [16, 32) (undone when dL/dz is written); forward activations (|a| < 2^6 here) need no scaling.
 constexpr float kWScale = 16.0f;
+constexpr int kMaxPieces = 3;
+enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
 
+template <int PREC, int NC>
 struct SmemTC {
-  DpModelImageTC M;
-  __align__(16) unsigned char ping[kPieces][kPingBytes];  // [piece]  z (24) / a1 (60) / dL/dh1 (60)
-  __align__(16) unsigned char pong[kPieces][kPongBytes];  // [piece]  a0 (40) / dL/dy (92) / dL/dh0 (40)
+  static constexpr int NP = PREC ? 2 : 3;  // pieces
+  // the first NP pieces of the model image (weights are its last member, see DpModelImageTC)
+  __align__(16) unsigned char model[DP_TC_IMAGE_BYTES(NP)];
+  __align__(16) unsigned char ping[NP][Geo<NC>::kPingBytes];  // [piece]  z (24) / a1 (60) / dL/dh1 (60)
+  __align__(16) unsigned char pong[NP][Geo<NC>::kPongBytes];  // [piece]  a0 (40) / dL/dy (92) / dL/dh0 (40)
   __align__(16) float ybuf[NC][96];                 // y, then dL/dy in place (fp32, one row per clip)
   float zgrad[NC][25];                              // dL/dz from the decoder (fp32)
   float bscale[NC];                                 // fp16 path: 1 / (per-clip power-of-two scale of dL/dy)
   __align__(16) ClipTrackers trk[NC][32];
+  // per-clip optimiser state lives here, not in registers: the packed kinematics pass needs the register file
+  __align__(16) float2 st[NC][5][DP_L / 2];         // [ST_Z latent | ST_TL target latent | ST_M, ST_V Adam moments | ST_ZLAST]
+  __align__(16) float groot[NC][4];                 // previous world root rotation g (wxyz)
+  __align__(16) float2 fkscr[NC / 2][16];           // per clip pair: R_0, r, d parked between the two halves of the kinematics pass
+  double prev[NC];                                  // previous total loss (early stopping compares in double)
+  float loss[NC][3];                                // last evaluated lp, lr, lt
+  int iters[NC];
   uint64_t bar_w, bar_mma;
   uint32_t tmem_base;
+  __device__ __forceinline__ const DpModelImageTC& M() const { return *reinterpret_cast<const DpModelImageTC*>(model); }
 };
 
 template <bool ACC>
@@ -70,7 +91,7 @@ template <> struct Lay<2> { static constexpr int kin = 64, kout = 96; static con
 
 // the split products of one K step, smallest first
 template <int PREC>
-__device__ __forceinline__ void issue_terms(uint32_t tmem, const UmmaDescBase (&a)[kPieces], const UmmaDescBase (&b)[kPieces], uint32_t ao,
+__device__ __forceinline__ void issue_terms(uint32_t tmem, const UmmaDescBase (&a)[kMaxPieces], const UmmaDescBase (&b)[kMaxPieces], uint32_t ao,
                                             uint32_t bo, uint32_t idesc, bool first) {
   if (PREC == 0) {  // (3,1) (2,2) (1,3) | (2,1) (1,2) | (1,1)
     if (first) umma_f16_c<false>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
@@ -87,15 +108,17 @@ __device__ __forceinline__ void issue_terms(uint32_t tmem, const UmmaDescBase (&
 }
 
 // forward layer L: A = W_L (K-major: LBO 128 between input 8-groups, SBO between output-row 8-groups)
-template <int L, int PREC>
-__device__ __forceinline__ void issue_fwd(const SmemTC& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
+template <int L, int PREC, int NC>
+__device__ __forceinline__ void issue_fwd(const SmemTC<PREC, NC>& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
+  constexpr uint32_t kB_LBO = Geo<NC>::kB_LBO;
+  constexpr int NP = SmemTC<PREC, NC>::NP;
   constexpr uint32_t sbo = 128 * (Lay<L>::kin / 8);
   constexpr uint32_t fmt = PREC ? 0u : 1u;  // kind::f16 operand format: 0 = fp16, 1 = bf16
   constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);  // B MN-major
-  UmmaDescBase a[kPieces], b[kPieces];
+  UmmaDescBase a[kMaxPieces], b[kMaxPieces];
 #pragma unroll
-  for (int p = 0; p < kPieces; ++p) {
-    a[p] = umma_desc_base(smem_u32(S.M.w[p]) + Lay<L>::off, 128, sbo);
+  for (int p = 0; p < NP; ++p) {
+    a[p] = umma_desc_base(smem_u32(S.M().w[p]) + Lay<L>::off, 128, sbo);
     b[p] = umma_desc_base(smem_u32(src) + p * piece_stride, kB_LBO, kB_SBO);
   }
 #pragma unroll
@@ -105,15 +128,17 @@ __device__ __forceinline__ void issue_fwd(const SmemTC& S, uint32_t tmem, const 
   }
 }
 // backward of layer L: the SAME weight image read MN-major (M = inputs, K = outputs): LBO / SBO swap roles
-template <int L, int PREC>
-__device__ __forceinline__ void issue_bwd(const SmemTC& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
+template <int L, int PREC, int NC>
+__device__ __forceinline__ void issue_bwd(const SmemTC<PREC, NC>& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
+  constexpr uint32_t kB_LBO = Geo<NC>::kB_LBO;
+  constexpr int NP = SmemTC<PREC, NC>::NP;
   constexpr uint32_t wsbo = 128 * (Lay<L>::kin / 8);
   constexpr uint32_t fmt = PREC ? 0u : 1u;
   constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
-  UmmaDescBase a[kPieces], b[kPieces];
+  UmmaDescBase a[kMaxPieces], b[kMaxPieces];
 #pragma unroll
-  for (int p = 0; p < kPieces; ++p) {
-    a[p] = umma_desc_base(smem_u32(S.M.w[p]) + Lay<L>::off, wsbo, 128);
+  for (int p = 0; p < NP; ++p) {
+    a[p] = umma_desc_base(smem_u32(S.M().w[p]) + Lay<L>::off, wsbo, 128);
     b[p] = umma_desc_base(smem_u32(src) + p * piece_stride, kB_LBO, kB_SBO);
   }
 #pragma unroll
@@ -136,12 +161,13 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
 __device__ __forceinline__ void unpack_f16x2(uint32_t p, float& lo_elem, float& hi_elem) {
   asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo_elem), "=f"(hi_elem) : "r"(p));
 }
-// 16 fp32 values (feature k, clips 16*half .. +15) -> split pieces in an MN-major activation image
-template <int PREC>
-__device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_stride, int k, int half, const float (&v)[16]) {
-  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (2 * half) * kB_SBO;
+// EC fp32 values (feature k, clips EC*half .. +EC-1) -> split pieces in an MN-major activation image
+template <int PREC, int NC>
+__device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_stride, int k, int half, const float (&v)[Geo<NC>::EC]) {
+  constexpr int EC = Geo<NC>::EC;
+  unsigned char* dst = img + (k >> 3) * Geo<NC>::kB_LBO + (k & 7) * 16 + ((EC / 8) * half) * kB_SBO;
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < EC / 8; ++g) {
     uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -165,9 +191,9 @@ __device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_
   }
 }
 // a single fp32 value (feature k, clip n) -> its pieces (used by the Adam lanes for the latent)
-template <int PREC>
+template <int PREC, int NC>
 __device__ __forceinline__ void store_piece_scalar(unsigned char* img, uint32_t piece_stride, int k, int n, float x) {
-  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (n >> 3) * kB_SBO + (n & 7) * 2;
+  unsigned char* dst = img + (k >> 3) * Geo<NC>::kB_LBO + (k & 7) * 16 + (n >> 3) * kB_SBO + (n & 7) * 2;
   if (PREC == 0) {
     const uint32_t p = pack_bf16x2(x, 0.0f);
     const float r = x - __uint_as_float(p << 16);
@@ -187,22 +213,24 @@ __device__ __forceinline__ void store_piece_scalar(unsigned char* img, uint32_t 
   }
 }
 
+template <int PREC, int NC>
 struct Ctx {
-  SmemTC* S;
+  SmemTC<PREC, NC>* S;
   uint32_t tmem;
   int warp, lane;
   uint32_t phase;  // parity of the next MMA completion
 };
 
 // one dense layer on the tensor pipe + its epilogue; every thread of the CTA calls this (ends with __syncthreads)
-template <int L, bool FWD, int PREC, class Epi>
-__device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
-  SmemTC& S = *c.S;
-  if (c.warp == kIssueWarp) {
+template <int L, bool FWD, int PREC, int NC, class Epi>
+__device__ __forceinline__ void tc_layer(Ctx<PREC, NC>& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
+  SmemTC<PREC, NC>& S = *c.S;
+  constexpr int EC = Geo<NC>::EC;
+  if (c.warp == Geo<NC>::kIssueWarp) {
     tc_fence_after();
     if (elect_one()) {
-      if (FWD) issue_fwd<L, PREC>(S, c.tmem, src, src_stride);
-      else issue_bwd<L, PREC>(S, c.tmem, src, src_stride);
+      if (FWD) issue_fwd<L, PREC, NC>(S, c.tmem, src, src_stride);
+      else issue_bwd<L, PREC, NC>(S, c.tmem, src, src_stride);
       umma_commit(&S.bar_mma);
     }
     __syncwarp();
@@ -212,8 +240,9 @@ __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint3
     if (quarter * 32 < out_rows) {
       mbar_wait(&S.bar_mma, c.phase);
       tc_fence_after();
-      float v[16];
-      tmem_ld16(c.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(16 * half), v);
+      float v[EC];
+      if constexpr (EC == 16) tmem_ld16(c.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(EC * half), reinterpret_cast<float (&)[16]>(v));
+      else tmem_ld8(c.tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(EC * half), reinterpret_cast<float (&)[8]>(v));
       tmem_ld_wait();
       const int k = quarter * 32 + c.lane;
       if (k < out_rows) epi(k, half, v);
@@ -225,39 +254,42 @@ __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint3
   __syncthreads();
 }
 
-template <int PREC>
-__global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __grid_constant__ DpFrameArgs A) {
+template <int PREC, int NC>
+__global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_frame_tc_kernel(const __grid_constant__ DpFrameArgs A) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  SmemTC& S = *reinterpret_cast<SmemTC*>(smem_raw);
-  const DpModelImageTC& M = S.M;
+  using Smem = SmemTC<PREC, NC>;
+  constexpr int kWarps = Geo<NC>::kWarps, EC = Geo<NC>::EC;
+  constexpr uint32_t kPingBytes = Geo<NC>::kPingBytes, kPongBytes = Geo<NC>::kPongBytes;
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const DpModelImageTC& M = S.M();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(&S.bar_w, 1);
     mbar_init(&S.bar_mma, 1);
     fence_barrier_init();
   }
-  if (warp == kIssueWarp) tmem_alloc(&S.tmem_base, 32);
+  if (warp == Geo<NC>::kIssueWarp) tmem_alloc(&S.tmem_base, 32);
   for (int i = threadIdx.x; i < (int)(sizeof(S.ping) + sizeof(S.pong)) / 16; i += kWarps * 32)
     reinterpret_cast<uint4*>(&S.ping[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);  // ping and pong are contiguous; pad rows must stay finite
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (threadIdx.x == 0) {
-    constexpr uint32_t kBytes = (uint32_t)sizeof(DpModelImageTC);
+    constexpr uint32_t kBytes = (uint32_t)sizeof(S.model);
     constexpr uint32_t kChunk = 32768;
     mbar_expect_tx(&S.bar_w, kBytes);
     for (uint32_t o = 0; o < kBytes; o += kChunk)
-      tma_bulk_g2s(reinterpret_cast<unsigned char*>(&S.M) + o, reinterpret_cast<const unsigned char*>(PREC ? A.model_tc16 : A.model_tc) + o, min(kChunk, kBytes - o), &S.bar_w);
+      tma_bulk_g2s(S.model + o, reinterpret_cast<const unsigned char*>(PREC ? A.model_tc16 : A.model_tc) + o, min(kChunk, kBytes - o), &S.bar_w);
   }
-  Ctx ctx{&S, S.tmem_base, warp, lane, 0u};
+  Ctx<PREC, NC> ctx{&S, S.tmem_base, warp, lane, 0u};
   constexpr int CPW = NC / kWarps;  // 2 clips per warp in the per-clip phases
   const int n0 = warp * CPW;        // local clip index (tile column) of this warp's first clip
   const int clip0 = blockIdx.x * A.clips_per_cta + n0;
 
   // ---- per-clip frame inputs (same as the fp32 kernel)
+  static_assert(CPW == 2, "the kinematics pass packs exactly two clips per warp");
   bool valid[CPW];
-  float g[CPW][4], inv3e[CPW], lrot9e[CPW];
-  float2 z[CPW], tl[CPW], am[CPW], av[CPW], zlast[CPW];
+  float inv3e[CPW], lrot9e[CPW];
 #pragma unroll
   for (int c = 0; c < CPW; ++c) {
     const int clip = clip0 + c;
@@ -266,15 +298,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
     const int ne = A.n_ee ? A.n_ee[cc] : A.ee_stride;
     inv3e[c] = 1.0f / (3.0f * (float)ne);
     lrot9e[c] = A.lambda_rot / (9.0f * (float)ne);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) g[c][i] = A.grot[cc * 4 + i];
-    z[c] = tl[c] = make_float2(0.f, 0.f);
+    if (lane < 4) S.groot[n0 + c][lane] = A.grot[cc * 4 + lane];
+    float2 z = make_float2(0.f, 0.f), tl = z;
     if (lane < DP_L / 2 && valid[c]) {
-      z[c] = reinterpret_cast<const float2*>(A.latent + (size_t)cc * DP_L)[lane];
-      tl[c] = reinterpret_cast<const float2*>(A.target_buf + ((size_t)cc * A.target_rows + A.target_index) * DP_L)[lane];
+      z = reinterpret_cast<const float2*>(A.latent + (size_t)cc * DP_L)[lane];
+      tl = reinterpret_cast<const float2*>(A.target_buf + ((size_t)cc * A.target_rows + A.target_index) * DP_L)[lane];
     }
-    am[c] = av[c] = make_float2(0.f, 0.f);
-    zlast[c] = z[c];
+    if (lane < DP_L / 2) {
+      S.st[n0 + c][ST_Z][lane] = z;
+      S.st[n0 + c][ST_TL][lane] = tl;
+      S.st[n0 + c][ST_M][lane] = make_float2(0.f, 0.f);
+      S.st[n0 + c][ST_V][lane] = make_float2(0.f, 0.f);
+      S.st[n0 + c][ST_ZLAST][lane] = z;
+    }
+    if (lane == 0) {
+      S.prev[n0 + c] = 10000000.0;
+      S.loss[n0 + c][0] = S.loss[n0 + c][1] = S.loss[n0 + c][2] = __int_as_float(0x7f800000);
+      S.iters[n0 + c] = 0;
+    }
     ClipTrackers row;
     row.pw = row.r0 = row.r1 = row.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int32_t* jn = A.joints + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride);
@@ -291,189 +332,213 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
     }
     S.trk[n0 + c][lane] = row;
     if (lane < DP_L / 2) {  // latent -> B operand of the first layer
-      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z[c].x);
-      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z[c].y);
+      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z.x);
+      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z.y);
     }
   }
+  const P2 inv3e2 = mk2(inv3e[0], inv3e[1]), lrot9e2 = mk2(lrot9e[0], lrot9e[1]);
+  __syncwarp();
   fence_proxy_async();
   mbar_wait(&S.bar_w, 0);  // model image (weights, statistics, skeleton tables) has landed
 
   constexpr float wsc = PREC ? 1.0f / kWScale : 1.0f;  // undoes the weight-image scaling of the fp16 path
   unsigned neg0 = 0, neg1 = 0;  // LeakyReLU slope bits of (feature k, this thread's 16 clips) for the backward pass
   auto forward = [&]() {
-    tc_layer<0, true, PREC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[16]) {
+    tc_layer<0, true, PREC, NC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b0[k];
       neg0 = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] = fmaf(v[i], wsc, b); neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces<PREC>(&S.pong[0][0], kPongBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) { v[i] = fmaf(v[i], wsc, b); neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces<PREC, NC>(&S.pong[0][0], kPongBytes, k, half, v);
     });
-    tc_layer<1, true, PREC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[16]) {
+    tc_layer<1, true, PREC, NC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b1[k];
       neg1 = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] = fmaf(v[i], wsc, b); neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces<PREC>(&S.ping[0][0], kPingBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) { v[i] = fmaf(v[i], wsc, b); neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces<PREC, NC>(&S.ping[0][0], kPingBytes, k, half, v);
     });
-    tc_layer<2, true, PREC>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[16]) {
+    tc_layer<2, true, PREC, NC>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b2[k];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) S.ybuf[16 * half + i][k] = fmaf(v[i], wsc, b);
+      for (int i = 0; i < EC; ++i) S.ybuf[EC * half + i][k] = fmaf(v[i], wsc, b);
     });
   };
   auto backward = [&]() {
     if (warp < kEpiWarps) {  // dL/dy (fp32 rows written by the kinematics warps) -> B operand
       const int k = (warp & 3) * 32 + lane, half = warp >> 2;
       if (k < DP_Y) {
-        float v[16];
+        float v[EC];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = S.ybuf[16 * half + i][k];
-        store_pieces<PREC>(&S.pong[0][0], kPongBytes, k, half, v);
+        for (int i = 0; i < EC; ++i) v[i] = S.ybuf[EC * half + i][k];
+        store_pieces<PREC, NC>(&S.pong[0][0], kPongBytes, k, half, v);
       }
       fence_proxy_async();
     }
     __syncthreads();
-    tc_layer<2, false, PREC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[16]) {
+    tc_layer<2, false, PREC, NC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
-      store_pieces<PREC>(&S.ping[0][0], kPingBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
+      store_pieces<PREC, NC>(&S.ping[0][0], kPingBytes, k, half, v);
     });
-    tc_layer<1, false, PREC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[16]) {
+    tc_layer<1, false, PREC, NC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f * wsc : wsc;
-      store_pieces<PREC>(&S.pong[0][0], kPongBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f * wsc : wsc;
+      store_pieces<PREC, NC>(&S.pong[0][0], kPongBytes, k, half, v);
     });
-    tc_layer<0, false, PREC>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[16]) {
+    tc_layer<0, false, PREC, NC>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) S.zgrad[16 * half + i][k] = v[i] * (PREC ? wsc * S.bscale[16 * half + i] : 1.0f);
+      for (int i = 0; i < EC; ++i) S.zgrad[EC * half + i][k] = v[i] * (PREC ? wsc * S.bscale[EC * half + i] : 1.0f);
     });
   };
 
   // ---- optimisation loop (drag_pose.py:296-355)
-  bool active[CPW];
-  double prev[CPW], incr[CPW];
-  float lp[CPW], lr[CPW], lt[CPW];
-  int iters[CPW];
-#pragma unroll
-  for (int c = 0; c < CPW; ++c) {
-    active[c] = valid[c];
-    prev[c] = 10000000.0;
-    incr[c] = 1.0;
-    lp[c] = lr[c] = lt[c] = __int_as_float(0x7f800000);
-    iters[c] = 0;
-  }
+  // early-stop test of the NEXT iteration, evaluated right after each Adam step (initial losses are +inf, initial increment 1)
+  bool active[CPW] = {valid[0] && 1.0 > A.min_incr, valid[1] && 1.0 > A.min_incr};
   const float lt_scale = A.lambda_t * (1.0f / (float)DP_L);
-  for (int it = 0; it < A.max_iter; ++it) {
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < CPW; ++c) {
-      active[c] = active[c] && ((double)lp[c] > A.eps_pos || (double)lr[c] > A.eps_rot) && (incr[c] > A.min_incr);
-      any = any || active[c];
+  const bool clocked = A.phase_cycles != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tick = clocked ? clock64() : 0;
+  auto phase_done = [&](int i) {
+    if (clocked) {
+      const long long now = clock64();
+      A.phase_cycles[i] += (unsigned long long)(now - tick);
+      tick = now;
     }
-    if (!__syncthreads_or(any ? 1 : 0)) break;  // also publishes the latent pieces written by the Adam lanes
-#pragma unroll
-    for (int c = 0; c < CPW; ++c)
-      if (active[c]) zlast[c] = z[c];
+  };
+  for (int it = 0; it < A.max_iter; ++it) {
+    if (!__syncthreads_or((active[0] || active[1]) ? 1 : 0)) break;  // also publishes the latent pieces written by the Adam lanes
+    if (lane == 0) {  // the Adam phase reads two table entries: pull their lines into L1 now instead of stalling there
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.adam_tab + it));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.adam_tab + A.max_iter + it));
+    }
+    phase_done(3);
     forward();
-    float nlp[CPW], nlr[CPW];
+    phase_done(0);
+    float nlp[CPW] = {0.f, 0.f}, nlr[CPW] = {0.f, 0.f};
+    if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
+      const FkOut2 o = fk_loss2<true, false>(M, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0], &S.trk[n0 + 1][0], &S.groot[n0][0], &S.fkscr[warp][0], inv3e2,
+                                             lrot9e2, lane, nullptr, nullptr, nullptr, nullptr);
+      phase_done(4);
+      nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x;
+      nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y;
+      if (PREC) {  // bring the largest |dL/dy| component of each clip into [16, 32) with an exact power of two
+        float4* row0 = reinterpret_cast<float4*>(&S.ybuf[n0][0]);
+        float4* row1 = reinterpret_cast<float4*>(&S.ybuf[n0 + 1][0]);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 y0 = lane < 23 ? row0[lane] : zero4, y1 = lane < 23 ? row1[lane] : zero4;
+        float mx0 = fmaxf(fmaxf(fabsf(y0.x), fabsf(y0.y)), fmaxf(fabsf(y0.z), fabsf(y0.w)));
+        float mx1 = fmaxf(fmaxf(fabsf(y1.x), fabsf(y1.y)), fmaxf(fabsf(y1.z), fabsf(y1.w)));
 #pragma unroll
-    for (int c = 0; c < CPW; ++c) {
-      nlp[c] = lp[c];
-      nlr[c] = lr[c];
-      if (active[c]) {
-        const FkOut o = fk_loss<true, false>(M, &S.ybuf[n0 + c][0], &S.trk[n0 + c][0], g[c], inv3e[c], lrot9e[c], lane, nullptr, nullptr,
-                                             nullptr, nullptr);
-        nlp[c] = o.lp;
-        nlr[c] = o.lr;
-        if (PREC) {  // bring the largest |dL/dy| component of this clip into [16, 32) with an exact power of two
-          float4* row = reinterpret_cast<float4*>(&S.ybuf[n0 + c][0]);
-          float4 yb = lane < 23 ? row[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-          float mx = fmaxf(fmaxf(fabsf(yb.x), fabsf(yb.y)), fmaxf(fabsf(yb.z), fabsf(yb.w)));
-#pragma unroll
-          for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
-          int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;  // floor(log2(mx)) for normal mx
-          e = mx > 0.f ? max(-100, min(100, e)) : 4;
-          const float sc = __uint_as_float((uint32_t)(127 + 4 - e) << 23), isc = __uint_as_float((uint32_t)(127 - 4 + e) << 23);
-          if (lane < 23) row[lane] = make_float4(yb.x * sc, yb.y * sc, yb.z * sc, yb.w * sc);
-          if (lane == 0) S.bscale[n0 + c] = isc;
-          __syncwarp();
+        for (int sh = 16; sh > 0; sh >>= 1) {
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, sh));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, sh));
+        }
+        int e0 = (int)((__float_as_uint(mx0) >> 23) & 0xffu) - 127, e1 = (int)((__float_as_uint(mx1) >> 23) & 0xffu) - 127;  // floor(log2)
+        e0 = mx0 > 0.f ? max(-100, min(100, e0)) : 4;
+        e1 = mx1 > 0.f ? max(-100, min(100, e1)) : 4;
+        const float sc0 = __uint_as_float((uint32_t)(127 + 4 - e0) << 23), sc1 = __uint_as_float((uint32_t)(127 + 4 - e1) << 23);
+        if (lane < 23) {
+          row0[lane] = make_float4(y0.x * sc0, y0.y * sc0, y0.z * sc0, y0.w * sc0);
+          row1[lane] = make_float4(y1.x * sc1, y1.y * sc1, y1.z * sc1, y1.w * sc1);
+        }
+        if (lane == 0) {
+          S.bscale[n0] = __uint_as_float((uint32_t)(127 - 4 + e0) << 23);
+          S.bscale[n0 + 1] = __uint_as_float((uint32_t)(127 - 4 + e1) << 23);
         }
       }
     }
     __syncthreads();
+    phase_done(1);
     backward();
+    phase_done(2);
     const float step_size = A.adam_tab[it], inv_bc2s = A.adam_tab[A.max_iter + it];  // lr/(1-b1^k), 1/sqrt(1-b2^k)
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
-      const float dx = z[c].x - tl[c].x, dy = z[c].y - tl[c].y;
-      float s = (lane < DP_L / 2) ? fmaf(dx, dx, dy * dy) : 0.0f;
-      s = warp_sum(s);
-      const float nlt = s * lt_scale;
+      const int n = n0 + c;
+      float2 z = make_float2(0.f, 0.f), tl = z;
+      if (lane < DP_L / 2) { z = S.st[n][ST_Z][lane]; tl = S.st[n][ST_TL][lane]; }
+      const float dx = z.x - tl.x, dy = z.y - tl.y;
+      const float nlt = warp_sum(fmaf(dx, dx, dy * dy)) * lt_scale;
       float gx = 0.f, gy = 0.f;
       if (lane < DP_L / 2) {
-        gx = fmaf(2.0f * lt_scale, dx, S.zgrad[n0 + c][2 * lane]);
-        gy = fmaf(2.0f * lt_scale, dy, S.zgrad[n0 + c][2 * lane + 1]);
+        gx = fmaf(2.0f * lt_scale, dx, S.zgrad[n][2 * lane]);
+        gy = fmaf(2.0f * lt_scale, dy, S.zgrad[n][2 * lane + 1]);
       }
       if (A.trace && active[c]) {
         float* row = A.trace + ((size_t)(clip0 + c) * A.trace_iters + it) * 52;
         if (lane < DP_L / 2) {
-          reinterpret_cast<float2*>(row)[lane] = z[c];
+          reinterpret_cast<float2*>(row)[lane] = z;
           reinterpret_cast<float2*>(row + DP_L)[lane] = make_float2(gx, gy);
         }
         if (lane == 0) { row[48] = nlp[c]; row[49] = nlr[c]; row[50] = nlt; row[51] = 1.0f; }
       }
       if (A.eval_only) {
         if (active[c] && lane < DP_L / 2) reinterpret_cast<float2*>(A.eval_grad + (size_t)(clip0 + c) * DP_L)[lane] = make_float2(gx, gy);
-      } else if (active[c]) {
-        am[c].x = fmaf(0.1f, gx - am[c].x, am[c].x);
-        am[c].y = fmaf(0.1f, gy - am[c].y, am[c].y);
-        av[c].x = av[c].x * 0.999f + (0.001f * gx) * gx;
-        av[c].y = av[c].y * 0.999f + (0.001f * gy) * gy;
-        z[c].x += __fdividef(-step_size * am[c].x, fmaf(fast_sqrt(av[c].x), inv_bc2s, 1e-8f));
-        z[c].y += __fdividef(-step_size * am[c].y, fmaf(fast_sqrt(av[c].y), inv_bc2s, 1e-8f));
+      } else if (active[c] && lane < DP_L / 2) {
+        float2 am = S.st[n][ST_M][lane], av = S.st[n][ST_V][lane];
+        am.x = fmaf(0.1f, gx - am.x, am.x);
+        am.y = fmaf(0.1f, gy - am.y, am.y);
+        av.x = av.x * 0.999f + (0.001f * gx) * gx;
+        av.y = av.y * 0.999f + (0.001f * gy) * gy;
+        S.st[n][ST_M][lane] = am;
+        S.st[n][ST_V][lane] = av;
+        S.st[n][ST_ZLAST][lane] = z;  // the frame's output is decoded from the last EVALUATED latent
+        z.x += __fdividef(-step_size * am.x, fmaf(fast_sqrt(av.x), inv_bc2s, 1e-8f));
+        z.y += __fdividef(-step_size * am.y, fmaf(fast_sqrt(av.y), inv_bc2s, 1e-8f));
+        S.st[n][ST_Z][lane] = z;
       }
       // the latent rows of the ping image were overwritten by the a1 / dL/dh1 pieces of this iteration: restore them for
       // EVERY clip (stopped and padding clips included) so that no column ever feeds back on its own garbage -- a
       // non-finite value in a K-padding row would poison the column through 0 x NaN
       if (lane < DP_L / 2) {
-        store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z[c].x);
-        store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z[c].y);
+        store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane, n, z.x);
+        store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n, z.y);
       }
       if (active[c]) {
-        lp[c] = nlp[c];
-        lr[c] = nlr[c];
-        lt[c] = nlt;
         const float total = (nlp[c] + nlr[c]) + nlt;
-        incr[c] = prev[c] - (double)total;
-        prev[c] = (double)total;
-        iters[c] += 1;
+        const double incr = S.prev[n] - (double)total;
+        __syncwarp();
+        if (lane == 0) {
+          S.prev[n] = (double)total;
+          S.loss[n][0] = nlp[c]; S.loss[n][1] = nlr[c]; S.loss[n][2] = nlt;
+          S.iters[n] += 1;
+        }
+        active[c] = ((double)nlp[c] > A.eps_pos || (double)nlr[c] > A.eps_rot) && (incr > A.min_incr);
       }
     }
     fence_proxy_async();
   }
 
   // ---- frame epilogue (drag_pose.py:369-414) from the LAST EVALUATED latent (pre-step)
+  __syncwarp();
 #pragma unroll
   for (int c = 0; c < CPW; ++c)
     if (lane < DP_L / 2) {
-      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zlast[c].x);
-      store_piece_scalar<PREC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zlast[c].y);
+      const float2 zl = S.st[n0 + c][ST_ZLAST][lane];
+      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zl.x);
+      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zl.y);
     }
   fence_proxy_async();
   __syncthreads();
   forward();
+  P2 q2[4], r2[4], p2[3], d2[3];
+  if (valid[0] || valid[1])
+    fk_loss2<false, true>(M, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0], &S.trk[n0 + 1][0], &S.groot[n0][0], &S.fkscr[warp][0], inv3e2, lrot9e2, lane, q2, r2, p2, d2);
 #pragma unroll
   for (int c = 0; c < CPW; ++c) {
     if (!valid[c]) continue;
     const int clip = clip0 + c;
     float q[4], r[4], p[3], d[3];
-    fk_loss<false, true>(M, &S.ybuf[n0 + c][0], &S.trk[n0 + c][0], g[c], inv3e[c], lrot9e[c], lane, q, r, p, d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q[i] = c ? q2[i].v.y : q2[i].v.x; r[i] = c ? r2[i].v.y : r2[i].v.x; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p[i] = c ? p2[i].v.y : p2[i].v.x; d[i] = c ? d2[i].v.y : d2[i].v.x; }
     if (A.eval_only) {
       if (lane < DP_J && A.eval_pos) {
         float* o = A.eval_pos + ((size_t)clip * DP_J + lane) * 3;
         o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
       }
-      if (lane == 0 && A.out_losses) { A.out_losses[clip * 3] = lp[c]; A.out_losses[clip * 3 + 1] = lr[c]; A.out_losses[clip * 3 + 2] = lt[c]; }
+      if (lane < 3 && A.out_losses) A.out_losses[clip * 3 + lane] = S.loss[n0 + c][lane];
       continue;
     }
     float p0[3], gp[3], adj[3] = {0.f, 0.f, 0.f};
@@ -495,8 +560,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
     const int hs = M.height_slot[lane];
     if (hs >= 0) A.height_buf[((size_t)clip * DP_PAST + A.ring_head) * DP_NH + hs] = p[1] + gp[1];
     if (lane < DP_L / 2) {
-      reinterpret_cast<float2*>(A.latent_buf + ((size_t)clip * DP_PAST + A.ring_head) * DP_L)[lane] = zlast[c];
-      reinterpret_cast<float2*>(A.latent + (size_t)clip * DP_L)[lane] = z[c];
+      reinterpret_cast<float2*>(A.latent_buf + ((size_t)clip * DP_PAST + A.ring_head) * DP_L)[lane] = S.st[n0 + c][ST_ZLAST][lane];
+      reinterpret_cast<float2*>(A.latent + (size_t)clip * DP_L)[lane] = S.st[n0 + c][ST_Z][lane];
     }
     if (lane == 0) {
 #pragma unroll
@@ -507,10 +572,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) A.grot[clip * 4 + i] = r[i];
-      A.out_iters[clip] = iters[c];
-      A.out_losses[clip * 3] = lp[c];
-      A.out_losses[clip * 3 + 1] = lr[c];
-      A.out_losses[clip * 3 + 2] = lt[c];
+      A.out_iters[clip] = S.iters[n0 + c];
+      A.out_losses[clip * 3] = S.loss[n0 + c][0];
+      A.out_losses[clip * 3 + 1] = S.loss[n0 + c][1];
+      A.out_losses[clip * 3 + 2] = S.loss[n0 + c][2];
     }
     if (lane < DP_J) {
       const float4 mq = reinterpret_cast<const float4*>(M.mean_q)[lane];
@@ -522,28 +587,30 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kIssueWarp) tmem_dealloc(ctx.tmem, 32);
+  if (warp == Geo<NC>::kIssueWarp) tmem_dealloc(ctx.tmem, 32);
 }
 
 }  // namespace
 
 cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem = sizeof(SmemTC) + 1024;
+  const size_t smem32 = sizeof(SmemTC<0, 32>) + 1024, smem16 = sizeof(SmemTC<1, 16>) + 1024;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dp_frame_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<0, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dp_frame_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  // 4096 clips: 28 real clips per 32-column tile -> 147 CTAs, one per SM, instead of 128 CTAs of 32
+  // spread the clips over every CTA slot of the device: 4096 clips -> 14 real clips per 16-column tile on 293 of the 296
+  // slots (fp16x2, two CTAs per SM), or 28 per 32-column tile on 147 SMs (bf16x3)
   DpFrameArgs a = args;
-  int cpc = (args.n_clips + num_sms - 1) / num_sms;
-  cpc = cpc < 1 ? 1 : (cpc > NC ? NC : cpc);
-  if (args.n_clips > num_sms * NC) cpc = NC;  // several waves anyway: use full tiles
+  const int nc = fp16 ? 16 : 32, slots = fp16 ? 2 * num_sms : num_sms;
+  int cpc = (args.n_clips + slots - 1) / slots;
+  cpc = cpc < 1 ? 1 : (cpc > nc ? nc : cpc);
+  if (args.n_clips > slots * nc) cpc = nc;  // several waves anyway: use full tiles
   a.clips_per_cta = cpc;
   const int grid = (args.n_clips + cpc - 1) / cpc;
-  if (fp16) dp_frame_tc_kernel<1><<<grid, kWarps * 32, smem, stream>>>(a);
-  else dp_frame_tc_kernel<0><<<grid, kWarps * 32, smem, stream>>>(a);
+  if (fp16) dp_frame_tc_kernel<1, 16><<<grid, Geo<16>::kWarps * 32, smem16, stream>>>(a);
+  else dp_frame_tc_kernel<0, 32><<<grid, Geo<32>::kWarps * 32, smem32, stream>>>(a);
   return cudaGetLastError();
 }

@@ -232,6 +232,13 @@ class BatchedDragPose:
     def set_profiling(self, on=True):
         _lib.check(self.lib.dp_engine_set_profiling(self.h, int(on)))
 
+    def phase_cycles(self):
+        """Phase clock of CTA 0 of the tcgen05 frame kernel since set_profiling(2): cycles in [decoder forward, scaling + barrier,
+        decoder backward, Adam, kinematics pass, 0, 0, 0] (include/dp_engine.h)."""
+        out = (C.c_ulonglong * 8)()
+        _lib.check(self.lib.dp_engine_get_phase_cycles(self.h, out))
+        return [int(v) for v in out]
+
     def profile(self):
         """(ms in the temporal predictor, ms in the frame kernel, frames) since set_profiling(True)."""
         a, b, n = C.c_double(0), C.c_double(0), C.c_longlong(0)

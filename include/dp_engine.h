@@ -159,15 +159,20 @@ int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
  * dp_run_params.decoder_path = 0 picks tcgen05 for batches >= 1024 clips and fp32 below. */
 int dp_engine_last_decoder_path(const dp_engine* e);
 
-/* Feed-forward GEMMs of the predictor: 0 = tcgen05 tensor cores, 3xTF32 (default);
+/* Feed-forward GEMMs of the predictor: 0 = tcgen05 tensor cores, fp16x2 split products (default);
  * 1 = fp32 CUDA-core kernel (kept as an on-device cross-check, same results to ~1e-6). */
 int dp_engine_set_predictor_path(dp_engine* e, int path);
 
 /* Device-side timing of the two kernel groups, measured with CUDA events on the
  * launching stream: accumulated milliseconds of the temporal predictor and of the
- * persistent frame kernel over the frames run since profiling was (re)enabled. */
+ * persistent frame kernel over the frames run since profiling was (re)enabled.
+ * enable = 2 additionally runs the phase clock read by dp_engine_get_phase_cycles. */
 int dp_engine_set_profiling(dp_engine* e, int enable);
 int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double* ms_frame_kernel, long long* n_frames);
+/* Phase clock of CTA 0 of the tcgen05 frame kernel (device clock64, accumulated since profiling level 2 was enabled),
+ * 8 counters: [0] decoder forward, [1] dL/dy scaling + block barrier after the kinematics, [2] decoder backward,
+ * [3] Adam + bookkeeping + loop barrier, [4] kinematics + loss + adjoint pass, [5..7] reserved (0). */
+int dp_engine_get_phase_cycles(dp_engine* e, unsigned long long* cycles8);
 
 /* Number of kernels launched by this engine since creation (bench "gpu_launches"). */
 long long dp_engine_launch_count(const dp_engine* e);
