@@ -36,7 +36,7 @@ struct dp_engine {
   DpModelImageTC* d_model_tc = nullptr;
   DpModelImageTC* d_model_tc16 = nullptr;
   float* d_tblob = nullptr;
-  unsigned char* d_fftiles = nullptr;  // pre-tiled 3xTF32 FF weights of the 6 predictor layers
+  unsigned char* d_fftiles = nullptr;  // pre-tiled fp16x2 tensor-core weight images of the predictor (DP_TC_TILES_BYTES)
   int predictor_path = 0;              // 0 = tcgen05 FF (default), 1 = fp32 CUDA-core FF
   int last_path = 0;                   // decoder path of the last frame: 1 = fp32, 2 = tcgen05
   float *d_mu = nullptr, *d_sigma = nullptr;
@@ -296,10 +296,15 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
   CK(cudaMemcpy(e->d_mu, means_latent, DP_L * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->d_sigma, stds_latent, DP_L * 4, cudaMemcpyHostToDevice));
   {
-    std::vector<unsigned char> tiles((size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES);
+    std::vector<unsigned char> tiles(DP_TC_TILES_BYTES);
     for (int l = 0; l < TP_NENC + TP_NDEC; ++l) {
       const TpFF& f = l < TP_NENC ? e->tl.enc[l].ff : e->tl.dec[l - TP_NENC].ff;
       dp_ff_tc_pack(blob + f.w1, blob + f.b1, blob + f.w2, tiles.data() + (size_t)l * FFT_LAYER_BYTES);
+    }
+    for (int l = 0; l < TP_NENC; ++l) {
+      const TpAttn& a = e->tl.enc[l].sa;
+      dp_attn_tc_pack(blob + a.w_in, blob + a.b_in, blob + a.w_out, blob + a.b_out,
+                      tiles.data() + (size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES + (size_t)l * ATT_LAYER_BYTES);
     }
     if (!e->d_fftiles) CK(cudaMalloc(&e->d_fftiles, tiles.size()));
     CK(cudaMemcpy(e->d_fftiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));

@@ -377,7 +377,10 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
   for (int l = 0; l < TP_NENC; ++l) {
-    err = launch_mha(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2, B, st);
+    if (fftiles)
+      err = dp_attn_tc_launch(fftiles + (size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES + (size_t)l * ATT_LAYER_BYTES, blob, L.enc[l].n1, e, B, e2, st);
+    else
+      err = launch_mha(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2, B, st);
     if (err != cudaSuccess) return err;
     if (fftiles) {
       err = dp_ff_tc_launch(fftiles + (size_t)l * FFT_LAYER_BYTES, blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm, l == TP_NENC - 1, e2,

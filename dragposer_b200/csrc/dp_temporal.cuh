@@ -22,6 +22,8 @@
 #define FFT_HC 64                 // hidden units per tensor-core FF chunk
 #define FFT_CHUNK_BYTES 24832     // W1c pieces (2 x 6144 fp16) + b1c (256 fp32) + W2c pieces (2 x 6144 fp16)
 #define FFT_LAYER_BYTES ((TP_FF / FFT_HC) * FFT_CHUNK_BYTES)
+#define ATT_TILE_CLIPS 9           // whole clips per tensor-core attention tile (9 x 14 = 126 of 128 rows)
+#define ATT_LAYER_BYTES 37632      // W_in pieces (2 x 13824 fp16) + W_o pieces (2 x 4608 fp16) + b_in (576) + b_o (192)
 
 struct TpAttn {   // offsets (floats) into the blob
   size_t w_in;    // [48][144]  (q | k | v columns)
@@ -67,3 +69,19 @@ inline TpLayout tp_layout() {
   L.total = o;
   return L;
 }
+
+#ifdef __CUDACC__
+// LayerNorm of one 48-wide row held by one thread (eps 1e-5, torch nn.LayerNorm)
+__device__ __forceinline__ void ln48(float (&v)[TP_D], const float* __restrict__ w, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < TP_D; ++i) s += v[i];
+  const float mean = s * (1.0f / TP_D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < TP_D; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+  const float rstd = rsqrtf(q * (1.0f / TP_D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < TP_D; ++i) v[i] = v[i] * rstd * w[i] + b[i];
+}
+#endif

@@ -88,33 +88,6 @@ __device__ __forceinline__ void issue_mma2(const Smem& S, int stage, uint32_t tm
   }
 }
 
-__device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {  // lower 16 bits <- lo_elem (the even K index)
-  uint32_t p;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
-  return p;
-}
-// two fp32 values -> packed first pieces and packed second pieces
-__device__ __forceinline__ void split_h2(float a, float b, float& p1, float& p2) {
-  const uint32_t w = pack_h2(a, b);
-  float ha, hb;
-  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(ha), "=f"(hb) : "r"(w));
-  p1 = __uint_as_float(w);
-  p2 = __uint_as_float(pack_h2(a - ha, b - hb));
-}
-
-__device__ __forceinline__ void ln48(float (&v)[TP_D], const float* __restrict__ w, const float* __restrict__ b) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < TP_D; ++i) s += v[i];
-  const float mean = s * (1.0f / TP_D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < TP_D; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
-  const float rstd = rsqrtf(q * (1.0f / TP_D) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < TP_D; ++i) v[i] = v[i] * rstd * w[i] + b[i];
-}
-
 __device__ __forceinline__ void load_w1(Smem& S, const unsigned char* wtiles, int c) {
   const int st = c % kW1Stages;
   mbar_expect_tx(&S.w1full[st], kPart1);

@@ -152,6 +152,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])),
+               "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -188,4 +193,19 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
   hi = __uint_as_float(h);
   lo = x - hi;
+}
+
+// ---- fp16x2 split: x = p1 + p2 with p1 = fp16(x), p2 = fp16(x - p1); two values per 32-bit word (TS-mode A operand packing)
+__device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {  // lower 16 bits <- lo_elem (the even K index)
+  uint32_t p;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
+  return p;
+}
+// two fp32 values -> packed first pieces and packed second pieces
+__device__ __forceinline__ void split_h2(float a, float b, float& p1, float& p2) {
+  const uint32_t w = pack_h2(a, b);
+  float ha, hb;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(ha), "=f"(hb) : "r"(w));
+  p1 = __uint_as_float(w);
+  p2 = __uint_as_float(pack_h2(a - ha, b - hb));
 }
