@@ -241,6 +241,103 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
   if (warp == 8) tmem_dealloc(tmem, kT_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K | V projections of the encoder memory for the cross-attention of ALL decoder layers, computed once per predictor call
+// (the reference, and the CUDA-core kernel, redo them in every decoder layer of every autoregressive pass):
+//   KV_l[rows x 96] = memory[rows x 48] . [W_k | W_v]_l^T + b     l = 0..2, one 128-row tile per CTA, 27 MMAs, one commit.
+constexpr uint32_t kKvWBytes = 2 * TP_D * TP_D * 2;   // one fp16 image of [W_k | W_v] as B operand [N = 96][K = 48]
+constexpr uint32_t kKv_LBO = 128 * (2 * TP_D / 8);
+constexpr uint32_t kKvOffBias = TP_NDEC * 2 * kKvWBytes;
+static_assert(kKvOffBias + TP_NDEC * 2 * TP_D * 4 == KV_IMAGE_BYTES, "kv image size");
+constexpr uint32_t kT_KV = 48, kT_KV_COLS = 512;      // three 96-column accumulators after the X pieces
+
+struct SmemKv {
+  __align__(16) unsigned char w[KV_IMAGE_BYTES];
+  uint64_t bar_w, bar_mma;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tp_kv_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict__ x_g, int n_rows, float* __restrict__ kv_g) {
+  extern __shared__ __align__(1024) unsigned char raw[];
+  SmemKv& S = *reinterpret_cast<SmemKv*>(raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&S.bar_w, 1);
+    mbar_init(&S.bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&S.tmem_base, kT_KV_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+  if (warp == 8 && elect_one()) {
+    constexpr uint32_t kPart = 2 * kKvWBytes;  // one layer's two pieces
+    mbar_expect_tx(&S.bar_w, KV_IMAGE_BYTES);
+    for (int l = 0; l < TP_NDEC; ++l) tma_bulk_g2s(S.w + l * kPart, wimg + l * kPart, kPart, &S.bar_w);
+    tma_bulk_g2s(S.w + kKvOffBias, wimg + kKvOffBias, KV_IMAGE_BYTES - kKvOffBias, &S.bar_w);
+  }
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int m = (warp & 3) * 32 + lane, h = (warp >> 2) & 1;
+  const int row = blockIdx.x * kTM + m;
+  const bool valid = row < n_rows;
+  if (warp < 4) {
+    float p1[24], p2[24];
+#pragma unroll
+    for (int j = 0; j < TP_D; j += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) v = *reinterpret_cast<const float4*>(x_g + (size_t)row * TP_D + j);
+      split_h2(v.x, v.y, p1[j / 2], p2[j / 2]);
+      split_h2(v.z, v.w, p1[j / 2 + 1], p2[j / 2 + 1]);
+    }
+    tmem_st8(tmem + lane_base + kT_A1, reinterpret_cast<float (&)[8]>(p1[0]));
+    tmem_st8(tmem + lane_base + kT_A1 + 8, reinterpret_cast<float (&)[8]>(p1[8]));
+    tmem_st8(tmem + lane_base + kT_A1 + 16, reinterpret_cast<float (&)[8]>(p1[16]));
+    tmem_st8(tmem + lane_base + kT_A2, reinterpret_cast<float (&)[8]>(p2[0]));
+    tmem_st8(tmem + lane_base + kT_A2 + 8, reinterpret_cast<float (&)[8]>(p2[8]));
+    tmem_st8(tmem + lane_base + kT_A2 + 16, reinterpret_cast<float (&)[8]>(p2[16]));
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    mbar_wait(&S.bar_w, 0);
+    if (elect_one()) {
+      for (int l = 0; l < TP_NDEC; ++l)
+        issue_proj<2 * TP_D>(tmem, kT_KV + 2 * TP_D * l, smem_u32(S.w) + l * 2 * kKvWBytes, kKvWBytes, kKv_LBO);
+      umma_commit(&S.bar_mma);
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(&S.bar_mma, 0);
+    tc_fence_after();
+    mbar_wait(&S.bar_w, 0);
+    const float* bias = reinterpret_cast<const float*>(S.w + kKvOffBias);
+#pragma unroll 1
+    for (int l = 0; l < TP_NDEC; ++l) {
+      float* dst = kv_g + ((size_t)l * n_rows + row) * (2 * TP_D) + TP_D * h;
+#pragma unroll
+      for (int j0 = 0; j0 < TP_D; j0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + lane_base + kT_KV + (uint32_t)(2 * TP_D * l + TP_D * h + j0), v);
+        tmem_ld_wait();
+        if (valid) {
+          const float* b = bias + 2 * TP_D * l + TP_D * h + j0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + j0 + j) = make_float4(fmaf(v[j], 1.0f / kWScale, b[j]), fmaf(v[j + 1], 1.0f / kWScale, b[j + 1]),
+                                                                  fmaf(v[j + 2], 1.0f / kWScale, b[j + 2]), fmaf(v[j + 3], 1.0f / kWScale, b[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, kT_KV_COLS);
+}
+
 }  // namespace
 
 // Host: build the pre-split, pre-tiled weight image of one self-attention block (ATT_LAYER_BYTES).
@@ -274,5 +371,35 @@ cudaError_t dp_attn_tc_launch(const unsigned char* wimg, const float* blob, cons
     configured = true;
   }
   tp_attn_tc_kernel<<<(n_clips + kClips - 1) / kClips, kThreads, smem, st>>>(wimg, blob, N1, x, n_clips, out);
+  return cudaGetLastError();
+}
+
+// Host: [W_k | W_v] images + biases of the TP_NDEC cross-attention blocks (KV_IMAGE_BYTES). w_in_t[l] is that block's
+// [48][144] transposed in-projection, b_in[l] its [144] bias.
+void dp_kv_tc_pack(const float* const* w_in_t, const float* const* b_in, unsigned char* dst) {
+  for (int l = 0; l < TP_NDEC; ++l) {
+    __half* pc[2] = {reinterpret_cast<__half*>(dst + l * 2 * kKvWBytes), reinterpret_cast<__half*>(dst + l * 2 * kKvWBytes + kKvWBytes)};
+    for (int n = 0; n < 2 * TP_D; ++n)
+      for (int k = 0; k < TP_D; ++k) {
+        float r = kWScale * w_in_t[l][(size_t)k * 3 * TP_D + TP_D + n];
+        const uint32_t off = ((n >> 3) * kSBO + (k >> 3) * kKv_LBO + (n & 7) * 16 + (k & 7) * 2) / 2;
+        for (int p = 0; p < 2; ++p) {
+          pc[p][off] = __float2half_rn(r);
+          r -= __half2float(pc[p][off]);
+        }
+      }
+    memcpy(dst + kKvOffBias + l * 2 * TP_D * sizeof(float), b_in[l] + TP_D, 2 * TP_D * sizeof(float));
+  }
+}
+
+cudaError_t dp_kv_tc_launch(const unsigned char* wimg, const float* x, int n_rows, float* kv, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = sizeof(SmemKv) + 1024;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tp_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  tp_kv_tc_kernel<<<(n_rows + kTM - 1) / kTM, kThreads, smem, st>>>(wimg, x, n_rows, kv);
   return cudaGetLastError();
 }
