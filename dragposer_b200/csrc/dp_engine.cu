@@ -113,6 +113,8 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaMalloc(&e->tw.dec2, B * TP_MAXT * TP_D * 4));
   CK(cudaMalloc(&e->tw.dec_lat, B * TP_MAXT * TP_LAT * 4));
   CK(cudaMalloc(&e->tw.kvmem, (size_t)TP_NDEC * B * TP_S * 2 * TP_D * 4));
+  CK(cudaMalloc(&e->tw.ffpart, DP_FF_PART_FLOATS * 4));
+  e->tw.num_sms = e->num_sms;
   CK(cudaMalloc(&e->d_pose, B * DP_POSE * 4));
   CK(cudaMalloc(&e->d_gp, B * 3 * 4));
   CK(cudaMallocHost(&e->h_pose, B * DP_POSE * 4));
@@ -138,7 +140,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
-  cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat); cudaFree(e->tw.kvmem);
+  cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat); cudaFree(e->tw.kvmem); cudaFree(e->tw.ffpart);
   cudaFree(e->d_pose); cudaFree(e->d_gp); cudaFreeHost(e->h_pose); cudaFreeHost(e->h_gp);
   cudaStreamDestroy(e->stream);
   delete e;

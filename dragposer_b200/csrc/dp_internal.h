@@ -10,7 +10,10 @@ struct TpWork {
   float* dec2;
   float* dec_lat;
   float* kvmem;  // [TP_NDEC][B * 14][96]: cross-attention K | V of the encoder memory, all decoder layers
+  float* ffpart; // hidden-split partial sums of the feed-forward kernel (DP_FF_PART_FLOATS)
+  int num_sms;
 };
+#define DP_FF_PART_FLOATS ((size_t)8 * 296 * 128 * TP_D / 2)
 
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
 cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream);
@@ -29,5 +32,7 @@ cudaError_t dp_kv_tc_launch(const unsigned char* wimg, const float* x, int n_row
 cudaError_t dp_attn_tc_launch(const unsigned char* wimg, const float* blob, const TpNorm& N1, const float* x, int n_clips, float* out,
                               cudaStream_t st);
 void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned char* dst);
-cudaError_t dp_ff_tc_launch(const unsigned char* wtiles, const float* blob, const TpFF& F, const TpNorm& N1, const TpNorm& N2,
-                            int has_n2, const float* x, int n_rows, int T, int row_stride, float* out, cudaStream_t st);
+// part: workspace of part_floats floats for the hidden-split mode used when the row count cannot fill the device (or null)
+cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const TpFF& F, const TpNorm& N1, const TpNorm& N2, int has_n2,
+                            const float* x, int n_rows, int T, int row_stride, float* out, float* part, size_t part_floats, int num_sms,
+                            cudaStream_t st, long long* launches);

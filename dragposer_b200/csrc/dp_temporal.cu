@@ -394,8 +394,9 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     if (err != cudaSuccess) return err;
     if (fftiles) {
       err = dp_ff_tc_launch(fftiles + (size_t)l * FFT_LAYER_BYTES, blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm, l == TP_NENC - 1, e2,
-                            enc_rows, TP_S, TP_S, e, st);
+                            enc_rows, TP_S, TP_S, e, w.ffpart, DP_FF_PART_FLOATS, w.num_sms, st, launches);
       if (err != cudaSuccess) return err;
+      --*launches;  // counted again below
     } else {
       tp_ff_ln_kernel<<<(enc_rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm,
                                                                       l == TP_NENC - 1, e2, enc_rows, TP_S, TP_S, e);
@@ -422,8 +423,9 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
       if (err != cudaSuccess) return err;
       if (fftiles) {
         err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
-                              l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, st);
+                              l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, w.ffpart, DP_FF_PART_FLOATS, w.num_sms, st, launches);
         if (err != cudaSuccess) return err;
+        --*launches;  // counted again below
       } else {
         tp_ff_ln_kernel<<<(rows + FF_TM - 1) / FF_TM, 256, kFfSmem, st>>>(blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
                                                                     l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2);
