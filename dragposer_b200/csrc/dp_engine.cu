@@ -112,7 +112,6 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaMalloc(&e->tw.dec, B * TP_MAXT * TP_D * 4));
   CK(cudaMalloc(&e->tw.dec2, B * TP_MAXT * TP_D * 4));
   CK(cudaMalloc(&e->tw.dec_lat, B * TP_MAXT * TP_LAT * 4));
-  CK(cudaMalloc(&e->tw.kvmem, (size_t)TP_NDEC * B * TP_S * 2 * TP_D * 4));
   CK(cudaMalloc(&e->tw.ffpart, DP_FF_PART_FLOATS * 4));
   e->tw.num_sms = e->num_sms;
   CK(cudaMalloc(&e->d_pose, B * DP_POSE * 4));
@@ -140,7 +139,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
-  cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat); cudaFree(e->tw.kvmem); cudaFree(e->tw.ffpart);
+  cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat); cudaFree(e->tw.ffpart);
   cudaFree(e->d_pose); cudaFree(e->d_gp); cudaFreeHost(e->h_pose); cudaFreeHost(e->h_gp);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -304,16 +303,9 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
       const TpFF& f = l < TP_NENC ? e->tl.enc[l].ff : e->tl.dec[l - TP_NENC].ff;
       dp_ff_tc_pack(blob + f.w1, blob + f.b1, blob + f.w2, tiles.data() + (size_t)l * FFT_LAYER_BYTES);
     }
-    {
-      const float* w_in[TP_NDEC];
-      const float* b_in[TP_NDEC];
-      for (int l = 0; l < TP_NDEC; ++l) { w_in[l] = blob + e->tl.dec[l].ca.w_in; b_in[l] = blob + e->tl.dec[l].ca.b_in; }
-      dp_kv_tc_pack(w_in, b_in, tiles.data() + DP_TC_KV_OFFSET);
-    }
-    for (int l = 0; l < TP_NENC; ++l) {
-      const TpAttn& a = e->tl.enc[l].sa;
-      dp_attn_tc_pack(blob + a.w_in, blob + a.b_in, blob + a.w_out, blob + a.b_out,
-                      tiles.data() + (size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES + (size_t)l * ATT_LAYER_BYTES);
+    for (int i = 0; i < TP_NENC + 2 * TP_NDEC; ++i) {  // encoder self, decoder self, decoder cross
+      const TpAttn& a = i < TP_NENC ? e->tl.enc[i].sa : (i < TP_NENC + TP_NDEC ? e->tl.dec[i - TP_NENC].sa : e->tl.dec[i - TP_NENC - TP_NDEC].ca);
+      dp_attn_tc_pack(blob + a.w_in, blob + a.b_in, blob + a.w_out, blob + a.b_out, tiles.data() + DP_TC_ATT_OFFSET + (size_t)i * ATT_LAYER_BYTES);
     }
     if (!e->d_fftiles) CK(cudaMalloc(&e->d_fftiles, tiles.size()));
     CK(cudaMemcpy(e->d_fftiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));

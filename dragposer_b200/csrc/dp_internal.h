@@ -9,7 +9,6 @@ struct TpWork {
   float* dec;
   float* dec2;
   float* dec_lat;
-  float* kvmem;  // [TP_NDEC][B * 14][96]: cross-attention K | V of the encoder memory, all decoder layers
   float* ffpart; // hidden-split partial sums of the feed-forward kernel (DP_FF_PART_FLOATS)
   int num_sms;
 };
@@ -18,19 +17,17 @@ struct TpWork {
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
 cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream);
 // fftiles: (TP_NENC + TP_NDEC) x FFT_LAYER_BYTES pre-tiled fp16x2 FF weights (encoder layers first) followed by
-// TP_NENC x ATT_LAYER_BYTES encoder self-attention images and the KV_IMAGE_BYTES cross-attention K|V image, or null to
-// run the fp32 CUDA-core kernels.
-#define DP_TC_KV_OFFSET ((size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES + (size_t)TP_NENC * ATT_LAYER_BYTES)
-#define DP_TC_TILES_BYTES (DP_TC_KV_OFFSET + (size_t)KV_IMAGE_BYTES)
+// the attention images (ATT_LAYER_BYTES each): TP_NENC encoder self-attention blocks, TP_NDEC decoder self-attention blocks,
+// TP_NDEC decoder cross-attention blocks; or null to run the fp32 CUDA-core kernels.
+#define DP_TC_ATT_OFFSET ((size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES)
+#define DP_TC_TILES_BYTES (DP_TC_ATT_OFFSET + (size_t)(TP_NENC + 2 * TP_NDEC) * ATT_LAYER_BYTES)
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
                             const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
                             int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
                             long long* launches);
 void dp_attn_tc_pack(const float* w_in_t, const float* b_in, const float* w_out_t, const float* b_out, unsigned char* dst);
-void dp_kv_tc_pack(const float* const* w_in_t, const float* const* b_in, unsigned char* dst);
-cudaError_t dp_kv_tc_launch(const unsigned char* wimg, const float* x, int n_rows, float* kv, cudaStream_t st);
-cudaError_t dp_attn_tc_launch(const unsigned char* wimg, const float* blob, const TpNorm& N1, const float* x, int n_clips, float* out,
-                              cudaStream_t st);
+cudaError_t dp_attn_tc_launch(const unsigned char* wimg, const float* blob, const TpNorm& N1, const float* xq, int T, int q_stride,
+                              const float* xkv, int S, int kv_stride, int n_clips, float* out, cudaStream_t st);
 void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned char* dst);
 // part: workspace of part_floats floats for the hidden-split mode used when the row count cannot fill the device (or null)
 cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const TpFF& F, const TpNorm& N1, const TpNorm& N2, int has_n2,

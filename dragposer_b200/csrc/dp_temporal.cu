@@ -116,8 +116,7 @@ template <int MQ, int MKV>
 __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __restrict__ blob, TpAttn A, TpNorm N,
                                                                 const float* __restrict__ xq_g, int T, int q_stride,
                                                                 const float* __restrict__ xkv_g, int S, int kv_stride,
-                                                                float* __restrict__ out_g, int n_clips, int G,
-                                                                const float* __restrict__ kv_pre) {
+                                                                float* __restrict__ out_g, int n_clips, int G) {
   extern __shared__ __align__(16) unsigned char mha_raw[];
   MhaSmem<MQ, MKV>& M = *reinterpret_cast<MhaSmem<MQ, MKV>*>(mha_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -134,22 +133,13 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
     const int r = idx / (TP_D / 4), c4 = idx % (TP_D / 4);
     reinterpret_cast<float4*>(&xq[r][0])[c4] = reinterpret_cast<const float4*>(xq_g + ((size_t)(b0 + r / T) * q_stride + r % T) * TP_D)[c4];
   }
-  if (kv_pre) {  // K | V rows already projected (tensor-core pass over the encoder memory): rows (clip * S + s) x 96
-    for (int idx = tid; idx < RK * (2 * TP_D / 4); idx += MHA_THREADS) {
-      const int r = idx / (2 * TP_D / 4), c4 = idx % (2 * TP_D / 4);
-      const float4 t = reinterpret_cast<const float4*>(kv_pre + ((size_t)b0 * S + r) * (2 * TP_D))[c4];
-      if (c4 < TP_D / 4) { k[r][4 * c4] = t.x; k[r][4 * c4 + 1] = t.y; k[r][4 * c4 + 2] = t.z; k[r][4 * c4 + 3] = t.w; }
-      else reinterpret_cast<float4*>(&v[r][0])[c4 - TP_D / 4] = t;
-    }
-  } else {
-    for (int idx = tid; idx < RK * (TP_D / 4); idx += MHA_THREADS) {
-      const int r = idx / (TP_D / 4), c4 = idx % (TP_D / 4);
-      reinterpret_cast<float4*>(&xkv[r][0])[c4] = reinterpret_cast<const float4*>(xkv_g + ((size_t)(b0 + r / S) * kv_stride + r % S) * TP_D)[c4];
-    }
+  for (int idx = tid; idx < RK * (TP_D / 4); idx += MHA_THREADS) {
+    const int r = idx / (TP_D / 4), c4 = idx % (TP_D / 4);
+    reinterpret_cast<float4*>(&xkv[r][0])[c4] = reinterpret_cast<const float4*>(xkv_g + ((size_t)(b0 + r / S) * kv_stride + r % S) * TP_D)[c4];
   }
   __syncthreads();
   const float* Win = blob + A.w_in;
-  if (tid < (kv_pre ? TP_D : 3 * TP_D)) {  // feature tid of [q | k | v]
+  if (tid < 3 * TP_D) {  // feature tid of [q | k | v]
     const bool is_q = tid < TP_D;
     const int n_tok = is_q ? RQ : RK;
     const float (*src)[TP_D] = is_q ? xq : xkv;
@@ -228,7 +218,7 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
 
 template <int MQ, int MKV>
 static cudaError_t launch_mha_t(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
-                                int S, int kv_stride, float* out, int B, cudaStream_t st, const float* kv_pre) {
+                                int S, int kv_stride, float* out, int B, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tp_mha_ln_kernel<MQ, MKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MhaSmem<MQ, MKV>));
@@ -237,18 +227,18 @@ static cudaError_t launch_mha_t(const float* blob, const TpAttn& A, const TpNorm
   }
   int G = MQ / T < MKV / S ? MQ / T : MKV / S;
   G = G < 1 ? 1 : G;
-  tp_mha_ln_kernel<MQ, MKV><<<(B + G - 1) / G, MHA_THREADS, sizeof(MhaSmem<MQ, MKV>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, G, kv_pre);
+  tp_mha_ln_kernel<MQ, MKV><<<(B + G - 1) / G, MHA_THREADS, sizeof(MhaSmem<MQ, MKV>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, G);
   return cudaGetLastError();
 }
 
 static cudaError_t launch_mha(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
-                              int S, int kv_stride, float* out, int B, cudaStream_t st, const float* kv_pre = nullptr) {
+                              int S, int kv_stride, float* out, int B, cudaStream_t st) {
   // (query rows, key rows) per CTA: short decoder self-attention packs 16/T clips, cross-attention min(16/T, 4) clips,
   // the 14-token encoder 2 clips; long decoder sequences fall back to one clip per CTA
   const bool cross = xq != xkv;
-  if (cross && T <= 16) return launch_mha_t<16, 64>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st, kv_pre);
-  if (!cross && T <= 8) return launch_mha_t<16, 16>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st, kv_pre);
-  return launch_mha_t<32, 32>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st, kv_pre);
+  if (cross && T <= 16) return launch_mha_t<16, 64>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st);
+  if (!cross && T <= 8) return launch_mha_t<16, 16>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st);
+  return launch_mha_t<32, 32>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, st);
 }
 
 // ---- out = LN(x + W2 relu(W1 x + b1) + b2) [then an optional second LayerNorm]; 64 tokens per CTA.
@@ -388,7 +378,7 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
   const int enc_rows = B * TP_S;
   for (int l = 0; l < TP_NENC; ++l) {
     if (fftiles)
-      err = dp_attn_tc_launch(fftiles + (size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES + (size_t)l * ATT_LAYER_BYTES, blob, L.enc[l].n1, e, B, e2, st);
+      err = dp_attn_tc_launch(fftiles + DP_TC_ATT_OFFSET + (size_t)l * ATT_LAYER_BYTES, blob, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, B, e2, st);
     else
       err = launch_mha(blob, L.enc[l].sa, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, e2, B, st);
     if (err != cudaSuccess) return err;
@@ -403,11 +393,6 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     }
     *launches += 2;
   }
-  if (fftiles) {  // cross-attention K | V of the memory for all decoder layers and all autoregressive passes, once
-    err = dp_kv_tc_launch(fftiles + DP_TC_KV_OFFSET, e, enc_rows, w.kvmem, st);
-    if (err != cudaSuccess) return err;
-    ++*launches;
-  }
   int T = 1;
   for (int i = 0; i <= window; i += 4, ++T) {
     tp_dec_embed_kernel<<<B, 128, 0, st>>>(blob, L, w.dec_lat, T, w.dec);
@@ -416,10 +401,16 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     float* d2 = w.dec2;
     const int rows = B * T;
     for (int l = 0; l < TP_NDEC; ++l) {
-      err = launch_mha(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2, B, st);
-      if (err != cudaSuccess) return err;
-      err = launch_mha(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d, B, st,
-                       fftiles ? w.kvmem + (size_t)l * enc_rows * 2 * TP_D : nullptr);
+      if (fftiles) {
+        const unsigned char* att = fftiles + DP_TC_ATT_OFFSET;
+        err = dp_attn_tc_launch(att + (size_t)(TP_NENC + l) * ATT_LAYER_BYTES, blob, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, B, d2, st);
+        if (err != cudaSuccess) return err;
+        err = dp_attn_tc_launch(att + (size_t)(TP_NENC + TP_NDEC + l) * ATT_LAYER_BYTES, blob, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, B, d, st);
+      } else {
+        err = launch_mha(blob, L.dec[l].sa, L.dec[l].n1, d, T, TP_MAXT, d, T, TP_MAXT, d2, B, st);
+        if (err != cudaSuccess) return err;
+        err = launch_mha(blob, L.dec[l].ca, L.dec[l].n2, d2, T, TP_MAXT, e, TP_S, TP_S, d, B, st);
+      }
       if (err != cudaSuccess) return err;
       if (fftiles) {
         err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,

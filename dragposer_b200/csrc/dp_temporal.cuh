@@ -22,8 +22,6 @@
 #define FFT_HC 64                 // hidden units per tensor-core FF chunk
 #define FFT_STEP_BYTES 24576      // one pipeline step: W2c pieces of chunk t-2 (2 x 6144 fp16) + W1c pieces of chunk t (2 x 6144 fp16)
 #define FFT_LAYER_BYTES (TP_FF * 4 + (TP_FF / FFT_HC + 2) * FFT_STEP_BYTES)   // b1 (fp32) + 34 steps
-#define ATT_TILE_CLIPS 9           // whole clips per tensor-core attention tile (9 x 14 = 126 of 128 rows)
-#define KV_IMAGE_BYTES 56448       // cross-attention [W_k | W_v] pieces of the 3 decoder layers (3 x 2 x 9216 fp16) + biases (3 x 384)
 #define ATT_LAYER_BYTES 37632      // W_in pieces (2 x 13824 fp16) + W_o pieces (2 x 4608 fp16) + b_in (576) + b_o (192)
 
 struct TpAttn {   // offsets (floats) into the blob

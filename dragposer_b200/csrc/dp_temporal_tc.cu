@@ -253,37 +253,35 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
   if (warp == 8) tmem_dealloc(tmem, kT_COLS);
 }
 
-// second half of the hidden-split mode: out = LN(x + sum of partials + b2) [+ second LayerNorm], one thread per row
-__global__ void __launch_bounds__(128)
+// second half of the hidden-split mode: out = LN(x + sum of partials + b2) [+ second LayerNorm]; one warp per row, lane
+// holds features lane and lane + 32 (< 48), so every load is a coalesced row segment
+__device__ __forceinline__ void ln_row_warp(float& v0, float& v1, bool has1, const float* __restrict__ w, const float* __restrict__ b, int lane) {
+  const float mean = warp_sum(v0 + (has1 ? v1 : 0.0f)) * (1.0f / TP_D);
+  const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.0f;
+  const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / TP_D) + 1e-5f);
+  v0 = d0 * rstd * w[lane] + b[lane];
+  v1 = has1 ? d1 * rstd * w[lane + 32] + b[lane + 32] : 0.0f;
+}
+__global__ void __launch_bounds__(256)
 tp_ff_finish_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2, const float* __restrict__ x_g, int n_rows, int T,
                     int row_stride, const float* __restrict__ part, int n_split, float* __restrict__ out_g) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n_rows) return;
+  const bool has1 = lane + 32 < TP_D;
   const size_t g = ((size_t)(row / T) * row_stride + row % T) * TP_D;
-  const float* b2 = blob + F.b2;
-  float o[TP_D];
-#pragma unroll
-  for (int j = 0; j < TP_D; j += 4) {
-    const float4 xv = *reinterpret_cast<const float4*>(x_g + g + j);
-    o[j] = b2[j] + xv.x; o[j + 1] = b2[j + 1] + xv.y; o[j + 2] = b2[j + 2] + xv.z; o[j + 3] = b2[j + 3] + xv.w;
-  }
-  float acc[TP_D];
-#pragma unroll
-  for (int j = 0; j < TP_D; ++j) acc[j] = 0.0f;
+  float v0 = blob[F.b2 + lane] + x_g[g + lane], v1 = has1 ? blob[F.b2 + lane + 32] + x_g[g + lane + 32] : 0.0f;
+  float a0 = 0.0f, a1 = 0.0f;
   for (int s = 0; s < n_split; ++s) {  // fixed order: the result does not depend on scheduling
-    const float4* p = reinterpret_cast<const float4*>(part + ((size_t)s * n_rows + row) * TP_D);
-#pragma unroll
-    for (int j = 0; j < TP_D; j += 4) {
-      const float4 t = p[j / 4];
-      acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
-    }
+    const float* p = part + ((size_t)s * n_rows + row) * TP_D;
+    a0 += p[lane];
+    if (has1) a1 += p[lane + 32];
   }
-#pragma unroll
-  for (int j = 0; j < TP_D; ++j) o[j] += acc[j];
-  ln48(o, blob + N1.w, blob + N1.b);
-  if (has_n2) ln48(o, blob + N2.w, blob + N2.b);
-#pragma unroll
-  for (int j = 0; j < TP_D; j += 4) *reinterpret_cast<float4*>(out_g + g + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+  v0 += a0;
+  v1 += a1;
+  ln_row_warp(v0, v1, has1, blob + N1.w, blob + N1.b, lane);
+  if (has_n2) ln_row_warp(v0, v1, has1, blob + N2.w, blob + N2.b, lane);
+  out_g[g + lane] = v0;
+  if (has1) out_g[g + lane + 32] = v1;
 }
 
 }  // namespace
@@ -340,7 +338,7 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
   tp_ff_tc_kernel<<<dim3(tiles, n_split), kThreads, smem, st>>>(wimg, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, part);
   ++*launches;
   if (n_split > 1) {
-    tp_ff_finish_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, part, n_split, out);
+    tp_ff_finish_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, part, n_split, out);
     ++*launches;
   }
   return cudaGetLastError();
