@@ -144,6 +144,30 @@ def test_temporal_predictor_vs_reference(golden_dir, engine_factory):
         assert err <= 2e-5
 
 
+@pytest.mark.parametrize("n_clips", [1, 37, 300])
+def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory, n_clips):
+    """Every decoder length (T = 1 + W/4 up to 30 tokens), ragged last tiles: tcgen05 kernels vs the fp32 CUDA-core kernels."""
+    g = np.load(os.path.join(golden_dir, "ref_temporal.npz"))
+    rng = np.random.default_rng(5)
+    reps = -(-n_clips // g["latent_buf"].shape[0])
+    lat = np.tile(g["latent_buf"], (reps, 1, 1))[:n_clips] + rng.normal(0, 0.05, (n_clips, 60, 24)).astype(np.float32)
+    disp = np.tile(g["disp_buf"], (reps, 1, 1))[:n_clips]
+    hgt = np.tile(g["height_buf"], (reps, 1, 1))[:n_clips]
+    eng = engine_factory(512)
+    eng.set_initial_state(np.zeros((n_clips, 24)), np.zeros((n_clips, 3)), np.tile([[1.0, 0, 0, 0]], (n_clips, 1)), np.zeros((n_clips, 6)))
+    eng.set_ring_buffers(lat, disp, hgt)
+    for W in (0, 4, 28, 60, 116):
+        eng.set_predictor_path(0)
+        tc = eng.predict_targets(W).copy()
+        eng.set_predictor_path(1)
+        ref = eng.predict_targets(W).copy()
+        eng.set_predictor_path(0)
+        rows = slice(0, max(W, 1))
+        err = np.abs(tc[:, rows] - ref[:, rows]).max()
+        print(f"{n_clips} clips, window {W}: tensor-core vs CUDA-core predictor max abs diff {err:.2e}")
+        assert np.isfinite(tc[:, rows]).all() and err <= 2e-5
+
+
 @pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_frames_3trk.npz"))
