@@ -102,13 +102,15 @@ constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 64;  // 8 epilogue war
 // a 4096-row decoder step would otherwise occupy 32 SMs for 32 serial chunks).
 __global__ void __launch_bounds__(kThreads, 2)
 tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2,
-                const float* __restrict__ x_g, int n_rows, int T, int row_stride, float* __restrict__ out_g, float* __restrict__ part) {
+                const float* __restrict__ x_g, int n_rows, int T, int row_stride, float* __restrict__ out_g, float* __restrict__ part,
+                long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& S = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTM;
   const int n_loc = kChunks / (int)gridDim.y, c0 = (int)blockIdx.y * n_loc;  // this CTA's chunks: c0 .. c0 + n_loc - 1
   const unsigned char* steps = wimg + TP_FF * 4;
+  if (trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) trace[7] = clock64();
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&S.wfull[i], 1); mbar_init(&S.wfree[i], 1); }
     mbar_init(&S.hfull[0], 1); mbar_init(&S.hfull[1], 1);
@@ -171,8 +173,11 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
       const int b = i & 1, st = (i + 2) % kStages;
       const uint32_t hcol = b ? kT_H1 : kT_H0;
       mbar_wait(&S.wfull[st], ((i + 2) / kStages) & 1);  // usually long complete
+      const bool traced = trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+      if (traced) trace[i * 8 + 0] = clock64();
       mbar_wait(&S.hready[b], (i >> 1) & 1);             // all epilogue threads converted H(i) into its pieces
       tc_fence_after();
+      if (traced) trace[i * 8 + 1] = clock64();
       if (elect_one()) {
         issue_mma2(S, st, tmem, hcol, i == 0);
         if (i + 2 < n_loc) issue_mma1(S, st, tmem, hcol);
@@ -180,6 +185,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
         umma_commit(&S.wfree[st]);
       }
       __syncwarp();
+      if (traced) trace[i * 8 + 2] = clock64();
     }
   } else if (warp == 9) {
     // ===== TMA producer warp, part 2: one step per iteration through the kStages ring; a stage is free again when the
@@ -202,15 +208,19 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
       const float* b1 = S.b1 + (c0 + i) * kHC + chalf * 32;
       mbar_wait(&S.hfull[b], (i >> 1) & 1);  // H(i) accumulated; MMA2(i-2) has released this buffer
       tc_fence_after();
+      const bool traced = trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+      if (traced) trace[i * 8 + 4] = clock64();
       float v[32], p1[16], p2[16];
       tmem_ld32(tmem + lane_base + hcol + (uint32_t)(chalf * 32), v);
       tmem_ld_wait();
+      if (traced) trace[i * 8 + 5] = clock64();
 #pragma unroll
       for (int j = 0; j < 32; j += 2)
         split_h2(fmaxf(fmaf(v[j], 1.0f / kFfWScale, b1[j]), 0.f), fmaxf(fmaf(v[j + 1], 1.0f / kFfWScale, b1[j + 1]), 0.f), p1[j / 2], p2[j / 2]);
       tmem_st16(tmem + lane_base + hcol + (uint32_t)(chalf * 32), p1);
       tmem_st16(tmem + lane_base + hcol + (uint32_t)(chalf * 32) + 16u, p2);
       tmem_st_wait();
+      if (traced) trace[i * 8 + 6] = clock64();
       tc_fence_before();
       mbar_arrive(&S.hready[b]);
     }
@@ -250,6 +260,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
   }
   tc_fence_before();
   __syncthreads();
+  if (trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) trace[15] = clock64();
   if (warp == 8) tmem_dealloc(tmem, kT_COLS);
 }
 
@@ -335,8 +346,26 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
   int n_split = 1;
   while (n_split < 8 && tiles * n_split * 2 <= 2 * num_sms && (size_t)(n_split * 2) * n_rows * TP_D <= part_floats) n_split *= 2;
   if (!part) n_split = 1;
-  tp_ff_tc_kernel<<<dim3(tiles, n_split), kThreads, smem, st>>>(wimg, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, part);
+  // debug: DP_FF_TRACE=n prints the pipeline clock of CTA (0,0) of the n-th launch (cycles since its first H accumulator)
+  static const int want_trace = getenv("DP_FF_TRACE") ? atoi(getenv("DP_FF_TRACE")) : 0;
+  static int n_launch = 0;
+  long long* trace = nullptr;
+  if (want_trace && ++n_launch == want_trace && cudaMallocManaged(&trace, kChunks * 8 * sizeof(long long)) == cudaSuccess) {
+    memset(trace, 0, kChunks * 8 * sizeof(long long));
+    cudaMemPrefetchAsync(trace, kChunks * 8 * sizeof(long long), 0, st);
+  }
+  tp_ff_tc_kernel<<<dim3(tiles, n_split), kThreads, smem, st>>>(wimg, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, part, trace);
   ++*launches;
+  if (trace) {
+    cudaStreamSynchronize(st);
+    const long long t0 = trace[4];
+    printf("FF trace: kernel start %lld, end %lld (cycles relative to the first H accumulator)\n", trace[7] - t0, trace[15] - t0);
+    printf("FF trace (%d rows, split %d): chunk | issuer: weights ready, pieces ready, issued | epilogue: H ready, loaded, stored\n", n_rows, n_split);
+    for (int c = 0; c < kChunks / n_split; ++c)
+      printf("  %2d | %7lld %7lld %7lld | %7lld %7lld %7lld\n", c, trace[c * 8] - t0, trace[c * 8 + 1] - t0, trace[c * 8 + 2] - t0, trace[c * 8 + 4] - t0,
+             trace[c * 8 + 5] - t0, trace[c * 8 + 6] - t0);
+    cudaFree(trace);
+  }
   if (n_split > 1) {
     tp_ff_finish_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, part, n_split, out);
     ++*launches;
