@@ -74,6 +74,8 @@ struct __align__(16) DpModelImageTC {
   // LAST member: a kernel that uses only the first n pieces copies (and reserves shared memory for) a prefix of the image
   __align__(16) unsigned char w[DP_TC_PIECES][DP_TC_W_BYTES];
 };
+// fp16x2 weights for the tensor-memory-resident kernel (dp_frame_tc16.cu): 352 32-bit words per TMEM lane, image [word][128 lanes]
+#define DP_TC_TMEM_WORDS 352
 #define DP_TC_IMAGE_BYTES(n_pieces) (sizeof(DpModelImageTC) - (DP_TC_PIECES - (n_pieces)) * DP_TC_W_BYTES)
 static_assert(sizeof(DpModelImageTC) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
 
@@ -81,6 +83,7 @@ struct DpFrameArgs {
   const DpModelImage* model;
   const DpModelImageTC* model_tc;    // bf16x3 pieces
   const DpModelImageTC* model_tc16;  // fp16x2 pieces of 16 W (w[2] unused)
+  const uint32_t* model_tmem;        // fp16x2 pieces of 16 W and 16 W^T as tensor-memory words [DP_TC_TMEM_WORDS][128]
   int n_clips;
   // carried state (HBM)
   float* latent;        // (B,24) latent after the last Adam step (seeds the next frame)

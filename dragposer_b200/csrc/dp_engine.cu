@@ -35,6 +35,7 @@ struct dp_engine {
   DpModelImage* d_model = nullptr;
   DpModelImageTC* d_model_tc = nullptr;
   DpModelImageTC* d_model_tc16 = nullptr;
+  uint32_t* d_model_tmem = nullptr;
   float* d_tblob = nullptr;
   unsigned char* d_fftiles = nullptr;  // pre-tiled fp16x2 tensor-core weight images of the predictor (DP_TC_TILES_BYTES)
   int predictor_path = 0;              // 0 = tcgen05 FF (default), 1 = fp32 CUDA-core FF
@@ -95,6 +96,7 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaMalloc(&e->d_model, sizeof(DpModelImage)));
   CK(cudaMalloc(&e->d_model_tc, sizeof(DpModelImageTC)));
   CK(cudaMalloc(&e->d_model_tc16, sizeof(DpModelImageTC)));
+  CK(cudaMalloc(&e->d_model_tmem, (size_t)DP_TC_TMEM_WORDS * 128 * 4));
   CK(cudaMalloc(&e->d_latent, B * DP_L * 4));
   CK(cudaMalloc(&e->d_gpos, B * 3 * 4));
   CK(cudaMalloc(&e->d_grot, B * 4 * 4));
@@ -135,7 +137,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_stage(e);
-  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_model_tmem); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
@@ -283,6 +285,32 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
         }
     }
     CK(cudaMemcpy(e->d_model_tc16, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
+    // tensor-memory image of the same fp16 pieces: lane m, word c holds K elements (2c', 2c'+1) of row m of the A operand --
+    // forward layer l: A = 16 W_l (rows = outputs), backward: A = 16 W_l^T (rows = inputs); order and widths as WT<> in
+    // dp_frame_tc16.cu: fwd0 (K 32) fwd1 (48) fwd2 (64) bwd2 (96) bwd1 (64) bwd0 (48), two pieces each
+    std::vector<uint32_t> tm((size_t)DP_TC_TMEM_WORDS * 128, 0u);
+    const int kpad[3] = {32, 48, 64}, opad[3] = {48, 64, 96};
+    uint32_t col = 0;
+    auto put = [&](int l, bool fwd) {
+      const int K = dims[l], N = dims[l + 1];          // W_l is [N][K]
+      const int kk = fwd ? kpad[l] : opad[l];          // padded reduction length of this operand
+      for (int p = 0; p < 2; ++p) {
+        for (int m = 0; m < 128; ++m)
+          for (int k = 0; k < kk; ++k) {
+            const bool in = fwd ? (m < N && k < K) : (m < K && k < N);
+            float r = in ? 16.0f * (fwd ? A[l][m * K + k] : A[l][k * K + m]) : 0.0f;
+            __half h = __float2half_rn(r);
+            if (p == 1) { r -= __half2float(h); h = __float2half_rn(r); }
+            uint16_t bits;
+            memcpy(&bits, &h, 2);
+            tm[(size_t)(col + k / 2) * 128 + m] |= (uint32_t)bits << (16 * (k & 1));
+          }
+        col += kk / 2;
+      }
+    };
+    put(0, true); put(1, true); put(2, true); put(2, false); put(1, false); put(0, false);
+    if (col != DP_TC_TMEM_WORDS) return fail(DP_ERR_STATE, "tensor-memory weight image layout");
+    CK(cudaMemcpy(e->d_model_tmem, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
   }
   e->has_pose = true;
   return DP_OK;
@@ -413,6 +441,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.model = e->d_model;
   a.model_tc = e->d_model_tc;
   a.model_tc16 = e->d_model_tc16;
+  a.model_tmem = e->d_model_tmem;
   a.n_clips = e->n_clips;
   a.latent = e->d_latent; a.gpos = e->d_gpos; a.grot = e->d_grot;
   a.latent_buf = e->d_latent_buf; a.disp_buf = e->d_disp_buf; a.height_buf = e->d_height_buf;
@@ -433,7 +462,8 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   // auto: tensor-core decoder once a batch fills a fair share of the SMs with 32-clip tiles; the fp32 warp-per-clip
   // kernel is the low-latency path for small batches (B = 1 streaming)
   const int path = p->decoder_path ? p->decoder_path : (e->n_clips >= 1024 ? DP_AUTO_TC_PATH : 1);
-  if (path >= 2) CK(dp_frame_tc_launch(a, e->num_sms, path == 3, st));
+  if (path == 3) CK(dp_frame_tc16_launch(a, e->num_sms, st));
+  else if (path == 2) CK(dp_frame_tc_launch(a, e->num_sms, st));
   else CK(dp_frame_simt_launch(a, e->num_sms, st));
   e->last_path = path;
   ++e->launches;
@@ -574,14 +604,15 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   CK(cudaMemcpy(d_tr, tgt_rot, N * S * 36, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_adam, 0, 8));
   DpFrameArgs a{};
-  a.model = e->d_model; a.model_tc = e->d_model_tc; a.model_tc16 = e->d_model_tc16; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
+  a.model = e->d_model; a.model_tc = e->d_model_tc; a.model_tc16 = e->d_model_tc16; a.model_tmem = e->d_model_tmem; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
   a.target_buf = d_t; a.target_rows = 1; a.target_index = 0;
   a.n_ee = d_ne; a.joints = d_j; a.weights = d_w; a.shared_trackers = shared; a.tgt_pos = d_tp; a.tgt_rot = d_tr;
   a.ee_stride = ee_stride;
   a.eps_pos = -1.0; a.eps_rot = -1.0; a.min_incr = -std::numeric_limits<double>::infinity();
   a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
   a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
-  if (decoder_path >= 2) CK(dp_frame_tc_launch(a, e->num_sms, decoder_path == 3, e->stream));
+  if (decoder_path == 3) CK(dp_frame_tc16_launch(a, e->num_sms, e->stream));
+  else if (decoder_path == 2) CK(dp_frame_tc_launch(a, e->num_sms, e->stream));
   else CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
   ++e->launches;
   CK(cudaStreamSynchronize(e->stream));

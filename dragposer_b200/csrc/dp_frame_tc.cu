@@ -592,25 +592,20 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
 
 }  // namespace
 
-cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream) {
+cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem32 = sizeof(SmemTC<0, 32>) + 1024, smem16 = sizeof(SmemTC<1, 16>) + 1024;
+  const size_t smem = sizeof(SmemTC<0, 32>) + 1024;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<0, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dp_frame_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<0, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  // spread the clips over every CTA slot of the device: 4096 clips -> 14 real clips per 16-column tile on 293 of the 296
-  // slots (fp16x2, two CTAs per SM), or 28 per 32-column tile on 147 SMs (bf16x3)
+  // 4096 clips: 28 real clips per 32-column tile -> 147 CTAs, one per SM, instead of 128 CTAs of 32
   DpFrameArgs a = args;
-  const int nc = fp16 ? 16 : 32, slots = fp16 ? 2 * num_sms : num_sms;
-  int cpc = (args.n_clips + slots - 1) / slots;
-  cpc = cpc < 1 ? 1 : (cpc > nc ? nc : cpc);
-  if (args.n_clips > slots * nc) cpc = nc;  // several waves anyway: use full tiles
+  int cpc = (args.n_clips + num_sms - 1) / num_sms;
+  cpc = cpc < 1 ? 1 : (cpc > 32 ? 32 : cpc);
+  if (args.n_clips > num_sms * 32) cpc = 32;  // several waves anyway: use full tiles
   a.clips_per_cta = cpc;
-  const int grid = (args.n_clips + cpc - 1) / cpc;
-  if (fp16) dp_frame_tc_kernel<1, 16><<<grid, Geo<16>::kWarps * 32, smem16, stream>>>(a);
-  else dp_frame_tc_kernel<0, 32><<<grid, Geo<32>::kWarps * 32, smem32, stream>>>(a);
+  dp_frame_tc_kernel<0, 32><<<(args.n_clips + cpc - 1) / cpc, Geo<32>::kWarps * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

@@ -15,7 +15,8 @@ struct TpWork {
 #define DP_FF_PART_FLOATS ((size_t)8 * 296 * 128 * TP_D / 2)
 
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
-cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, bool fp16, cudaStream_t stream);
+cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);    // bf16x3, weights in shared memory
+cudaError_t dp_frame_tc16_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);  // fp16x2, weights in tensor memory
 // fftiles: (TP_NENC + TP_NDEC) x FFT_LAYER_BYTES pre-tiled fp16x2 FF weights (encoder layers first) followed by
 // the attention images (ATT_LAYER_BYTES each): TP_NENC encoder self-attention blocks, TP_NDEC decoder self-attention blocks,
 // TP_NDEC decoder cross-attention blocks; or null to run the fp32 CUDA-core kernels.
