@@ -172,8 +172,9 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
     if (rd >= n_jump) break;
     const int a = M.jump[rd][lane];
     const int src = a >= 0 ? a : lane;
+    const float take = a >= 0 ? 1.0f : 0.0f;  // multiplicative mask: one FFMA2 instead of a predicated add plus two moves
     const P2 t0 = shfl(p[0], src), t1 = shfl(p[1], src), t2 = shfl(p[2], src);
-    if (a >= 0) { p[0] = p[0] + t0; p[1] = p[1] + t1; p[2] = p[2] + t2; }
+    p[0] = mad(take, t0, p[0]); p[1] = mad(take, t1, p[1]); p[2] = mad(take, t2, p[2]);
   }
   // masked tracker loss (drag_pose.py:116-124); untracked lanes carry zero weights
   const ClipTrackers ta = trk_a[lane], tb = trk_b[lane];
@@ -216,7 +217,8 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const P2 t0 = shfl_up(P[0], o), t1 = shfl_up(P[1], o), t2 = shfl_up(P[2], o);
-      if (lane >= o) { P[0] = P[0] + t0; P[1] = P[1] + t1; P[2] = P[2] + t2; }
+      const float take = lane >= o ? 1.0f : 0.0f;
+      P[0] = mad(take, t0, P[0]); P[1] = mad(take, t1, P[1]); P[2] = mad(take, t2, P[2]);
     }
     const int last = M.last[lane];
     P2 cb[3];
@@ -234,12 +236,10 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
       const int ch = M.child[k][lane];
       const int src = ch >= 0 ? ch : lane;
       const P2 t0 = shfl(cb[0], src), t1 = shfl(cb[1], src), t2 = shfl(cb[2], src);
-      if (ch >= 0) {
-        const float4 co = *reinterpret_cast<const float4*>(M.coff[k][lane]);
-        Rb[0] = mad(co.x, t0, Rb[0]); Rb[1] = mad(co.y, t0, Rb[1]); Rb[2] = mad(co.z, t0, Rb[2]);
-        Rb[3] = mad(co.x, t1, Rb[3]); Rb[4] = mad(co.y, t1, Rb[4]); Rb[5] = mad(co.z, t1, Rb[5]);
-        Rb[6] = mad(co.x, t2, Rb[6]); Rb[7] = mad(co.y, t2, Rb[7]); Rb[8] = mad(co.z, t2, Rb[8]);
-      }
+      const float4 co = *reinterpret_cast<const float4*>(M.coff[k][lane]);  // zero offsets where there is no k-th child
+      Rb[0] = mad(co.x, t0, Rb[0]); Rb[1] = mad(co.y, t0, Rb[1]); Rb[2] = mad(co.z, t0, Rb[2]);
+      Rb[3] = mad(co.x, t1, Rb[3]); Rb[4] = mad(co.y, t1, Rb[4]); Rb[5] = mad(co.z, t1, Rb[5]);
+      Rb[6] = mad(co.x, t2, Rb[6]); Rb[7] = mad(co.y, t2, Rb[7]); Rb[8] = mad(co.z, t2, Rb[8]);
     }
     if (is_root) {  // p_0 = R_0 d
 #pragma unroll

@@ -364,59 +364,65 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     backward();
     phase_done(2);
     const float step_size = A.adam_tab[it], inv_bc2s = A.adam_tab[A.max_iter + it];  // lr/(1-b1^k), 1/sqrt(1-b2^k)
-#pragma unroll
-    for (int c = 0; c < CPW; ++c) {
-      const int n = n0 + c;
+    {  // latent loss, Adam and early-stop bookkeeping of BOTH clips in one pass: clip 0 on lanes 0..11, clip 1 on lanes 16..27
+      const int c = lane >> 4, j = lane & 15, n = n0 + c;
+      const bool lat = j < DP_L / 2;
+      const bool act = c ? active[1] : active[0];
+      const float my_lp = c ? nlp[1] : nlp[0], my_lr = c ? nlr[1] : nlr[0];
       float2 z = make_float2(0.f, 0.f), tl = z;
-      if (lane < DP_L / 2) { z = S.st[n][ST_Z][lane]; tl = S.st[n][ST_TL][lane]; }
+      if (lat) { z = S.st[n][ST_Z][j]; tl = S.st[n][ST_TL][j]; }
       const float dx = z.x - tl.x, dy = z.y - tl.y;
-      const float nlt = warp_sum(fmaf(dx, dx, dy * dy)) * lt_scale;
+      float ssq = fmaf(dx, dx, dy * dy);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);  // sums stay inside each 16-lane half
+      const float nlt = ssq * lt_scale;
       float gx = 0.f, gy = 0.f;
-      if (lane < DP_L / 2) {
-        gx = fmaf(2.0f * lt_scale, dx, S.zgrad[n][2 * lane]);
-        gy = fmaf(2.0f * lt_scale, dy, S.zgrad[n][2 * lane + 1]);
+      if (lat) {
+        gx = fmaf(2.0f * lt_scale, dx, S.zgrad[n][2 * j]);
+        gy = fmaf(2.0f * lt_scale, dy, S.zgrad[n][2 * j + 1]);
       }
-      if (A.trace && active[c]) {
+      if (A.trace && act) {
         float* row = A.trace + ((size_t)(clip0 + c) * A.trace_iters + it) * 52;
-        if (lane < DP_L / 2) {
-          reinterpret_cast<float2*>(row)[lane] = z;
-          reinterpret_cast<float2*>(row + DP_L)[lane] = make_float2(gx, gy);
+        if (lat) {
+          reinterpret_cast<float2*>(row)[j] = z;
+          reinterpret_cast<float2*>(row + DP_L)[j] = make_float2(gx, gy);
         }
-        if (lane == 0) { row[48] = nlp[c]; row[49] = nlr[c]; row[50] = nlt; row[51] = 1.0f; }
+        if (j == 0) { row[48] = my_lp; row[49] = my_lr; row[50] = nlt; row[51] = 1.0f; }
       }
       if (A.eval_only) {
-        if (active[c] && lane < DP_L / 2) reinterpret_cast<float2*>(A.eval_grad + (size_t)(clip0 + c) * DP_L)[lane] = make_float2(gx, gy);
-      } else if (active[c] && lane < DP_L / 2) {
-        float2 am = S.st[n][ST_M][lane], av = S.st[n][ST_V][lane];
+        if (act && lat) reinterpret_cast<float2*>(A.eval_grad + (size_t)(clip0 + c) * DP_L)[j] = make_float2(gx, gy);
+      } else if (act && lat) {
+        float2 am = S.st[n][ST_M][j], av = S.st[n][ST_V][j];
         am.x = fmaf(0.1f, gx - am.x, am.x);
         am.y = fmaf(0.1f, gy - am.y, am.y);
         av.x = av.x * 0.999f + (0.001f * gx) * gx;
         av.y = av.y * 0.999f + (0.001f * gy) * gy;
-        S.st[n][ST_M][lane] = am;
-        S.st[n][ST_V][lane] = av;
-        S.st[n][ST_ZLAST][lane] = z;  // the frame's output is decoded from the last EVALUATED latent
+        S.st[n][ST_M][j] = am;
+        S.st[n][ST_V][j] = av;
+        S.st[n][ST_ZLAST][j] = z;  // the frame's output is decoded from the last EVALUATED latent
         z.x += __fdividef(-step_size * am.x, fmaf(fast_sqrt(av.x), inv_bc2s, 1e-8f));
         z.y += __fdividef(-step_size * am.y, fmaf(fast_sqrt(av.y), inv_bc2s, 1e-8f));
-        S.st[n][ST_Z][lane] = z;
+        S.st[n][ST_Z][j] = z;
       }
       // the latent rows of the ping image were overwritten by the a1 / dL/dh1 pieces of this iteration: restore them for
       // EVERY clip (stopped and padding clips included) so that no column ever feeds back on its own garbage -- a
       // non-finite value in a K-padding row would poison the column through 0 x NaN
-      if (lane < DP_L / 2) {
-        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n, z.x);
-        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n, z.y);
+      if (lat) {
+        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * j, n, z.x);
+        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * j + 1, n, z.y);
       }
-      if (active[c]) {
-        const float total = (nlp[c] + nlr[c]) + nlt;
-        const double incr = S.prev[n] - (double)total;
-        __syncwarp();
-        if (lane == 0) {
-          S.prev[n] = (double)total;
-          S.loss[n][0] = nlp[c]; S.loss[n][1] = nlr[c]; S.loss[n][2] = nlt;
-          S.iters[n] += 1;
-        }
-        active[c] = ((double)nlp[c] > A.eps_pos || (double)nlr[c] > A.eps_rot) && (incr > A.min_incr);
+      const float total = (my_lp + my_lr) + nlt;
+      const double incr = S.prev[n] - (double)total;
+      __syncwarp();
+      if (act && j == 0) {
+        S.prev[n] = (double)total;
+        S.loss[n][0] = my_lp; S.loss[n][1] = my_lr; S.loss[n][2] = nlt;
+        S.iters[n] += 1;
       }
+      const bool next = act && ((double)my_lp > A.eps_pos || (double)my_lr > A.eps_rot) && (incr > A.min_incr);
+      const unsigned votes = __ballot_sync(0xffffffffu, next);
+      active[0] = votes & 1u;
+      active[1] = (votes >> 16) & 1u;
     }
     fence_proxy_async();
   }
