@@ -30,6 +30,16 @@ HBM_BYTES_PER_CLIP_FRAME = 1300.0  # algorithmic state + tracker + result bytes 
 MAX_ITER = 100
 
 
+KERNEL_NAMES = {
+    1: "dp_frame_simt_kernel (persistent per-frame loop; fp32 CUDA-core decoder)",
+    2: "dp_frame_tc_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, bf16x3 split, weights in shared memory)",
+    3: "dp_frame_tc16_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, fp16x2 split, weights in tensor memory)",
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture whose
+# summary is committed under profiles/ (keyed by decoder path, clips per GPU, tracker config); null for other configurations
+NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 2955008}
+
+
 def fixed_opts(cfg):
     return dict(stop_eps_pos=-1.0, stop_eps_rot=-1.0, max_iter=MAX_ITER, min_loss_incr=-float("inf"), learning_rate=1e-2,
                 lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window,
@@ -280,12 +290,9 @@ def run_ours(args):
             "metric": "clip-frames/sec (fixed 100 opt iters)", "value": value, "unit": "clip-frames/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, cfg, n_total),
-            "roofline": {"bound": "tensor", "kernel": ("dp_frame_tc_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, %s split)"
-                                                       % ("fp16x2" if eng.last_decoder_path() == 3 else "bf16x3")
-                                                       if eng.last_decoder_path() >= 2 else
-                                                       "dp_frame_simt_kernel (persistent per-frame loop; fp32 CUDA-core decoder)"),
+            "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[eng.last_decoder_path()],
                          "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf32_peak,
-                         "traffic": None, "peak_source": which, "kernel_ms_per_launch": frame_ms,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((eng.last_decoder_path(), B, args.trackers)), "peak_source": which, "kernel_ms_per_launch": frame_ms,
                          "predictor_ms_per_step": ms_pred / max(nprof, 1),
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
                          "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"},
