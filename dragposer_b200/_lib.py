@@ -55,6 +55,7 @@ SIGNATURES = {
     "dp_engine_n_clips": (C.c_int, [_VP]),
     "dp_engine_run_frame_device": (C.c_int, [_VP, C.POINTER(RunParams), _VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, _VP]),
     "dp_engine_run_frame_host": (C.c_int, [_VP, C.POINTER(RunParams), _VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP]),
+    "dp_engine_run_frames_host": (C.c_int, [_VP, C.POINTER(RunParams), C.c_int, _VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP]),
     "dp_engine_run_frames_device": (C.c_int, [_VP, C.POINTER(RunParams), C.c_int, _VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, _VP, _VP, _VP]),
     "dp_engine_get_frame_stats": (C.c_int, [_VP, _VP, _VP]),
     "dp_engine_enable_trace": (C.c_int, [_VP, C.c_int]),

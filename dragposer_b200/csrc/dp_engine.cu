@@ -63,6 +63,14 @@ struct dp_engine {
   int32_t *h_nee = nullptr, *d_nee = nullptr, *h_joints = nullptr, *d_joints = nullptr;
   float *h_w = nullptr, *d_w = nullptr, *h_tp = nullptr, *d_tp = nullptr, *h_tr = nullptr, *d_tr = nullptr;
   float *h_pose = nullptr, *d_pose = nullptr, *h_gp = nullptr, *d_gp = nullptr;
+  // double-buffered staging of dp_engine_run_frames_host: one contiguous block per slot and direction
+  struct FramePipe {
+    int stride = 0;
+    unsigned char *h_in[2] = {nullptr, nullptr}, *d_in[2] = {nullptr, nullptr};
+    float *h_out[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaStream_t cs_in = nullptr, cs_out = nullptr;
+  } pipe;
   cudaStream_t stream = nullptr;
   long long launches = 0;
   // optional device-side timing of the two kernel groups (bench roofline)
@@ -124,6 +132,18 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   return DP_OK;
 }
 
+static void free_pipe(dp_engine* e) {
+  for (int i = 0; i < 2; ++i) {
+    cudaFreeHost(e->pipe.h_in[i]); cudaFree(e->pipe.d_in[i]); cudaFreeHost(e->pipe.h_out[i]); cudaFree(e->pipe.d_out[i]);
+    if (e->pipe.ev_h2d[i]) cudaEventDestroy(e->pipe.ev_h2d[i]);
+    if (e->pipe.ev_run[i]) cudaEventDestroy(e->pipe.ev_run[i]);
+    if (e->pipe.ev_d2h[i]) cudaEventDestroy(e->pipe.ev_d2h[i]);
+  }
+  if (e->pipe.cs_in) cudaStreamDestroy(e->pipe.cs_in);
+  if (e->pipe.cs_out) cudaStreamDestroy(e->pipe.cs_out);
+  e->pipe = dp_engine::FramePipe();
+}
+
 static void free_stage(dp_engine* e) {
   cudaFreeHost(e->h_nee); cudaFreeHost(e->h_joints); cudaFreeHost(e->h_w); cudaFreeHost(e->h_tp); cudaFreeHost(e->h_tr);
   cudaFree(e->d_nee); cudaFree(e->d_joints); cudaFree(e->d_w); cudaFree(e->d_tp); cudaFree(e->d_tr);
@@ -137,6 +157,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_stage(e);
+  free_pipe(e);
   cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_model_tmem); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
@@ -548,6 +569,97 @@ extern "C" int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, co
   CK(cudaStreamSynchronize(st));
   memcpy(out_pose, e->h_pose, B * DP_POSE * 4);
   memcpy(out_gpos, e->h_gp, B * 3 * 4);
+  return DP_OK;
+}
+
+// Offsets of the per-frame inputs inside one staging block (all 16-byte aligned): n_ee | joints | weights | tgt_pos | tgt_rot
+struct PipeLayout {
+  size_t nee, joints, w, tp, tr, total;
+  PipeLayout(size_t B, size_t S) {
+    auto up = [](size_t x) { return (x + 15) & ~size_t(15); };
+    nee = 0;
+    joints = up(B * 4);
+    w = joints + up(B * S * 4);
+    tp = w + up(B * S * 8);
+    tr = tp + up(B * S * 12);
+    total = tr + up(B * S * 36);
+  }
+};
+
+static int ensure_pipe(dp_engine* e, int ee_stride) {
+  if (e->pipe.stride >= ee_stride) return DP_OK;
+  free_pipe(e);
+  const PipeLayout L((size_t)e->max_clips, (size_t)ee_stride);
+  const size_t out_bytes = (size_t)e->max_clips * (DP_POSE + 3) * 4;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMallocHost(&e->pipe.h_in[i], L.total)); CK(cudaMalloc(&e->pipe.d_in[i], L.total));
+    CK(cudaMallocHost(&e->pipe.h_out[i], out_bytes)); CK(cudaMalloc(&e->pipe.d_out[i], out_bytes));
+    CK(cudaEventCreateWithFlags(&e->pipe.ev_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->pipe.ev_run[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->pipe.ev_d2h[i], cudaEventDisableTiming));
+  }
+  CK(cudaStreamCreateWithFlags(&e->pipe.cs_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->pipe.cs_out, cudaStreamNonBlocking));
+  e->pipe.stride = ee_stride;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, int n_frames, const int32_t* n_ee, const int32_t* joints,
+                                         const float* weights, int shared, const float* tgt_pos, const float* tgt_rot, int ee_stride,
+                                         float* out_pose, float* out_gpos) {
+  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || !out_gpos || n_frames < 0)
+    return fail(DP_ERR_ARG, "dp_engine_run_frames_host: null argument");
+  int rc = check_params(e, p, ee_stride);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  rc = ensure_pipe(e, ee_stride);
+  if (rc) return rc;
+  rc = ensure_adam(e, p->max_iter, p->learning_rate);
+  if (rc) return rc;
+  dp_engine::FramePipe& P = e->pipe;
+  cudaStream_t st = e->stream;
+  const size_t B = (size_t)e->n_clips, S = (size_t)ee_stride;
+  const size_t nj = shared ? S : B * S;
+  const PipeLayout L((size_t)e->max_clips, (size_t)P.stride);
+  const size_t out_bytes = B * (DP_POSE + 3) * 4;
+  auto unstage = [&](int t) -> int {  // frame t's results: pinned slot -> caller's arrays
+    const int slot = t & 1;
+    CK(cudaEventSynchronize(P.ev_d2h[slot]));
+    memcpy(out_pose + (size_t)t * B * DP_POSE, P.h_out[slot], B * DP_POSE * 4);
+    memcpy(out_gpos + (size_t)t * B * 3, P.h_out[slot] + B * DP_POSE, B * 3 * 4);
+    return DP_OK;
+  };
+  for (int t = 0; t < n_frames; ++t) {
+    const int slot = t & 1;
+    // (1) stage frame t's inputs while the device works on frame t-1
+    if (t >= 2) CK(cudaEventSynchronize(P.ev_h2d[slot]));  // the pinned block was last read by the copy of frame t-2
+    unsigned char* h = P.h_in[slot];
+    if (n_ee) memcpy(h + L.nee, n_ee + (size_t)t * B, B * 4);
+    memcpy(h + L.joints, joints + (shared ? 0 : (size_t)t * nj), nj * 4);
+    memcpy(h + L.w, weights + (shared ? 0 : (size_t)t * nj * 2), nj * 8);
+    memcpy(h + L.tp, tgt_pos + (size_t)t * B * S * 3, B * S * 12);
+    memcpy(h + L.tr, tgt_rot + (size_t)t * B * S * 9, B * S * 36);
+    // (2) copy in on its own stream (after frame t-2 has finished reading this device block), run, copy out on a third stream
+    if (t >= 2) CK(cudaStreamWaitEvent(P.cs_in, P.ev_run[slot], 0));
+    CK(cudaMemcpyAsync(P.d_in[slot], h, L.total, cudaMemcpyHostToDevice, P.cs_in));
+    CK(cudaEventRecord(P.ev_h2d[slot], P.cs_in));
+    CK(cudaStreamWaitEvent(st, P.ev_h2d[slot], 0));
+    if (t >= 2) CK(cudaStreamWaitEvent(st, P.ev_d2h[slot], 0));  // frame t-2's results have left this device block
+    unsigned char* d = P.d_in[slot];
+    float* d_pose = P.d_out[slot];
+    rc = run_one(e, p, n_ee ? reinterpret_cast<const int32_t*>(d + L.nee) : nullptr, reinterpret_cast<const int32_t*>(d + L.joints),
+                 reinterpret_cast<const float*>(d + L.w), shared, reinterpret_cast<const float*>(d + L.tp),
+                 reinterpret_cast<const float*>(d + L.tr), ee_stride, d_pose, d_pose + B * DP_POSE, st);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    CK(cudaEventRecord(P.ev_run[slot], st));
+    CK(cudaStreamWaitEvent(P.cs_out, P.ev_run[slot], 0));
+    CK(cudaMemcpyAsync(P.h_out[slot], d_pose, out_bytes, cudaMemcpyDeviceToHost, P.cs_out));
+    CK(cudaEventRecord(P.ev_d2h[slot], P.cs_out));
+    // (3) hand frame t-1's results to the caller
+    if (t >= 1) { rc = unstage(t - 1); if (rc) return rc; }
+  }
+  if (n_frames >= 1) { rc = unstage(n_frames - 1); if (rc) return rc; }
+  CK(cudaStreamSynchronize(st));
   return DP_OK;
 }
 

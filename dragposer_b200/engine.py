@@ -166,6 +166,30 @@ class BatchedDragPose:
         ne = None if n_ee is None else _i32(n_ee).reshape(B)
         return joints, weights, shared, ne
 
+    def run_frames(self, target_ee_pos, target_ee_rot, mask_joints, weights_joints, n_ee=None, **opts):
+        """T consecutive frames from HOST arrays in one call: target_ee_pos (T,B,E,3), target_ee_rot (T,B,E,3,3),
+        mask_joints (E,) / weights_joints (E,2) shared by every clip and frame or (T,B,E) / (T,B,E,2), n_ee (T,B) or None
+        -> poses (T,B,88), global_pos (T,B,3).  Same results as T calls of run(); the staging and host<->device copies of
+        neighbouring frames overlap the kernels (dp_engine_run_frames_host)."""
+        B = self.n_clips
+        tp = _f32(target_ee_pos)
+        T = tp.shape[0]
+        tp = tp.reshape(T, B, -1, 3)
+        E = tp.shape[2]
+        tr = _f32(target_ee_rot).reshape(T, B, E, 9)
+        joints, weights = _i32(mask_joints), _f32(weights_joints)
+        shared = int(joints.ndim == 1)
+        if shared:
+            assert joints.shape == (E,) and weights.shape == (E, 2)
+        else:
+            assert joints.shape == (T, B, E) and weights.shape == (T, B, E, 2)
+        ne = None if n_ee is None else _i32(n_ee).reshape(T, B)
+        p = opts["options"].c if "options" in opts else RunOptions(**opts).c
+        pose, gpos = np.empty((T, B, 88), F32), np.empty((T, B, 3), F32)
+        _lib.check(self.lib.dp_engine_run_frames_host(self.h, C.byref(p), T, _ptr(ne), _ptr(joints), _ptr(weights), shared,
+                                                      _ptr(tp), _ptr(tr), E, _ptr(pose), _ptr(gpos)))
+        return pose, gpos
+
     def run(self, target_ee_pos, target_ee_rot, mask_joints, weights_joints, n_ee=None, **opts):
         """HOST buffers in, host arrays out (copies + one sync inside the call).
         target_ee_pos (B,E,3), target_ee_rot (B,E,3,3), mask_joints (E,) or (B,E),

@@ -117,6 +117,16 @@ int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, const int32_t
                              const float* tgt_pos, const float* tgt_rot, int ee_stride,
                              float* out_pose, float* out_global_pos);
 
+/* n_frames consecutive frames from HOST arrays laid out frame-major (tgt_pos (T,B,ee_stride,3), tgt_rot (T,B,ee_stride,3,3),
+ * n_ee (T,B) or NULL; joints/weights either one shared row used by every clip and frame (shared_trackers != 0) or
+ * (T,B,ee_stride[,2])), results (T,B,88) / (T,B,3).  Same arithmetic as n_frames calls of dp_engine_run_frame_host, but
+ * the pageable<->pinned staging and the host<->device copies of frame t+1 / t-1 overlap the kernels of frame t
+ * (double-buffered blocks, copy-in and copy-out on their own streams).  Synchronises before returning. */
+int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, int n_frames, const int32_t* n_ee,
+                              const int32_t* joints, const float* weights, int shared_trackers,
+                              const float* tgt_pos, const float* tgt_rot, int ee_stride,
+                              float* out_pose, float* out_global_pos);
+
 /* n_frames consecutive frames with device-resident inputs laid out frame-major
  * (frame stride = B*ee_stride*{1,2,3,9} elements; n_ee stride = B; joints/weights
  * follow the frame stride unless shared_trackers).  Outputs (n_frames,B,88)/(n_frames,B,3). */

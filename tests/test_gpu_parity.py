@@ -144,6 +144,38 @@ def test_temporal_predictor_vs_reference(golden_dir, engine_factory):
         assert err <= 2e-5
 
 
+@pytest.mark.parametrize("variable", [False, True], ids=["shared-trackers", "variable-mask"])
+def test_run_frames_pipelined_equals_frame_by_frame(engine_factory, pose_model, model_npz, variable):
+    """dp_engine_run_frames_host (double-buffered staging and copies) must give bit-identical results to per-frame run()."""
+    offsets = model_npz["offsets"]
+    cfg = synthetic.config_3_trackers() if variable else synthetic.config_6_trackers()
+    B, T = 200, 7
+    wl = synthetic.make_workload(pose_model, offsets, cfg, B, T, variable_mask=variable)
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window, max_iter=12,
+              joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
+    outs = []
+    for mode in ("frames", "single"):
+        eng = engine_factory(256)
+        eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+        if mode == "frames":
+            if variable:
+                outs.append(eng.run_frames(wl["tgt_pos"], wl["tgt_rot"], wl["joints_tb"], wl["weights_tb"], n_ee=wl["n_ee"], **kw))
+            else:
+                outs.append(eng.run_frames(wl["tgt_pos"], wl["tgt_rot"], wl["joints"], wl["weights"], **kw))
+        else:
+            ps, gs = [], []
+            for t in range(T):
+                if variable:
+                    p_, g_ = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints_tb"][t], wl["weights_tb"][t], n_ee=wl["n_ee"][t], **kw)
+                else:
+                    p_, g_ = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], **kw)
+                ps.append(p_); gs.append(g_)
+            outs.append((np.stack(ps), np.stack(gs)))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.isfinite(outs[0][0]).all()
+
+
 @pytest.mark.parametrize("n_clips", [1, 37, 300])
 def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory, n_clips):
     """Every decoder length (T = 1 + W/4 up to 30 tokens), ragged last tiles: tcgen05 kernels vs the fp32 CUDA-core kernels."""
