@@ -57,8 +57,9 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.rows, self.proc, self.device = [], None, device
+    def __init__(self, device, n_gpus=1):
+        self.rows, self.proc = [], None
+        self.device = str(device) if n_gpus == 1 else ",".join(str(i) for i in range(n_gpus))  # every GPU of the job
 
     def start(self):
         try:
@@ -218,7 +219,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, world)
     if rank == 0:
         clocks.start()
     eng.set_profiling(True)
@@ -238,11 +239,13 @@ def run_ours(args):
     ms_pred, ms_frame, nprof = eng.profile()
     eng.set_profiling(False)
     clk = clocks.stop() if rank == 0 else None
+    ms_by_rank = [ms / K]
     if world > 1:
         dist.barrier()
-        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+        every = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(every, torch.tensor([ms], dtype=torch.float64, device=dev))
+        ms_by_rank = [float(t.item()) / K for t in every]
+        ms = max(float(t.item()) for t in every)  # the job is as fast as its slowest rank
     value = n_total * K / (ms * 1e-3)
 
     # ---- e2e: HOST arrays through the public API (BatchedDragPose.run_frames), every frame's staging + H2D + D2H inside the
@@ -300,6 +303,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk,
         }
+        if world > 1:
+            line["ms_per_step_by_rank"] = [round(v, 4) for v in ms_by_rank]
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_reference(1, 6, args.trackers)
             line["cpu_baseline"] = {"value": v, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample}
