@@ -121,6 +121,108 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+# ----------------------------------------------------------------------------- single-frame latency (second half of the metric)
+LAT_POS = (-2.6648, 0.9977, 3.7518)
+LAT_ROT = (0.6381, 0.0078, -0.7698, 0.0110)
+
+
+def dll_latency(calls=1000):
+    """p50 / p90 wall-clock of drag_pose through the DragPoserDLL C ABI, B = 1, host buffers in and out:
+    Unity parameters (MaxIter 5 / 10, lr 0.01, window 16) and the offline 100 iterations; targets of DragPoserDLL/main.cpp."""
+    import ctypes as C
+    import tempfile
+
+    from dragposer_b200 import build, export_model
+
+    class F3(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+    class Q4(C.Structure):
+        _fields_ = [("w", C.c_float), ("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+    class F2(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+    lib = C.CDLL(build.build_all()[1])
+    V = C.c_void_p
+    lib.init_drag_poser.restype = V
+    lib.set_reference_skeleton.argtypes = [V, C.c_char_p]
+    lib.load_models.argtypes = [V, C.c_char_p]
+    lib.set_mask_and_weights.argtypes = [V, C.POINTER(C.c_float), C.POINTER(F2)]
+    lib.init_drag_model.argtypes = [V, F3, Q4]
+    lib.set_optim_params.argtypes = [V, C.c_float, C.c_float, C.c_int, C.c_float]
+    lib.set_lambdas.argtypes = [V, C.c_float, C.c_float, C.c_int]
+    lib.set_global_pos.argtypes = [V, F3]
+    lib.drag_pose.argtypes = [V, C.c_int, C.POINTER(F3), C.POINTER(Q4), C.POINTER(Q4), C.POINTER(F3)]
+    lib.destroy_drag_poser.argtypes = [V]
+    lib.dp_last_status.argtypes = [V]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_rundrag.npz"))
+    out = {"boundary": "DragPoserDLL C ABI drag_pose, B = 1, 6 trackers, host buffers in/out, window 16", "calls": calls,
+           "early_stop": "stopEpsPos 1e-4, stopEpsRot 1e-2 as in the reference session (the loop ends at MaxIter or at the thresholds)"}
+    with tempfile.TemporaryDirectory() as d:
+        export_model.export(GOLDEN, os.path.join(d, "model.dpm"))
+        for max_iter in (5, 10, 100):
+            h = lib.init_drag_poser()
+            lib.set_reference_skeleton(h, os.path.join(ROOT, "tests", "golden", "skeleton22.bvh").encode())
+            lib.load_models(h, d.encode())
+            mask = (C.c_float * 22)(*g["mask"].tolist())
+            weights = (F2 * 22)(*[F2(*w) for w in g["weights"].tolist()])
+            lib.init_drag_model(h, F3(*LAT_POS), Q4(*LAT_ROT))
+            if lib.dp_last_status(h) != 0:
+                raise SystemExit("bench.py: DragPoserDLL session failed to start")
+            T = g["tgt_pos"].shape[0]
+            pos = [(F3 * 6)(*[F3(*p) for p in g["tgt_pos"][t].tolist()]) for t in range(T)]
+            rot = (Q4 * 6)(*[Q4(*q) for q in g["tgt_quat"].tolist()])
+            res, gp = (Q4 * 22)(), (F3 * 1)()
+            n = calls if max_iter < 100 else max(100, calls // 5)
+            times = []
+            for i in range(n + 20):  # the per-frame call sequence of DragPoser.cs:137-173
+                lib.set_mask_and_weights(h, mask, weights)
+                lib.set_optim_params(h, 0.01 * 0.01, 0.01, max_iter, 0.01)
+                lib.set_lambdas(h, 1, 0.02, 16)
+                t0 = time.perf_counter()
+                lib.drag_pose(h, 6, pos[i % T], rot, res, gp)
+                times.append(time.perf_counter() - t0)
+                lib.set_global_pos(h, gp[0])
+            lib.destroy_drag_poser(h)
+            t = np.sort(np.array(times[20:])) * 1e3
+            out[f"max_iter_{max_iter}"] = {"p50_ms": float(t[len(t) // 2]), "p90_ms": float(t[int(len(t) * 0.9)])}
+    out["p50_ms"] = out["max_iter_5"]["p50_ms"]
+    return out
+
+
+def port_latency(calls=30):
+    """The reference arm of the latency metric: the oracle port's DragPose.run, B = 1, one core, same parameters."""
+    torch_threads = 1
+    import torch
+
+    torch.set_num_threads(torch_threads)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dragposer_port as port
+    from dragposer_b200 import model, synthetic
+
+    cfg = synthetic.config_6_trackers()
+    pm = model.load_folded_npz(GOLDEN)
+    npz = np.load(GOLDEN)
+    out = {"boundary": "oracle port of DragPose.run, B = 1, 6 trackers, one core, window 16", "calls": calls,
+           "early_stop": "stopEpsPos 1e-4, stopEpsRot 1e-2 (the loop ends at MaxIter or at the thresholds)"}
+    for max_iter in (5, 10):
+        wl = synthetic.make_workload(pm, npz["offsets"], cfg, 1, calls + 3)
+        drag = port.PortDragPose(port.PortWeights(npz), model.random_temporal_state(2222))
+        drag.set_initial_state(wl["latent0"], np.zeros((1, 3)), [[1.0, 0, 0, 0]], np.zeros((1, 6)))
+        times = []
+        for t in range(calls + 3):
+            t0 = time.perf_counter()
+            drag.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], stop_eps_pos=1e-4, stop_eps_rot=1e-2, max_iter=max_iter,
+                     min_loss_incr=1e-5, learning_rate=1e-2, lambda_rot=1.0, lambda_temporal=0.02, temporal_future_window=16,
+                     joint_adjustment=None, joint_adjustment_weight=0.0)
+            times.append(time.perf_counter() - t0)
+        t = np.sort(np.array(times[3:])) * 1e3
+        out[f"max_iter_{max_iter}"] = {"p50_ms": float(t[len(t) // 2]), "p90_ms": float(t[int(len(t) * 0.9)])}
+    out["p50_ms"] = out["max_iter_5"]["p50_ms"]
+    return out
+
+
 def cpu_reference(n_warm, n_timed, tracker_cfg, cores=None):
     """All host cores, one clip per core; returns (clip-frames/s, cores, sample text)."""
     import multiprocessing as mp
@@ -151,6 +253,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "clip-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_latency:
+        line["latency"] = port_latency()
     print(json.dumps(line))
 
 
@@ -305,6 +409,9 @@ def run_ours(args):
         }
         if world > 1:
             line["ms_per_step_by_rank"] = [round(v, 4) for v in ms_by_rank]
+        if world == 1 and not args.no_latency:
+            eng.close()  # the DLL session opens its own engine
+            line["latency"] = dll_latency()
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_reference(1, 6, args.trackers)
             line["cpu_baseline"] = {"value": v, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample}
@@ -323,6 +430,7 @@ def main():
     ap.add_argument("--clips", type=int, default=4096, help="clips per GPU (weak scaling)")
     ap.add_argument("--trackers", default="6", choices=["6", "3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 C-ABI latency measurement")
     ap.add_argument("--decoder-path", type=int, default=0, choices=[0, 1, 2, 3], help="0 auto, 1 fp32 CUDA-core decoder, 2 tcgen05 bf16x3, 3 tcgen05 fp16x2")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
