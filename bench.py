@@ -357,10 +357,14 @@ def run_ours(args):
     h_tp, h_tr = wl["tgt_pos"], wl["tgt_rot"]
     run_kw = dict(options=opts)
 
+    host_out = (np.zeros((K, B, 88), np.float32), np.zeros((K, B, 3), np.float32))  # result arrays of the caller, reused
+
     def run_host(t0, t1):
+        out = host_out if t1 - t0 == K else None
         if variable:
-            return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints_tb"][t0:t1], wl["weights_tb"][t0:t1], n_ee=wl["n_ee"][t0:t1], **run_kw)
-        return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints"], wl["weights"], **run_kw)
+            return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints_tb"][t0:t1], wl["weights_tb"][t0:t1], n_ee=wl["n_ee"][t0:t1],
+                                  out=out, **run_kw)
+        return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints"], wl["weights"], out=out, **run_kw)
 
     run_host(0, min(W, 2))
     torch.cuda.synchronize()

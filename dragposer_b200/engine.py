@@ -166,11 +166,12 @@ class BatchedDragPose:
         ne = None if n_ee is None else _i32(n_ee).reshape(B)
         return joints, weights, shared, ne
 
-    def run_frames(self, target_ee_pos, target_ee_rot, mask_joints, weights_joints, n_ee=None, **opts):
+    def run_frames(self, target_ee_pos, target_ee_rot, mask_joints, weights_joints, n_ee=None, out=None, **opts):
         """T consecutive frames from HOST arrays in one call: target_ee_pos (T,B,E,3), target_ee_rot (T,B,E,3,3),
         mask_joints (E,) / weights_joints (E,2) shared by every clip and frame or (T,B,E) / (T,B,E,2), n_ee (T,B) or None
         -> poses (T,B,88), global_pos (T,B,3).  Same results as T calls of run(); the staging and host<->device copies of
-        neighbouring frames overlap the kernels (dp_engine_run_frames_host)."""
+        neighbouring frames overlap the kernels (dp_engine_run_frames_host).  `out` = (poses, global_pos) float32 C-contiguous
+        arrays to write into (a long-running caller reuses them; fresh numpy pages cost a page fault per 4 KB)."""
         B = self.n_clips
         tp = _f32(target_ee_pos)
         T = tp.shape[0]
@@ -185,7 +186,12 @@ class BatchedDragPose:
             assert joints.shape == (T, B, E) and weights.shape == (T, B, E, 2)
         ne = None if n_ee is None else _i32(n_ee).reshape(T, B)
         p = opts["options"].c if "options" in opts else RunOptions(**opts).c
-        pose, gpos = np.empty((T, B, 88), F32), np.empty((T, B, 3), F32)
+        if out is None:
+            pose, gpos = np.empty((T, B, 88), F32), np.empty((T, B, 3), F32)
+        else:
+            pose, gpos = out
+            assert pose.dtype == F32 and gpos.dtype == F32 and pose.flags.c_contiguous and gpos.flags.c_contiguous
+            assert pose.shape == (T, B, 88) and gpos.shape == (T, B, 3)
         _lib.check(self.lib.dp_engine_run_frames_host(self.h, C.byref(p), T, _ptr(ne), _ptr(joints), _ptr(weights), shared,
                                                       _ptr(tp), _ptr(tr), E, _ptr(pose), _ptr(gpos)))
         return pose, gpos
