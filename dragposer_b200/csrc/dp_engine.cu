@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -622,16 +623,24 @@ extern "C" int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, i
   const size_t nj = shared ? S : B * S;
   const PipeLayout L((size_t)e->max_clips, (size_t)P.stride);
   const size_t out_bytes = B * (DP_POSE + 3) * 4;
+  static const bool pipe_trace = getenv("DP_PIPE_TRACE") != nullptr;  // debug: host-side time per pipeline stage
+  double t_stage = 0, t_enq = 0, t_wait = 0, t_unstage = 0;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto unstage = [&](int t) -> int {  // frame t's results: pinned slot -> caller's arrays
     const int slot = t & 1;
+    const double w0 = now();
     CK(cudaEventSynchronize(P.ev_d2h[slot]));
+    const double w1 = now();
+    t_wait += w1 - w0;
     memcpy(out_pose + (size_t)t * B * DP_POSE, P.h_out[slot], B * DP_POSE * 4);
     memcpy(out_gpos + (size_t)t * B * 3, P.h_out[slot] + B * DP_POSE, B * 3 * 4);
+    t_unstage += now() - w1;
     return DP_OK;
   };
   for (int t = 0; t < n_frames; ++t) {
     const int slot = t & 1;
     // (1) stage frame t's inputs while the device works on frame t-1
+    const double s0 = now();
     if (t >= 2) CK(cudaEventSynchronize(P.ev_h2d[slot]));  // the pinned block was last read by the copy of frame t-2
     unsigned char* h = P.h_in[slot];
     if (n_ee) memcpy(h + L.nee, n_ee + (size_t)t * B, B * 4);
@@ -639,6 +648,8 @@ extern "C" int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, i
     memcpy(h + L.w, weights + (shared ? 0 : (size_t)t * nj * 2), nj * 8);
     memcpy(h + L.tp, tgt_pos + (size_t)t * B * S * 3, B * S * 12);
     memcpy(h + L.tr, tgt_rot + (size_t)t * B * S * 9, B * S * 36);
+    const double s1 = now();
+    t_stage += s1 - s0;
     // (2) copy in on its own stream (after frame t-2 has finished reading this device block), run, copy out on a third stream
     if (t >= 2) CK(cudaStreamWaitEvent(P.cs_in, P.ev_run[slot], 0));
     CK(cudaMemcpyAsync(P.d_in[slot], h, L.total, cudaMemcpyHostToDevice, P.cs_in));
@@ -655,11 +666,15 @@ extern "C" int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, i
     CK(cudaStreamWaitEvent(P.cs_out, P.ev_run[slot], 0));
     CK(cudaMemcpyAsync(P.h_out[slot], d_pose, out_bytes, cudaMemcpyDeviceToHost, P.cs_out));
     CK(cudaEventRecord(P.ev_d2h[slot], P.cs_out));
+    t_enq += now() - s1;
     // (3) hand frame t-1's results to the caller
     if (t >= 1) { rc = unstage(t - 1); if (rc) return rc; }
   }
   if (n_frames >= 1) { rc = unstage(n_frames - 1); if (rc) return rc; }
   CK(cudaStreamSynchronize(st));
+  if (pipe_trace && n_frames > 0)
+    fprintf(stderr, "run_frames_host: %d frames, host ms per frame: stage %.3f, enqueue %.3f, wait for device %.3f, unstage %.3f\n", n_frames,
+            t_stage / n_frames, t_enq / n_frames, t_wait / n_frames, t_unstage / n_frames);
   return DP_OK;
 }
 

@@ -160,4 +160,6 @@ def make_workload(model: PoseModel, offsets, cfg: TrackerConfig, n_clips, n_fram
         out["tgt_pos"] = np.take_along_axis(tgt_pos, order_t[..., None], 2)
         out["tgt_rot"] = np.take_along_axis(tgt_rot, order_t[..., None, None], 2)
         out["slot_order"] = order_t
+        for k in ("n_ee", "joints_tb", "weights_tb", "tgt_pos", "tgt_rot", "slot_order"):  # frame-major, C-contiguous like a recorded stream
+            out[k] = np.ascontiguousarray(out[k])
     return out
