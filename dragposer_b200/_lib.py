@@ -30,6 +30,7 @@ class RunParams(C.Structure):
         ("joint_adjust_slot", C.c_int32),
         ("joint_adjust_weight", C.c_float),
         ("decoder_path", C.c_int32),
+        ("targets_world", C.c_int32),
     ]
 
 

@@ -104,6 +104,7 @@ struct DpFrameArgs {
   const float* tgt_pos;
   const float* tgt_rot;
   int ee_stride;
+  int targets_world;  // tgt_pos is world-absolute: subtract the clip's current global position when loading it
   // optimiser
   double eps_pos, eps_rot, min_incr;
   int max_iter;

@@ -471,6 +471,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.target_buf = e->d_target_buf; a.target_rows = W + 1; a.target_index = e->current_index;
   a.n_ee = n_ee; a.joints = joints; a.weights = weights; a.shared_trackers = shared;
   a.tgt_pos = tgt_pos; a.tgt_rot = tgt_rot; a.ee_stride = ee_stride;
+  a.targets_world = p->targets_world ? 1 : 0;
   a.eps_pos = p->stop_eps_pos; a.eps_rot = p->stop_eps_rot; a.min_incr = p->min_loss_incr;
   a.max_iter = p->max_iter;
   a.lambda_rot = p->lambda_rot; a.lambda_t = p->lambda_temporal;

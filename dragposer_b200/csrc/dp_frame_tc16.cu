@@ -226,13 +226,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     }
     ClipTrackers row;
     row.pw = row.r0 = row.r1 = row.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float origin[3] = {0.f, 0.f, 0.f};  // world-absolute targets are taken relative to the clip's current global position
+    if (A.targets_world) { origin[0] = A.gpos[cc * 3]; origin[1] = A.gpos[cc * 3 + 1]; origin[2] = A.gpos[cc * 3 + 2]; }
     const int32_t* jn = A.joints + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride);
     const float* wt = A.weights + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride * 2);
     for (int e = 0; e < ne; ++e) {
       if (jn[e] == lane) {
         const float* tp = A.tgt_pos + ((size_t)cc * A.ee_stride + e) * 3;
         const float* tr = A.tgt_rot + ((size_t)cc * A.ee_stride + e) * 9;
-        row.pw = make_float4(tp[0], tp[1], tp[2], wt[2 * e]);
+        row.pw = make_float4(tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt[2 * e]);
         row.r0 = make_float4(tr[0], tr[1], tr[2], wt[2 * e + 1]);
         row.r1 = make_float4(tr[3], tr[4], tr[5], 0.f);
         row.r2 = make_float4(tr[6], tr[7], tr[8], 0.f);
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const float pj = __shfl_sync(0xffffffffu, p[i], A.adj_joint);
-        adj[i] = (tp[i] - pj) * A.adj_w;
+        adj[i] = ((tp[i] - (A.targets_world ? A.gpos[clip * 3 + i] : 0.0f)) - pj) * A.adj_w;
         gp[i] += adj[i];
       }
     }

@@ -72,13 +72,13 @@ class RunOptions:
 
     def __init__(self, stop_eps_pos=1e-2, stop_eps_rot=1e-2, max_iter=100, min_loss_incr=0.00001, learning_rate=1e-3,
                  lambda_rot=1, lambda_temporal=1, temporal_future_window=60, joint_adjustment_indices=None,
-                 joint_adjustment_weight=0.01, decoder_path=0):
+                 joint_adjustment_weight=0.01, decoder_path=0, targets_world=False):
         self.c = _lib.RunParams(
             float(stop_eps_pos), float(stop_eps_rot), float(min_loss_incr), int(max_iter), float(learning_rate),
             float(lambda_rot), float(lambda_temporal), int(temporal_future_window),
             -1 if joint_adjustment_indices is None else int(joint_adjustment_indices[0]),
             0 if joint_adjustment_indices is None else int(joint_adjustment_indices[1]),
-            float(joint_adjustment_weight), int(decoder_path))
+            float(joint_adjustment_weight), int(decoder_path), int(bool(targets_world)))
 
 
 class BatchedDragPose:

@@ -69,6 +69,68 @@ def evaluate(model_path, input_path, config=None, verbose=False, max_frames=None
     return dict(mpjpe=m, mpeepe=e, time=elapsed, iterations=np.asarray(iters), poses=poses, global_pos=gposs, out_path=out_path)
 
 
+def evaluate_batch(model_path, input_paths, config=None, save=False, seed=2222, quiet=True, initial_latents=None, max_frames=None,
+                   device=0):
+    """Many BVH clips at once: every clip becomes one row of a BatchedDragPose, the ground-truth tracker
+    targets of ALL frames are built once in world coordinates (motion.world_targets) and the whole sequence runs through
+    run_frames with targets_world=True, so nothing on the host depends on the previous frame's result.  Clips must share the
+    skeleton; shorter clips are padded by repeating their last frame (their metrics only use their own frames).
+    Same optimiser settings and metrics as evaluate(); returns one result dict per clip."""
+    from .engine import BatchedDragPose
+
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    cfg = synthetic.TrackerConfig.load(config) if config else synthetic.config_6_trackers()
+    bvhs = [Bvh(p) for p in input_paths]
+    parents, offsets = bvhs[0].skeleton()
+    for b in bvhs[1:]:
+        p2, o2 = b.skeleton()
+        if list(p2) != list(parents) or not np.allclose(o2, offsets, atol=1e-6):
+            raise ValueError("evaluate_batch: all clips must share one skeleton")
+    pm = dpm.load_pose_model(model_path, parents)
+    tdir = model_path if os.path.isdir(model_path) else os.path.dirname(model_path)
+    tm = dpm.load_temporal_model(tdir)
+    joints, weights = cfg.joints, cfg.tracker_weights
+    rots = [b.quaternions() for b in bvhs]
+    clips = [motion.ClipData(r, b.positions[:, 0, :], parents, offsets, pm.mean_dqs, pm.std_dqs) for r, b in zip(rots, bvhs)]
+    lens = [c.n_frames if max_frames is None else min(max_frames, c.n_frames) for c in clips]
+    B, T, E = len(clips), max(lens), len(joints)
+    tgt_pos, tgt_rot = np.empty((T, B, E, 3), np.float32), np.empty((T, B, E, 3, 3), np.float32)
+    latent0 = np.empty((B, dpm.LATENT), np.float32)
+    for b, c in enumerate(clips):
+        tp, tr = motion.world_targets(c, pm.mean_q, pm.std_q, parents, offsets, joints, lens[b])
+        tgt_pos[: lens[b], b], tgt_rot[: lens[b], b] = tp, tr
+        tgt_pos[lens[b]:, b], tgt_rot[lens[b]:, b] = tp[-1], tr[-1]
+        if initial_latents is not None:
+            latent0[b] = np.asarray(initial_latents[b], np.float32).reshape(-1)
+        else:  # mu + eps * exp(0.5 logvar), eps ~ torch.randn (autoencoder.py:19-27), one draw per clip in clip order
+            mu, logvar = pm.encode_np(c.dqs[0].reshape(1, 176))
+            latent0[b] = mu + torch.randn(1, dpm.LATENT).numpy() * np.exp(np.float32(0.5) * logvar)
+    eng = BatchedDragPose(pm, offsets, tm, B, device=device)
+    eng.set_initial_state(latent0, np.stack([c.global_pos[0] for c in clips]), np.stack([c.global_rot[0] for c in clips]),
+                          np.stack([c.heights[0] for c in clips]))
+    start = time.time()
+    poses, gposs = eng.run_frames(tgt_pos, tgt_rot, joints, weights, stop_eps_pos=0.01 * 0.01, stop_eps_rot=0.01, max_iter=100,
+                                  min_loss_incr=0.00001, learning_rate=1e-2, lambda_rot=1, lambda_temporal=cfg.lambda_temporal,
+                                  temporal_future_window=cfg.temporal_future_window, joint_adjustment_indices=cfg.joint_adjustment,
+                                  joint_adjustment_weight=cfg.joint_adjustment_weight, targets_world=True)
+    elapsed = time.time() - start
+    eng.close()
+    results = []
+    for b, (bvh, c) in enumerate(zip(bvhs, clips)):
+        local = motion.result_local_quats(poses[: lens[b], b], pm.mean_q, pm.std_q, parents)
+        out_path = None
+        if save:
+            os.makedirs("data", exist_ok=True)
+            out_path = os.path.join("data", "eval_" + os.path.basename(input_paths[b]))
+            write_result_bvh(bvh, local, gposs[: lens[b], b], out_path)
+        m, e = motion.mpjpe(rots[b][: lens[b]], local.astype(np.float64), np.asarray(offsets, np.float64), parents)
+        if not quiet:
+            print("{}: MPJPE {} MPEEPE {}".format(os.path.basename(input_paths[b]), m, e))
+        results.append(dict(mpjpe=m, mpeepe=e, time=elapsed, poses=poses[: lens[b], b], global_pos=gposs[: lens[b], b], out_path=out_path))
+    return results
+
+
 def write_result_bvh(bvh: Bvh, local_quats, root_pos, path):
     F = local_quats.shape[0]
     with open(path, "w") as fh:
@@ -115,8 +177,18 @@ def main():
     ap.add_argument("input_path", type=str, help="input .bvh file or a directory (every .bvh in it is evaluated)")
     ap.add_argument("--config", type=str, default=None, help="path to the tracker config file")
     ap.add_argument("--verbose", action="store_true", default=False, help="print additional information")
+    ap.add_argument("--batch", action="store_true", default=False,
+                    help="directory input: run all clips together as one batch (one engine row per clip, world-space targets)")
     args = ap.parse_args()
-    if os.path.isdir(args.input_path):
+    if os.path.isdir(args.input_path) and args.batch:
+        files = [os.path.join(args.input_path, fn) for fn in sorted(os.listdir(args.input_path)) if fn.endswith(".bvh")]
+        for fn, r in zip(files, evaluate_batch(args.model_path, files, args.config, save=True, quiet=True)):
+            print("Evaluate {} ------------------------".format(fn))
+            print("Evaluate Loss: {}".format(r["mpjpe"] + r["mpeepe"]))
+            print("Mean Per Joint Position Error: {}".format(r["mpjpe"]))
+            print("Mean End Effector Position Error: {}".format(r["mpeepe"]))
+            print("Time: {}".format(r["time"]))
+    elif os.path.isdir(args.input_path):
         for fn in sorted(os.listdir(args.input_path)):
             if fn.endswith(".bvh"):
                 print("Evaluate {} ------------------------".format(os.path.join(args.input_path, fn)))

@@ -108,6 +108,19 @@ def frame_targets(clip: ClipData, i, mean_q, std_q, parents, offsets, current_gl
     return pos[joints].astype(np.float32), R[joints].astype(np.float32)
 
 
+def world_targets(clip: ClipData, mean_q, std_q, parents, offsets, joints, n_frames=None):
+    """All frames at once: tracker positions (F,E,3) in WORLD coordinates (no dependence on the optimiser's root estimate) and
+    world rotation matrices (F,E,3,3).  With dp_run_params.targets_world the engine subtracts its current global position
+    itself, which is what eval_drag.py:164-202 does on the host once per frame."""
+    F = clip.n_frames if n_frames is None else n_frames
+    q = clip.dqs[:F].reshape(F, -1, 8)[:, :, :4] * np.asarray(std_q).reshape(1, -1, 4) + np.asarray(mean_q).reshape(1, -1, 4)
+    q = q.astype(np.float32)
+    q[:, 0] = clip.global_rot[:F]
+    local = rot.from_root_quat(q, parents)
+    pos, R = fk_np(local, clip.global_pos[:F], offsets, parents)
+    return pos[:, joints].astype(np.float32), R[:, joints].astype(np.float32)
+
+
 def result_local_quats(results_pose, mean_q, std_q, parents):
     """(F,88) standardised result -> (F,J,4) parent-local quaternions (train.py:466-484 with are_root_rot_incr=False)."""
     q = (results_pose * std_q + mean_q).reshape(results_pose.shape[0], -1, 4)

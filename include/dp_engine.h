@@ -62,6 +62,9 @@ typedef struct {
   int32_t joint_adjust_slot;        /* end-effector slot the joint is snapped towards */
   float joint_adjust_weight;
   int32_t decoder_path;             /* 0 = auto, 1 = fp32 CUDA-core decoder, 2 = tcgen05 bf16x3, 3 = tcgen05 fp16x2 */
+  int32_t targets_world;            /* 0: tgt_pos is relative to the clip's current global position (what DragPose.run takes);
+                                       1: tgt_pos is world-absolute and the kernel subtracts the current global position itself
+                                       (eval_drag.py:164-202 -- lets whole BVH clips stream without a per-frame host step) */
 } dp_run_params;
 
 /* Pose-VAE decoder folded to three dense layers + statistics + skeleton.

@@ -55,3 +55,44 @@ def test_eval_drag_on_bvh_excerpt_matches_reference(tmp_path, monkeypatch):
     ref_q = motion.result_local_quats(res["poses"], pm.mean_q, pm.std_q, par)
     dots = np.abs(np.sum(q * ref_q / np.linalg.norm(ref_q, axis=-1, keepdims=True), axis=-1))
     assert dots.min() > 1 - 1e-6
+
+
+def test_evaluate_batch_world_targets_matches_per_frame_loop(tmp_path, monkeypatch):
+    """whole clips streamed with world-absolute targets (the kernel subtracts the current root position)
+    against the per-frame host loop of evaluate(); three rows: the clip twice and a ragged 20-frame excerpt."""
+    import json
+
+    from dragposer_b200 import eval_drag, model, motion, synthetic
+    from dragposer_b200.bvh import Bvh
+
+    monkeypatch.chdir(tmp_path)
+    g = np.load(os.path.join(G, "ref_eval_bvh.npz"))
+    c = synthetic.config_6_trackers()
+    cfg = tmp_path / "6.json"
+    cfg.write_text(json.dumps(dict(mask=c.mask.tolist(), weights=c.weights.tolist(), enable_joint_adjustment=True,
+                                   joint_adjustment_indices=[0, 0], joint_adjustment_weight=1.0, lambda_temporal=0.02,
+                                   temporal_future_window=0)))
+    src = os.path.join(G, "example_48f.bvh")
+    short = tmp_path / "short_20f.bvh"
+    lines = open(src).read().split("\n")
+    m = next(i for i, l in enumerate(lines) if l.strip().startswith("Frames:"))
+    short.write_text("\n".join(lines[:m] + ["Frames: 20"] + lines[m + 1 : m + 2 + 20]) + "\n")
+    npz = os.path.join(G, "model_dancedb.npz")
+    one = eval_drag.evaluate(npz, src, str(cfg), quiet=True, initial_latent=g["latent0"], save=False)
+    res = eval_drag.evaluate_batch(npz, [src, src, str(short)], str(cfg), initial_latents=[g["latent0"]] * 3, save=True)
+    assert len(res) == 3 and res[0]["poses"].shape == (48, 88) and res[2]["poses"].shape == (20, 88)
+    assert np.array_equal(res[0]["poses"], res[1]["poses"])  # identical rows give identical results
+    assert np.array_equal(res[2]["poses"][:20], res[0]["poses"][:20])  # padding of the short clip does not leak into its frames
+    pm = model.load_folded_npz(npz)
+    par, off = Bvh(src).skeleton()
+    z = np.zeros((48, 3))
+    p1, _ = motion.fk_np(motion.result_local_quats(res[0]["poses"], pm.mean_q, pm.std_q, par).astype(np.float64), z, off.astype(np.float64), par)
+    p2, _ = motion.fk_np(motion.result_local_quats(one["poses"], pm.mean_q, pm.std_q, par).astype(np.float64), z, off.astype(np.float64), par)
+    d = np.abs(p1 - p2).max(axis=(1, 2))
+    root = np.abs(res[0]["global_pos"] - one["global_pos"]).max()
+    print(f"evaluate_batch vs per-frame loop: joint diff frames 0-7 {d[:8].max()*1e3:.4f} mm, all {d.max()*1e3:.2f} mm, root {root*1e3:.4f} mm; "
+          f"MPJPE {res[0]['mpjpe']*100:.2f} vs {one['mpjpe']*100:.2f} cm")
+    # same trajectory sensitivity as above: (root - origin) + R o is rounded differently from (root + R o) - origin
+    assert d[:8].max() < 1e-3 and root < 1e-3 and d.max() < 0.05
+    assert abs(res[0]["mpjpe"] - one["mpjpe"]) < 5e-3 and abs(res[0]["mpeepe"] - one["mpeepe"]) < 5e-3
+    assert os.path.exists(res[2]["out_path"]) and Bvh(res[2]["out_path"]).quaternions().shape[0] == 20
