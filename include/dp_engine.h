@@ -169,7 +169,7 @@ int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const floa
 int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
 
 /* Decoder path the last frame actually ran: 1 = fp32 CUDA-core kernel, 2 / 3 = tcgen05 kernel (bf16x3 / fp16x2), 0 = none yet.
- * dp_run_params.decoder_path = 0 picks tcgen05 for batches >= 1024 clips and fp32 below. */
+ * dp_run_params.decoder_path = 0 picks tcgen05 (fp16x2) for batches >= 512 clips (the measured crossover) and fp32 below. */
 int dp_engine_last_decoder_path(const dp_engine* e);
 
 /* Feed-forward GEMMs of the predictor: 0 = tcgen05 tensor cores, fp16x2 split products (default);
