@@ -50,7 +50,6 @@ struct Smem {
   float b1[TP_FF];
   uint64_t wfull[kStages], wfree[kStages], hfull[2], hready[2], b1full;
   uint32_t tmem_base;
-  int next_tile;
 };
 // tensor-memory columns (32-bit words per lane; lane = token row; fp16 operands hold two K elements per word)
 constexpr uint32_t kT_X1 = 0, kT_X2 = 24, kT_H0 = 48, kT_H1 = 112, kT_OUT = 176, kT_COLS = 256;
@@ -104,67 +103,37 @@ constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 64;  // 8 epilogue war
 __global__ void __launch_bounds__(kThreads, 2)
 tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2,
                 const float* __restrict__ x_g, int n_rows, int T, int row_stride, float* __restrict__ out_g, float* __restrict__ part,
-                int* __restrict__ sched, long long* __restrict__ trace) {
+                long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& S = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (n_rows + kTM - 1) / kTM;
+  const int row0 = blockIdx.x * kTM;
   const int n_loc = kChunks / (int)gridDim.y, c0 = (int)blockIdx.y * n_loc;  // this CTA's chunks: c0 .. c0 + n_loc - 1
   const unsigned char* steps = wimg + TP_FF * 4;
   if (trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) trace[7] = clock64();
-  int n_done = 0;
-  if (trace && tid == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[256 + 4 * (blockIdx.y * gridDim.x + blockIdx.x)] = t; }
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&S.wfull[i], 1); mbar_init(&S.wfree[i], 1); }
     mbar_init(&S.hfull[0], 1); mbar_init(&S.hfull[1], 1);
     mbar_init(&S.hready[0], kEpiThreads); mbar_init(&S.hready[1], kEpiThreads);
     mbar_init(&S.b1full, 1);
     fence_barrier_init();
-    // Tiles beyond the grid (sched != null): the FIRST CTA to arrive on each SM books one right away, so that every SM ends up
-    // with two co-resident tiles and then one more, instead of some SMs with four and others with two; what is left after
-    // that is handed out first come first served when a CTA runs out of tiles.  sched[smid] counts arrivals per SM,
-    // sched[255] is the queue head; both are zeroed by the launch.
-    S.next_tile = -1;
-    if (sched) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      if (atomicAdd(&sched[smid % 255u], 1) == 0) {
-        const int e = (int)gridDim.x + atomicAdd(&sched[255], 1);
-        S.next_tile = e < n_tiles ? e : -1;
-      }
-    }
   }
   if (warp == 8) tmem_alloc(&S.tmem_base, kT_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  // A CTA walks the row tiles blockIdx.x, blockIdx.x + gridDim.x, ... (the launch uses at most two CTAs per SM, so 448 tiles
-  // become 296 CTAs of which 152 take a second tile, instead of a second wave that the block scheduler packs two-per-SM on
-  // half of the device).  The mbarriers keep running across tiles: every role toggles its own parity bit after each wait.
-  uint32_t par_w = 0, par_h = 0;  // issuer: wfull / hready parities; producer: wfree (par_w); epilogue: hfull (par_h)
+  if (warp == 9 && elect_one()) {  // TMA producer, part 1 (no waits before the block barrier below): bias slice + first stages
+    mbar_expect_tx(&S.b1full, (uint32_t)(n_loc * kHC * 4));
+    tma_bulk_g2s(S.b1 + c0 * kHC, wimg + (size_t)c0 * kHC * 4, (uint32_t)(n_loc * kHC * 4), &S.b1full);
+    for (int j = 0; j < kStages && j < n_loc + 2; ++j) {  // local step j == image step c0 + j
+      mbar_expect_tx(&S.wfull[j], kStepBytes);
+      tma_bulk_g2s(S.w[j], steps + (size_t)(c0 + j) * kStepBytes, kStepBytes, &S.wfull[j]);
+    }
+  }
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int m = (warp & 3) * 32 + lane;          // token row == TMEM lane owned by this thread
   const int chalf = (warp >> 2) & 1;             // which 32 of a chunk's 64 hidden columns
-  int booked = S.next_tile;  // read after the block barrier above
-  bool first = true;
-  for (int tile = blockIdx.x; tile >= 0 && tile < n_tiles;) {
-  const int row0 = tile * kTM;
-  if (warp == 9) {  // TMA producer, part 1: bias slice once, then the first stages (a later tile first waits for the
-                    // previous tile's MMAs to release each stage -- they have retired by now, this does not block the barrier)
-    if (first && elect_one()) {
-      mbar_expect_tx(&S.b1full, (uint32_t)(n_loc * kHC * 4));
-      tma_bulk_g2s(S.b1 + c0 * kHC, wimg + (size_t)c0 * kHC * 4, (uint32_t)(n_loc * kHC * 4), &S.b1full);
-    }
-    for (int j = 0; j < kStages && j < n_loc + 2; ++j) {  // local step j == image step c0 + j
-      if (!first) { mbar_wait(&S.wfree[j], (par_w >> j) & 1u); par_w ^= 1u << j; }
-      if (elect_one()) {
-        mbar_expect_tx(&S.wfull[j], kStepBytes);
-        tma_bulk_g2s(S.w[j], steps + (size_t)(c0 + j) * kStepBytes, kStepBytes, &S.wfull[j]);
-      }
-      __syncwarp();
-    }
-  }
   const int row = row0 + m;
   const size_t g = row < n_rows ? ((size_t)(row / T) * row_stride + row % T) * TP_D : 0;
   // X tile -> tensor memory as the A operand (two fp16 pieces, two K elements per word); warps 0-3 own the 128 rows
@@ -192,8 +161,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
     // instruction); it only waits on barriers and feeds the tensor pipe -- iteration i: MMA2(i), MMA1(i+2), two commits
     tc_fence_after();
     for (int j = 0; j < 2 && j < n_loc; ++j) {  // prologue: H(0), H(1) from the W1 halves of steps 0, 1
-      mbar_wait(&S.wfull[j], (par_w >> j) & 1u);
-      par_w ^= 1u << j;
+      mbar_wait(&S.wfull[j], 0);
       if (elect_one()) {
         issue_mma1(S, j, tmem, j ? kT_H1 : kT_H0);
         umma_commit(&S.hfull[j]);
@@ -204,12 +172,10 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
     for (int i = 0; i < n_loc; ++i) {
       const int b = i & 1, st = (i + 2) % kStages;
       const uint32_t hcol = b ? kT_H1 : kT_H0;
-      mbar_wait(&S.wfull[st], (par_w >> st) & 1u);  // usually long complete
-      par_w ^= 1u << st;
-      const bool traced = trace && first && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+      mbar_wait(&S.wfull[st], ((i + 2) / kStages) & 1);  // usually long complete
+      const bool traced = trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
       if (traced) trace[i * 8 + 0] = clock64();
-      mbar_wait(&S.hready[b], (par_h >> b) & 1u);   // all epilogue threads converted H(i) into its pieces
-      par_h ^= 1u << b;
+      mbar_wait(&S.hready[b], (i >> 1) & 1);             // all epilogue threads converted H(i) into its pieces
       tc_fence_after();
       if (traced) trace[i * 8 + 1] = clock64();
       if (elect_one()) {
@@ -224,27 +190,25 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
   } else if (warp == 9) {
     // ===== TMA producer warp, part 2: one step per iteration through the kStages ring; a stage is free again when the
     // MMAs that read it have retired (tcgen05.commit by the issuer)
-    for (int j = kStages; j < n_loc + 2; ++j) {
-      const int st = j % kStages;
-      mbar_wait(&S.wfree[st], (par_w >> st) & 1u);
-      par_w ^= 1u << st;
-      if (elect_one()) {
+    if (elect_one()) {
+      for (int j = kStages; j < n_loc + 2; ++j) {
+        const int st = j % kStages;
+        mbar_wait(&S.wfree[st], ((j / kStages) - 1) & 1);
         mbar_expect_tx(&S.wfull[st], kStepBytes);
         tma_bulk_g2s(S.w[st], steps + (size_t)(c0 + j) * kStepBytes, kStepBytes, &S.wfull[st]);
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else if (warp < 8) {
     // ===== epilogue warps: H(i) accumulator -> relu(H / 64 + b1) -> two packed fp16 pieces, all inside tensor memory
-    if (first) mbar_wait(&S.b1full, 0);
+    mbar_wait(&S.b1full, 0);
     for (int i = 0; i < n_loc; ++i) {
       const int b = i & 1;
       const uint32_t hcol = b ? kT_H1 : kT_H0;
       const float* b1 = S.b1 + (c0 + i) * kHC + chalf * 32;
-      mbar_wait(&S.hfull[b], (par_h >> b) & 1u);  // H(i) accumulated; MMA2(i-2) has released this buffer
-      par_h ^= 1u << b;
+      mbar_wait(&S.hfull[b], (i >> 1) & 1);  // H(i) accumulated; MMA2(i-2) has released this buffer
       tc_fence_after();
-      const bool traced = trace && first && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+      const bool traced = trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
       if (traced) trace[i * 8 + 4] = clock64();
       float v[32], p1[16], p2[16];
       tmem_ld32(tmem + lane_base + hcol + (uint32_t)(chalf * 32), v);
@@ -261,13 +225,11 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
       mbar_arrive(&S.hready[b]);
     }
   }
-  if (warp < 8) {  // the last two commits cover MMA2(n_loc - 2) and MMA2(n_loc - 1) (n_loc is even): one more phase per buffer
-    mbar_wait(&S.hfull[0], par_h & 1u);
-    mbar_wait(&S.hfull[1], (par_h >> 1) & 1u);
-    par_h ^= 3u;
-    tc_fence_after();
-  }
   if (warp < 4) {
+    // the last two commits cover MMA2(n_loc - 2) and MMA2(n_loc - 1)
+    if (n_loc >= 2) mbar_wait(&S.hfull[n_loc & 1], (n_loc >> 1) & 1);
+    mbar_wait(&S.hfull[(n_loc - 1) & 1], (((n_loc - 1) >> 1) + 1) & 1);
+    tc_fence_after();
     float o[TP_D];
 #pragma unroll
     for (int j0 = 0; j0 < TP_D; j0 += 16) {
@@ -297,28 +259,8 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
     }
   }
   tc_fence_before();
-  if (trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) trace[first ? 15 : 23] = clock64();
-  if (tid == 0) {  // next tile: the booked one, else the queue (or the static stride without a scheduler)
-    int nt = -1;
-    if (booked >= 0) nt = booked;
-    else if (sched) { const int e = (int)gridDim.x + atomicAdd(&sched[255], 1); nt = e < n_tiles ? e : -1; }
-    else if (tile + (int)gridDim.x < n_tiles) nt = tile + (int)gridDim.x;
-    S.next_tile = nt;
-  }
   __syncthreads();
-  tile = S.next_tile;
-  booked = -1;
-  first = false;
-  ++n_done;
-  }  // tile loop
-  if (trace && tid == 0) {
-    long long t; uint32_t smid;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    long long* r = trace + 256 + 4 * (blockIdx.y * gridDim.x + blockIdx.x);
-    r[1] = t; r[2] = n_done; r[3] = smid;
-  }
-  __syncthreads();
+  if (trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) trace[15] = clock64();
   if (warp == 8) tmem_dealloc(tmem, kT_COLS);
 }
 
@@ -408,42 +350,20 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
   static const int want_trace = getenv("DP_FF_TRACE") ? atoi(getenv("DP_FF_TRACE")) : 0;
   static int n_launch = 0;
   long long* trace = nullptr;
-  if (want_trace && ++n_launch == want_trace && cudaMallocManaged(&trace, (256 + 4 * 4096) * sizeof(long long)) == cudaSuccess) {
-    memset(trace, 0, (256 + 4 * 4096) * sizeof(long long));
-    cudaMemPrefetchAsync(trace, (256 + 4 * 4096) * sizeof(long long), 0, st);
+  if (want_trace && ++n_launch == want_trace && cudaMallocManaged(&trace, kChunks * 8 * sizeof(long long)) == cudaSuccess) {
+    memset(trace, 0, kChunks * 8 * sizeof(long long));
+    cudaMemPrefetchAsync(trace, kChunks * 8 * sizeof(long long), 0, st);
   }
-  const int grid_x = n_split == 1 && part && tiles > 2 * num_sms ? 2 * num_sms : tiles;
-  int* sched = nullptr;
-  if (grid_x < tiles) {  // more tiles than resident CTAs: per-SM arrival counters + queue head in the (otherwise unused) workspace
-    sched = reinterpret_cast<int*>(part);
-    cudaError_t e = cudaMemsetAsync(sched, 0, 256 * sizeof(int), st);
-    if (e != cudaSuccess) return e;
-  }
-  tp_ff_tc_kernel<<<dim3(grid_x, n_split), kThreads, smem, st>>>(wimg, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, part, sched, trace);
+  tp_ff_tc_kernel<<<dim3(tiles, n_split), kThreads, smem, st>>>(wimg, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, part, trace);
   ++*launches;
   if (trace) {
     cudaStreamSynchronize(st);
     const long long t0 = trace[4];
-    printf("FF trace: kernel start %lld, end of first tile %lld, end of last tile %lld (cycles relative to the first H accumulator)\n", trace[7] - t0,
-           trace[15] - t0, trace[23] ? trace[23] - t0 : 0);
+    printf("FF trace: kernel start %lld, end %lld (cycles relative to the first H accumulator)\n", trace[7] - t0, trace[15] - t0);
     printf("FF trace (%d rows, split %d): chunk | issuer: weights ready, pieces ready, issued | epilogue: H ready, loaded, stored\n", n_rows, n_split);
     for (int c = 0; c < kChunks / n_split; ++c)
       printf("  %2d | %7lld %7lld %7lld | %7lld %7lld %7lld\n", c, trace[c * 8] - t0, trace[c * 8 + 1] - t0, trace[c * 8 + 2] - t0, trace[c * 8 + 4] - t0,
              trace[c * 8 + 5] - t0, trace[c * 8 + 6] - t0);
-    {  // per-CTA lifetimes (globaltimer, ns): start, end, tiles, SM
-      const int n_cta = grid_x * n_split;
-      long long t_min = trace[256], t_max = 0;
-      for (int i = 0; i < n_cta; ++i) { if (trace[256 + 4 * i] < t_min) t_min = trace[256 + 4 * i]; if (trace[256 + 4 * i + 1] > t_max) t_max = trace[256 + 4 * i + 1]; }
-      printf("FF trace: %d CTAs, first start to last end %.1f us\n", n_cta, (t_max - t_min) * 1e-3);
-      int per_sm[256] = {0};
-      for (int i = 0; i < n_cta; ++i) per_sm[trace[256 + 4 * i + 3] & 255] += (int)trace[256 + 4 * i + 2];
-      int hist[8] = {0};
-      for (int i = 0; i < 256; ++i) if (per_sm[i] < 8) ++hist[per_sm[i]];
-      printf("FF trace: SMs with 0..7 tiles: %d %d %d %d %d %d %d %d\n", hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7]);
-      for (int i = 0; i < n_cta; i += n_cta / 12 + 1)
-        printf("  CTA %3d: SM %3lld, start +%.1f us, end +%.1f us, %lld tiles\n", i, trace[256 + 4 * i + 3], (trace[256 + 4 * i] - t_min) * 1e-3,
-               (trace[256 + 4 * i + 1] - t_min) * 1e-3, trace[256 + 4 * i + 2]);
-    }
     cudaFree(trace);
   }
   if (n_split > 1) {
