@@ -51,12 +51,28 @@ __global__ void tp_embed_kernel(const float* __restrict__ blob, TpLayout L, cons
     dec_lat[((size_t)b * TP_MAXT) * TP_LAT + tid] = (latent_buf[((size_t)b * DP_PAST + slot) * DP_L + tid] - mu[tid]) / sigma[tid];
   }
   __syncthreads();
+  // 192 threads = 48 features x 4 token groups: a thread owns feature f of tokens kg, kg + 4, kg + 8 (, kg + 12), so every weight
+  // it loads feeds up to four tokens
   const float* W = blob + L.enc_in_w;
-  for (int idx = tid; idx < TP_S * TP_D; idx += blockDim.x) {
-    const int k = idx / TP_D, f = idx % TP_D;
-    float a = blob[L.enc_in_b + f];
-    for (int i = 0; i < TP_ENC_IN; ++i) a = fmaf(x[k][i], W[i * TP_D + f], a);
-    enc[((size_t)b * TP_S + k) * TP_D + f] = a + blob[L.pe + k * TP_D + f];
+  const int f = tid % TP_D, kg = tid / TP_D;
+  if (kg < 4) {
+    const float bias = blob[L.enc_in_b + f];
+    float a0 = bias, a1 = bias, a2 = bias, a3 = bias;
+    const bool has3 = kg + 12 < TP_S;
+#pragma unroll
+    for (int i = 0; i < TP_ENC_IN; ++i) {
+      const float w = W[i * TP_D + f];
+      a0 = fmaf(x[kg][i], w, a0);
+      a1 = fmaf(x[kg + 4][i], w, a1);
+      a2 = fmaf(x[kg + 8][i], w, a2);
+      if (has3) a3 = fmaf(x[kg + 12][i], w, a3);
+    }
+    float* dst = enc + (size_t)b * TP_S * TP_D + f;
+    const float* pe = blob + L.pe + f;
+    dst[kg * TP_D] = a0 + pe[kg * TP_D];
+    dst[(kg + 4) * TP_D] = a1 + pe[(kg + 4) * TP_D];
+    dst[(kg + 8) * TP_D] = a2 + pe[(kg + 8) * TP_D];
+    if (has3) dst[(kg + 12) * TP_D] = a3 + pe[(kg + 12) * TP_D];
   }
 }
 
@@ -371,7 +387,7 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
   cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
   if (err != cudaSuccess) return err;
 
-  tp_embed_kernel<<<B, 128, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
+  tp_embed_kernel<<<B, 192, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
   ++*launches;
   float* e = w.enc;
   float* e2 = w.enc2;
