@@ -276,6 +276,8 @@ def run_ours(args):
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("DP_BENCH_REVERSE_DEVICES"):  # diagnostic: is a slow rank a slow GPU or a slow process?
+        local = world - 1 - local
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -306,7 +308,6 @@ def run_ours(args):
         d_ne = None
     d_pose = torch.empty((T, B, 88), dtype=torch.float32, device=dev)
     d_gpos = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
-    gather_buf = torch.empty((world * B, dpdist.ROW), dtype=torch.float32, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     work_stream = torch.cuda.Stream(device=dev)  # everything timed runs (and is timed) on this stream
     torch.cuda.set_stream(work_stream)
@@ -315,20 +316,20 @@ def run_ours(args):
     def step(t):
         eng.run_frames_device(1, d_tp[t], d_tr[t], d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_pose[t], d_gpos[t],
                               n_ee=d_ne[t] if variable else None, shared=not variable, ee_stride=E, stream=stream, options=opts)
-        if world > 1:  # the only collective: gather of the result rows, in rank order
-            dpdist.gather_results(d_pose[t], d_gpos[t], n_total, out=gather_buf)
 
     for t in range(W):
         step(t)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    if world > 1:  # warm the collective too (NCCL connects its channels on the first call of a shape)
+        dpdist.gather_frames(d_pose[W:W + K], d_gpos[W:W + K], n_total)
     clocks = ClockSampler(local, world)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # before the barrier: every rank must enter the timed region at the same moment
     eng.set_profiling(True)
     l0 = eng.launch_count()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     evs = []
     for k in range(K):
         flush.zero_()  # L2 flush between timed steps (outside the event pair)
@@ -337,19 +338,26 @@ def run_ours(args):
         step(W + k)
         b.record()
         evs.append((a, b))
+    if world > 1:  # the only collective of the job: ONE gather of the K frames' result rows, in rank order, inside the timed region
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dpdist.gather_frames(d_pose[W:W + K], d_gpos[W:W + K], n_total)
+        b.record()
+        evs.append((a, b))
     torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = eng.launch_count() - l0
     ms_pred, ms_frame, nprof = eng.profile()
     eng.set_profiling(False)
     clk = clocks.stop() if rank == 0 else None
-    ms_by_rank = [ms / K]
+    ms_by_rank, parts_by_rank = [ms / K], None
     if world > 1:
         dist.barrier()
-        every = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(every, torch.tensor([ms], dtype=torch.float64, device=dev))
-        ms_by_rank = [float(t.item()) / K for t in every]
-        ms = max(float(t.item()) for t in every)  # the job is as fast as its slowest rank
+        every = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(every, torch.tensor([ms, ms_frame / max(nprof, 1), ms_pred / max(nprof, 1)], dtype=torch.float64, device=dev))
+        ms_by_rank = [float(t[0].item()) / K for t in every]
+        parts_by_rank = [[round(float(t[1].item()), 4), round(float(t[2].item()), 4)] for t in every]
+        ms = max(float(t[0].item()) for t in every)  # the job is as fast as its slowest rank
     value = n_total * K / (ms * 1e-3)
 
     # ---- e2e: HOST arrays through the public API (BatchedDragPose.run_frames), every frame's staging + H2D + D2H inside the
@@ -373,8 +381,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     poses, gposes = run_host(W, W + K)
     last = (poses[-1], gposes[-1])
-    if world > 1:  # final gather of the last frame's poses (NCCL)
-        dpdist.gather_results(torch.from_numpy(last[0]).to(dev), torch.from_numpy(last[1]).to(dev), n_total, out=gather_buf)
+    if world > 1:  # gather of the last frame's poses across the ranks (NCCL)
+        dpdist.gather_results(torch.from_numpy(last[0]).to(dev), torch.from_numpy(last[1]).to(dev), n_total)
         torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -413,6 +421,7 @@ def run_ours(args):
         }
         if world > 1:
             line["ms_per_step_by_rank"] = [round(v, 4) for v in ms_by_rank]
+            line["frame_kernel_and_predictor_ms_by_rank"] = parts_by_rank
         if world == 1 and not args.no_latency:
             eng.close()  # the DLL session opens its own engine
             line["latency"] = dll_latency()

@@ -46,3 +46,24 @@ def gather_results(pose: torch.Tensor, gpos: torch.Tensor, n_clips: int, group=N
         full = out if out is not None else torch.empty((world * per, ROW), dtype=torch.float32, device=pose.device)
         dist.all_gather_into_tensor(full, rows, group=group)
     return full[:n_clips, :88], full[:n_clips, 88:]
+
+
+def gather_frames(pose: torch.Tensor, gpos: torch.Tensor, n_clips: int, group=None):
+    """A whole batch of frames in ONE collective ("or once per run for all T frames"):
+    local pose (T,n,88), gpos (T,n,3) -> pose (T,n_clips,88), gpos (T,n_clips,3) on every rank, row c = clip c.
+    Shards are the contiguous equal shards of shard_bounds (the last one may be short; it is zero padded on the wire)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi, per = shard_bounds(n_clips, world, rank)
+    T, n = pose.shape[0], pose.shape[1]
+    assert n == hi - lo, "local shard size does not match shard_bounds"
+    rows = torch.zeros((T, per, ROW), dtype=torch.float32, device=pose.device)
+    rows[:, :n, :88] = pose
+    rows[:, :n, 88:] = gpos
+    if world == 1:
+        full = rows
+    else:
+        wire = torch.empty((world * T, per, ROW), dtype=torch.float32, device=pose.device)  # rank-major concatenation
+        dist.all_gather_into_tensor(wire, rows, group=group)
+        full = wire.view(world, T, per, ROW).permute(1, 0, 2, 3).reshape(T, world * per, ROW)  # clip order inside every frame
+    return full[:, :n_clips, :88], full[:, :n_clips, 88:]

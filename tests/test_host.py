@@ -141,6 +141,14 @@ gpos = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3) - 0.25
 P, G = dpdist.gather_results(pose, gpos, n)
 assert P.shape == (n, 88) and G.shape == (n, 3)
 assert torch.equal(P[:, 0], torch.arange(n, dtype=torch.float32) + 0.5) and torch.equal(G[:, 2], torch.arange(n, dtype=torch.float32) - 0.25)
+# a batch of frames in one collective: frame t, clip c carries 100 t + c
+T = 3
+pf = pose[None] + 100.0 * torch.arange(T, dtype=torch.float32)[:, None, None]
+gf = gpos[None] + 100.0 * torch.arange(T, dtype=torch.float32)[:, None, None]
+PF, GF = dpdist.gather_frames(pf, gf, n)
+assert PF.shape == (T, n, 88) and GF.shape == (T, n, 3)
+want = 100.0 * torch.arange(T, dtype=torch.float32)[:, None] + torch.arange(n, dtype=torch.float32)[None]
+assert torch.equal(PF[:, :, 5], want + 0.5) and torch.equal(GF[:, :, 1], want - 0.25)
 dist.destroy_process_group()
 print('rank', rank, 'ok')
 """)
