@@ -18,6 +18,10 @@
 // stays as the on-device cross-check (predictor path 1).
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
 #include "dp_common.cuh"
 #include "dp_internal.h"
 #include "dp_temporal.cuh"
@@ -84,6 +88,62 @@ __device__ __forceinline__ void row_to_tmem(const float* __restrict__ src, bool 
   tmem_st_wait();
 }
 
+// Attention of one query row for the head pair 2h, 2h+1 over the S keys of its clip (rows of the K|V tile in shared memory):
+// scores, max-subtracted softmax, P.V.  Packed fp32x2 arithmetic (FFMA2): a float4 of a K or V row is two aligned pairs.
+// NS > 0 fixes the key count at compile time so that the loads of all keys can be issued ahead of the arithmetic.
+template <int NS, int SMAX>
+__device__ __forceinline__ void attend(const float* __restrict__ kv0, const float (&q)[24], int h, int S, float (&o)[24]) {
+  constexpr int N = NS > 0 ? NS : SMAX;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int col = (2 * h + hh) * TP_HD;
+    float2 qp[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) qp[i] = make_float2(q[TP_HD * hh + 2 * i], q[TP_HD * hh + 2 * i + 1]);
+    float sc[N], mx = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      sc[j] = -3.0e38f;
+      if (NS > 0 || j < S) {
+        const float4* kr = reinterpret_cast<const float4*>(kv0 + j * kKvStride + col);
+        const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2];
+        float2 a = __fmul2_rn(qp[0], make_float2(k0.x, k0.y));
+        a = __ffma2_rn(qp[1], make_float2(k0.z, k0.w), a);
+        a = __ffma2_rn(qp[2], make_float2(k1.x, k1.y), a);
+        a = __ffma2_rn(qp[3], make_float2(k1.z, k1.w), a);
+        a = __ffma2_rn(qp[4], make_float2(k2.x, k2.y), a);
+        a = __ffma2_rn(qp[5], make_float2(k2.z, k2.w), a);
+        sc[j] = a.x + a.y;
+        mx = fmaxf(mx, sc[j]);
+      }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (NS > 0 || j < S) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+    const float inv = 1.0f / sum;
+    float2 op[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) op[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (NS > 0 || j < S) {
+        const float4* vr = reinterpret_cast<const float4*>(kv0 + j * kKvStride + TP_D + col);
+        const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2];
+        const float pj = sc[j] * inv;
+        const float2 pp = make_float2(pj, pj);
+        op[0] = __ffma2_rn(pp, make_float2(v0.x, v0.y), op[0]);
+        op[1] = __ffma2_rn(pp, make_float2(v0.z, v0.w), op[1]);
+        op[2] = __ffma2_rn(pp, make_float2(v1.x, v1.y), op[2]);
+        op[3] = __ffma2_rn(pp, make_float2(v1.z, v1.w), op[3]);
+        op[4] = __ffma2_rn(pp, make_float2(v2.x, v2.y), op[4]);
+        op[5] = __ffma2_rn(pp, make_float2(v2.z, v2.w), op[5]);
+      }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { o[TP_HD * hh + 2 * i] = op[i].x; o[TP_HD * hh + 2 * i + 1] = op[i].y; }
+  }
+}
+
 constexpr int kWorkThreads = 256, kThreads = kWorkThreads + 32;  // 8 worker warps + 1 MMA/TMA issuer warp
 
 // Rows of a tile: query row m = g*T + t, key/value row m = g*S + s (g = clip within the tile).  xq == xkv (and T == S) for
@@ -91,10 +151,11 @@ constexpr int kWorkThreads = 256, kThreads = kWorkThreads + 32;  // 8 worker war
 template <int SMAX>
 __global__ void __launch_bounds__(kThreads, 2)
 tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict__ blob, TpNorm N1, const float* __restrict__ xq_g, int T,
-                  int q_stride, const float* __restrict__ xkv_g, int S, int kv_stride, int n_clips, int G, float* __restrict__ out_g) {
+                  int q_stride, const float* __restrict__ xkv_g, int S, int kv_stride, int n_clips, int G, float* __restrict__ out_g, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& S_ = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (trace && blockIdx.x == 0 && tid == 0) trace[0] = clock64();
   const int clip0 = blockIdx.x * G;
   const int g_here = min(G, n_clips - clip0);
   const bool cross = xq_g != xkv_g;
@@ -106,6 +167,7 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
   if (warp == 8) tmem_alloc(&S_.tmem_base, kT_COLS);
   tc_fence_before();
   __syncthreads();
+  if (trace && blockIdx.x == 0 && tid == 0) trace[1] = clock64();
   tc_fence_after();
   const uint32_t tmem = S_.tmem_base;
   if (warp == 8 && elect_one()) {  // the whole weight image of this block: two bulk copies
@@ -124,6 +186,7 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
   else if (warp < 8 && cross) row_to_tmem(xq_g + gq, q_valid, tmem + lane_base + kT_Q1, tmem + lane_base + kT_Q2);
   tc_fence_before();
   __syncthreads();
+  if (trace && blockIdx.x == 0 && tid == 0) trace[2] = clock64();
   if (warp == 8) {
     tc_fence_after();
     mbar_wait(&S_.bar_w, 0);
@@ -170,48 +233,22 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
     tc_fence_before();
   }
   __syncthreads();  // K | V of the tile visible; the accumulator columns are free again
+  if (trace && blockIdx.x == 0 && tid == 0) trace[3] = clock64();
   if (warp < 8) {
     float o[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) o[i] = 0.0f;
-    if (q_valid) {
-      const float* kv0 = &S_.kv[(m / T) * S][0];
+    if (q_valid && S == 1) {  // a single key (first decoder pass): softmax is 1, the output is that key's V row
+      const float4* vr = reinterpret_cast<const float4*>(&S_.kv[m / T][TP_D + 24 * h]);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int col = (2 * h + hh) * TP_HD;
-        const float* qq = q + TP_HD * hh;
-        float sc[SMAX], mx = -3.0e38f;
-#pragma unroll
-        for (int j = 0; j < SMAX; ++j) {
-          sc[j] = -3.0e38f;
-          if (j < S) {
-            const float4* kr = reinterpret_cast<const float4*>(kv0 + j * kKvStride + col);
-            const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2];
-            float a = qq[0] * k0.x;
-            a = fmaf(qq[1], k0.y, a); a = fmaf(qq[2], k0.z, a); a = fmaf(qq[3], k0.w, a);
-            a = fmaf(qq[4], k1.x, a); a = fmaf(qq[5], k1.y, a); a = fmaf(qq[6], k1.z, a); a = fmaf(qq[7], k1.w, a);
-            a = fmaf(qq[8], k2.x, a); a = fmaf(qq[9], k2.y, a); a = fmaf(qq[10], k2.z, a); a = fmaf(qq[11], k2.w, a);
-            sc[j] = a;
-            mx = fmaxf(mx, a);
-          }
-        }
-        float sum = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SMAX; ++j)
-          if (j < S) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
-        const float inv = 1.0f / sum;
-        float* oo = o + TP_HD * hh;
-#pragma unroll
-        for (int j = 0; j < SMAX; ++j)
-          if (j < S) {
-            const float4* vr = reinterpret_cast<const float4*>(kv0 + j * kKvStride + TP_D + col);
-            const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2];
-            const float pj = sc[j] * inv;
-            oo[0] = fmaf(pj, v0.x, oo[0]); oo[1] = fmaf(pj, v0.y, oo[1]); oo[2] = fmaf(pj, v0.z, oo[2]); oo[3] = fmaf(pj, v0.w, oo[3]);
-            oo[4] = fmaf(pj, v1.x, oo[4]); oo[5] = fmaf(pj, v1.y, oo[5]); oo[6] = fmaf(pj, v1.z, oo[6]); oo[7] = fmaf(pj, v1.w, oo[7]);
-            oo[8] = fmaf(pj, v2.x, oo[8]); oo[9] = fmaf(pj, v2.y, oo[9]); oo[10] = fmaf(pj, v2.z, oo[10]); oo[11] = fmaf(pj, v2.w, oo[11]);
-          }
+      for (int i = 0; i < 6; ++i) {
+        const float4 t = vr[i];
+        o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
       }
+    } else if (q_valid) {
+      const float* kv0 = &S_.kv[(m / T) * S][0];
+      if (S == TP_S) attend<TP_S, TP_S>(kv0, q, h, TP_S, o);  // 14 keys (encoder self-, every cross-attention): compile-time trip count
+      else attend<0, SMAX>(kv0, q, h, S, o);
     }
     // attention output (features 24h .. 24h+23 of this row) -> fp16 pieces, words 12h .. 12h+11 of each piece
     float p1[12], p2[12];
@@ -226,6 +263,7 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
   }
   tc_fence_before();
   __syncthreads();
+  if (trace && blockIdx.x == 0 && tid == 0) trace[4] = clock64();
   if (warp == 8) {
     tc_fence_after();
     if (elect_one()) {
@@ -261,6 +299,7 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
   }
   tc_fence_before();
   __syncthreads();
+  if (trace && blockIdx.x == 0 && tid == 0) trace[5] = clock64();
   if (warp == 8) tmem_dealloc(tmem, kT_COLS);
 }
 
@@ -298,7 +337,22 @@ static cudaError_t launch_attn_t(const unsigned char* wimg, const float* blob, c
     configured = true;
   }
   const int G = kTM / (T > S ? T : S);
-  tp_attn_tc_kernel<SMAX><<<(n_clips + G - 1) / G, kThreads, smem, st>>>(wimg, blob, N1, xq, T, q_stride, xkv, S, kv_stride, n_clips, G, out);
+  // debug: DP_ATTN_TRACE=n prints the phase clock of CTA 0 of the n-th launch
+  static const int want_trace = getenv("DP_ATTN_TRACE") ? atoi(getenv("DP_ATTN_TRACE")) : 0;
+  static int n_launch = 0;
+  long long* trace = nullptr;
+  if (want_trace && ++n_launch == want_trace && cudaMallocManaged(&trace, 16 * sizeof(long long)) == cudaSuccess) {
+    memset(trace, 0, 16 * sizeof(long long));
+    cudaMemPrefetchAsync(trace, 16 * sizeof(long long), 0, st);
+  }
+  tp_attn_tc_kernel<SMAX><<<(n_clips + G - 1) / G, kThreads, smem, st>>>(wimg, blob, N1, xq, T, q_stride, xkv, S, kv_stride, n_clips, G, out, trace);
+  if (trace) {
+    cudaStreamSynchronize(st);
+    printf("attention trace (T %d, S %d, %d clips, G %d; cycles): setup+alloc %lld | tokens -> TMEM %lld | projections + K|V,Q epilogue %lld | attention %lld | "
+           "output projection + LayerNorm %lld\n", T, S, n_clips, G, trace[1] - trace[0], trace[2] - trace[1], trace[3] - trace[2], trace[4] - trace[3],
+           trace[5] - trace[4]);
+    cudaFree(trace);
+  }
   return cudaGetLastError();
 }
 
