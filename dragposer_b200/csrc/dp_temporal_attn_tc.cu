@@ -208,27 +208,29 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
     tc_fence_after();
     mbar_wait(&S_.bar_w, 0);  // acquire the TMA-written bias vectors
     const float* b_in = reinterpret_cast<const float*>(S_.w + kOffBin);
-    // K (h = 0) or V (h = 1) of key/value row m -> shared memory
-#pragma unroll
-    for (int j0 = 0; j0 < TP_D; j0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + lane_base + kT_QKV + (uint32_t)(TP_D + TP_D * h + j0), v);
+    // K (h = 0) or V (h = 1) of key/value row m -> shared memory; Q of heads 2h, 2h+1 -> registers (loads batched: two waits)
+    {
+      float v[TP_D];
+      tmem_ld16(tmem + lane_base + kT_QKV + (uint32_t)(TP_D + TP_D * h), reinterpret_cast<float (&)[16]>(v[0]));
+      tmem_ld16(tmem + lane_base + kT_QKV + (uint32_t)(TP_D + TP_D * h + 16), reinterpret_cast<float (&)[16]>(v[16]));
+      tmem_ld16(tmem + lane_base + kT_QKV + (uint32_t)(TP_D + TP_D * h + 32), reinterpret_cast<float (&)[16]>(v[32]));
       tmem_ld_wait();
-      const float* bb = b_in + TP_D + TP_D * h + j0;
+      const float* bb = b_in + TP_D + TP_D * h;
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(&S_.kv[m][TP_D * h + j0 + j]) =
+      for (int j = 0; j < TP_D; j += 4)
+        *reinterpret_cast<float4*>(&S_.kv[m][TP_D * h + j]) =
             make_float4(fmaf(v[j], 1.0f / kWScale, bb[j]), fmaf(v[j + 1], 1.0f / kWScale, bb[j + 1]), fmaf(v[j + 2], 1.0f / kWScale, bb[j + 2]),
                         fmaf(v[j + 3], 1.0f / kWScale, bb[j + 3]));
     }
-    const float qs = rsqrtf((float)TP_HD);
-#pragma unroll
-    for (int j0 = 0; j0 < 24; j0 += 8) {
-      float v[8];
-      tmem_ld8(tmem + lane_base + kT_QKV + (uint32_t)(24 * h + j0), v);
+    {
+      const float qs = rsqrtf((float)TP_HD);
+      float v[24];
+      tmem_ld8(tmem + lane_base + kT_QKV + (uint32_t)(24 * h), reinterpret_cast<float (&)[8]>(v[0]));
+      tmem_ld8(tmem + lane_base + kT_QKV + (uint32_t)(24 * h + 8), reinterpret_cast<float (&)[8]>(v[8]));
+      tmem_ld8(tmem + lane_base + kT_QKV + (uint32_t)(24 * h + 16), reinterpret_cast<float (&)[8]>(v[16]));
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[j0 + j] = fmaf(v[j], 1.0f / kWScale, b_in[24 * h + j0 + j]) * qs;
+      for (int j = 0; j < 24; ++j) q[j] = fmaf(v[j], 1.0f / kWScale, b_in[24 * h + j]) * qs;
     }
     tc_fence_before();
   }
@@ -276,14 +278,10 @@ tp_attn_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restric
     mbar_wait(&S_.bar_mma, 1);
     tc_fence_after();
     float o[TP_D];
-#pragma unroll
-    for (int j0 = 0; j0 < TP_D; j0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + lane_base + kT_QKV + (uint32_t)j0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) o[j0 + j] = v[j];
-    }
+    tmem_ld16(tmem + lane_base + kT_QKV, reinterpret_cast<float (&)[16]>(o[0]));  // three loads in flight, one wait
+    tmem_ld16(tmem + lane_base + kT_QKV + 16u, reinterpret_cast<float (&)[16]>(o[16]));
+    tmem_ld16(tmem + lane_base + kT_QKV + 32u, reinterpret_cast<float (&)[16]>(o[32]));
+    tmem_ld_wait();
     if (q_valid) {
       const float* b_o = reinterpret_cast<const float*>(S_.w + kOffBo);
 #pragma unroll
