@@ -176,6 +176,43 @@ def test_run_frames_pipelined_equals_frame_by_frame(engine_factory, pose_model, 
     assert np.isfinite(outs[0][0]).all()
 
 
+@pytest.mark.parametrize("n_clips", [5000, 1])
+def test_tcgen05_paths_agree_with_cuda_core_path_multi_wave(engine_factory, pose_model, model_npz, n_clips):
+    """More clips than one wave of 32-clip tiles (5000 > 148 x 32) and the single-clip corner, every clip checked: teacher-forced
+    gradients and joint positions of both tensor-core frame kernels against the fp32 CUDA-core kernel (deterministic), then a
+    short optimisation run (robust statistic: an early Adam step is lr * sign(g), so a gradient component inside the fp32 noise
+    can flip a +-lr kick between implementations on a few clips out of thousands)."""
+    rng = np.random.default_rng(3)
+    cfg = synthetic.config_6_trackers()
+    wl = synthetic.make_workload(pose_model, model_npz["offsets"], cfg, n_clips, 2)
+    lat = wl["latent0"] + 0.2 * rng.standard_normal((n_clips, 24)).astype(np.float32)
+    grot = rng.standard_normal((n_clips, 4)).astype(np.float32)
+    grot /= np.linalg.norm(grot, axis=1, keepdims=True)
+    tl = rng.standard_normal((n_clips, 24)).astype(np.float32) * 0.3
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window, max_iter=12,
+              stop_eps_pos=-1.0, stop_eps_rot=-1.0, min_loss_incr=-float("inf"), learning_rate=1e-2,
+              joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
+    grads, out = {}, {}
+    for path in (1, 2, 3):
+        eng = engine_factory(n_clips)
+        grads[path] = eng.eval_gradient(lat, grot, tl, wl["tgt_pos"][0], wl["tgt_rot"][0], wl["joints"], wl["weights"], lambda_rot=1.0,
+                                        lambda_temporal=0.02, decoder_path=path)
+        eng.set_initial_state(wl["latent0"], np.zeros((n_clips, 3)), np.tile([[1.0, 0, 0, 0]], (n_clips, 1)), np.zeros((n_clips, 6)))
+        for t in range(2):
+            out[path] = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], decoder_path=path, **kw)
+        assert eng.last_decoder_path() == path
+        eng.close()
+    for path in (2, 3):
+        rel = np.linalg.norm(grads[path]["grad"] - grads[1]["grad"], axis=1) / np.linalg.norm(grads[1]["grad"], axis=1)
+        dpos = np.abs(grads[path]["pos"] - grads[1]["pos"]).max()
+        dq = np.abs((out[path][0] - out[1][0]) * pose_model.std_q).max(axis=1)  # quaternion components per clip
+        dg = np.abs(out[path][1] - out[1][1]).max()
+        print(f"{n_clips} clips, path {path} vs fp32 path: gradient rel diff max {rel.max():.2e}, joint positions {dpos:.2e} m; after 2 x 12 "
+              f"iterations quaternion diff median {np.median(dq):.2e}, 99th percentile {np.percentile(dq, 99):.2e}, max {dq.max():.2e}, root {dg:.2e}")
+        assert rel.max() <= GRAD_REL and dpos <= 1e-5  # bar: 1e-4 relative, 1 mm
+        assert np.isfinite(out[path][0]).all() and np.median(dq) < 1e-5 and np.percentile(dq, 99) < 1e-3 and dq.max() < 5e-2 and dg < 1e-4
+
+
 @pytest.mark.parametrize("n_clips", [1, 37, 300])
 def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory, n_clips):
     """Every decoder length (T = 1 + W/4 up to 30 tokens), ragged last tiles: tcgen05 kernels vs the fp32 CUDA-core kernels."""
