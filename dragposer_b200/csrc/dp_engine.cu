@@ -125,6 +125,11 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaMalloc(&e->tw.dec_lat, B * TP_MAXT * TP_LAT * 4));
   CK(cudaMalloc(&e->tw.ffpart, DP_FF_PART_FLOATS * 4));
   e->tw.num_sms = e->num_sms;
+  CK(cudaEventCreateWithFlags(&e->tw.ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < DP_PRED_MAX_PARTS - 1; ++i) {
+    CK(cudaStreamCreateWithFlags(&e->tw.st_extra[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->tw.ev_join[i], cudaEventDisableTiming));
+  }
   CK(cudaMalloc(&e->d_pose, B * DP_POSE * 4));
   CK(cudaMalloc(&e->d_gp, B * 3 * 4));
   CK(cudaMallocHost(&e->h_pose, B * DP_POSE * 4));
@@ -164,6 +169,9 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
   cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat); cudaFree(e->tw.ffpart);
+  for (int i = 0; i < DP_PRED_MAX_PARTS - 1; ++i)
+    if (e->tw.st_extra[i]) { cudaStreamSynchronize(e->tw.st_extra[i]); cudaStreamDestroy(e->tw.st_extra[i]); cudaEventDestroy(e->tw.ev_join[i]); }
+  if (e->tw.ev_fork) cudaEventDestroy(e->tw.ev_fork);
   cudaFree(e->d_pose); cudaFree(e->d_gp); cudaFreeHost(e->h_pose); cudaFreeHost(e->h_gp);
   cudaStreamDestroy(e->stream);
   delete e;

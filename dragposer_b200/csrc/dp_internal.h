@@ -3,6 +3,8 @@
 #include "dp_common.cuh"
 #include "dp_temporal.cuh"
 
+#define DP_PRED_MAX_PARTS 4
+#define DP_PRED_PARTS_DEFAULT 2
 struct TpWork {
   float* enc;
   float* enc2;
@@ -11,6 +13,8 @@ struct TpWork {
   float* dec_lat;
   float* ffpart; // hidden-split partial sums of the feed-forward kernel (DP_FF_PART_FLOATS)
   int num_sms;
+  cudaStream_t st_extra[DP_PRED_MAX_PARTS - 1];  // extra streams + fork/join events: the predictor of a large batch runs in parts
+  cudaEvent_t ev_fork, ev_join[DP_PRED_MAX_PARTS - 1];
 };
 #define DP_FF_PART_FLOATS ((size_t)8 * 296 * 128 * TP_D / 2)
 

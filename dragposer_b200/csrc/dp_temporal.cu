@@ -380,12 +380,10 @@ __global__ void tp_out_kernel(const float* __restrict__ blob, TpLayout L, const 
 
 static const size_t kFfSmem = sizeof(float) * (2 * TP_D * FF_HC + FF_TM * (TP_D + 1) + FF_TM * (FF_HC + 1));
 
-cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
-                            const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
-                            int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
-                            long long* launches) {
-  cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
-  if (err != cudaSuccess) return err;
+static cudaError_t run_part(const float* blob, const TpLayout& L, const float* mu, const float* sigma, const float* latent_buf,
+                            const float* disp_buf, const float* height_buf, int head, int B, int window, float* target_buf, const TpWork& w,
+                            size_t part_floats, const unsigned char* fftiles, cudaStream_t st, long long* launches) {
+  cudaError_t err = cudaSuccess;
 
   tp_embed_kernel<<<B, 192, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
   ++*launches;
@@ -400,7 +398,7 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     if (err != cudaSuccess) return err;
     if (fftiles) {
       err = dp_ff_tc_launch(fftiles + (size_t)l * FFT_LAYER_BYTES, blob, L.enc[l].ff, L.enc[l].n2, L.enc_norm, l == TP_NENC - 1, e2,
-                            enc_rows, TP_S, TP_S, e, w.ffpart, DP_FF_PART_FLOATS, w.num_sms, st, launches);
+                            enc_rows, TP_S, TP_S, e, w.ffpart, part_floats, w.num_sms, st, launches);
       if (err != cudaSuccess) return err;
       --*launches;  // counted again below
     } else {
@@ -430,7 +428,7 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
       if (err != cudaSuccess) return err;
       if (fftiles) {
         err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm,
-                              l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, w.ffpart, DP_FF_PART_FLOATS, w.num_sms, st, launches);
+                              l == TP_NDEC - 1, d, rows, T, TP_MAXT, d2, w.ffpart, part_floats, w.num_sms, st, launches);
         if (err != cudaSuccess) return err;
         --*launches;  // counted again below
       } else {
@@ -444,4 +442,42 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     ++*launches;
   }
   return cudaGetLastError();
+}
+
+// The predictor of a large batch runs as several parts on their own streams: each kernel of a part has fewer tiles than the device has
+// CTA slots, so the block scheduler interleaves the parts and fills the tail of one kernel with the head of another
+// (448 tiles on 296 slots otherwise leave a third, half-empty round in every encoder kernel).
+cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
+                            const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
+                            int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
+                            long long* launches) {
+  cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
+  if (err != cudaSuccess) return err;
+  static const int split_min = getenv("DP_PRED_SPLIT_MIN") ? atoi(getenv("DP_PRED_SPLIT_MIN")) : 2048;
+  static const int n_parts_env = getenv("DP_PRED_PARTS") ? atoi(getenv("DP_PRED_PARTS")) : DP_PRED_PARTS_DEFAULT;
+  const int n_parts = n_parts_env < 1 ? 1 : (n_parts_env > DP_PRED_MAX_PARTS ? DP_PRED_MAX_PARTS : n_parts_env);
+  if (!fftiles || n_parts == 1 || B < split_min)
+    return run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, window, target_buf, w, DP_FF_PART_FLOATS, fftiles, st, launches);
+  if ((err = cudaEventRecord(w.ev_fork, st)) != cudaSuccess) return err;
+  const int per = (B + n_parts - 1) / n_parts;
+  for (int p = 0; p < n_parts; ++p) {
+    const int b0 = p * per, nb = (b0 + per <= B ? per : B - b0);
+    if (nb <= 0) break;
+    cudaStream_t sp = p == 0 ? st : w.st_extra[p - 1];
+    if (p > 0 && (err = cudaStreamWaitEvent(sp, w.ev_fork, 0)) != cudaSuccess) return err;
+    TpWork wp = w;
+    wp.enc += (size_t)b0 * TP_S * TP_D; wp.enc2 += (size_t)b0 * TP_S * TP_D;
+    wp.dec += (size_t)b0 * TP_MAXT * TP_D; wp.dec2 += (size_t)b0 * TP_MAXT * TP_D;
+    wp.dec_lat += (size_t)b0 * TP_MAXT * TP_LAT;
+    wp.ffpart += (DP_FF_PART_FLOATS / DP_PRED_MAX_PARTS) * p;
+    err = run_part(blob, L, mu, sigma, latent_buf + (size_t)b0 * DP_PAST * DP_L, disp_buf + (size_t)b0 * DP_PAST * 3,
+                   height_buf + (size_t)b0 * DP_PAST * DP_NH, head, nb, window, target_buf + (size_t)b0 * (window + 1) * TP_LAT, wp,
+                   DP_FF_PART_FLOATS / DP_PRED_MAX_PARTS, fftiles, sp, launches);
+    if (err != cudaSuccess) return err;
+    if (p > 0) {
+      if ((err = cudaEventRecord(w.ev_join[p - 1], sp)) != cudaSuccess) return err;
+      if ((err = cudaStreamWaitEvent(st, w.ev_join[p - 1], 0)) != cudaSuccess) return err;
+    }
+  }
+  return cudaSuccess;
 }
