@@ -34,6 +34,10 @@ class RunParams(C.Structure):
     ]
 
 
+class EncoderModelC(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("A0", "b0", "A1", "b1", "A2", "b2", "mu_w", "mu_b", "logvar_w", "logvar_b")]
+
+
 class PoseModelC(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("A0", "b0", "A1", "b1", "A2", "b2", "mean_q", "std_q", "mean_d", "std_d")] + [
         ("parents", c_int32_p),
@@ -69,6 +73,8 @@ SIGNATURES = {
     "dp_engine_last_decoder_path": (C.c_int, [_VP]),
     "dp_engine_set_predictor_path": (C.c_int, [_VP, C.c_int]),
     "dp_engine_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "dp_engine_set_encoder_model": (C.c_int, [_VP, C.POINTER(EncoderModelC)]),
+    "dp_engine_encode_host": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP]),
     "dp_engine_get_phase_cycles": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),
     "dp_engine_get_profile": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }

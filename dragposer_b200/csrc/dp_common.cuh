@@ -12,6 +12,12 @@
 
 #define DP_J 22
 #define DP_L 24
+// folded encoder widths (autoencoder.py:136-143 folded): 176 -> 112 -> 72 -> 48 -> (mu 24 | logvar 24)
+#define DP_ENC_IN 176
+#define DP_ENC_H0 112
+#define DP_ENC_H1 72
+#define DP_ENC_H2 48
+#define DP_ENC_BLOB_FLOATS (DP_ENC_IN * DP_ENC_H0 + DP_ENC_H0 + DP_ENC_H0 * DP_ENC_H1 + DP_ENC_H1 + DP_ENC_H1 * DP_ENC_H2 + DP_ENC_H2 + DP_ENC_H2 * 48 + 48)
 #define DP_H0 40
 #define DP_H1 60
 #define DP_Y 92

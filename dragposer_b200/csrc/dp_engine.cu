@@ -37,6 +37,7 @@ struct dp_engine {
   DpModelImageTC* d_model_tc = nullptr;
   DpModelImageTC* d_model_tc16 = nullptr;
   uint32_t* d_model_tmem = nullptr;
+  float* d_encoder = nullptr;  // folded encoder blob (DP_ENC_BLOB_FLOATS), set by dp_engine_set_encoder_model
   float* d_tblob = nullptr;
   unsigned char* d_fftiles = nullptr;  // pre-tiled fp16x2 tensor-core weight images of the predictor (DP_TC_TILES_BYTES)
   int predictor_path = 0;              // 0 = tcgen05 FF (default), 1 = fp32 CUDA-core FF
@@ -164,7 +165,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaStreamSynchronize(e->stream);
   free_stage(e);
   free_pipe(e);
-  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_model_tmem); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_model_tmem); cudaFree(e->d_encoder); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
@@ -684,6 +685,53 @@ extern "C" int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, i
   if (pipe_trace && n_frames > 0)
     fprintf(stderr, "run_frames_host: %d frames, host ms per frame: stage %.3f, enqueue %.3f, wait for device %.3f, unstage %.3f\n", n_frames,
             t_stage / n_frames, t_enq / n_frames, t_wait / n_frames, t_unstage / n_frames);
+  return DP_OK;
+}
+
+extern "C" int dp_engine_set_encoder_model(dp_engine* e, const dp_encoder_model* m) {
+  if (!e || !m || !m->A0 || !m->b0 || !m->A1 || !m->b1 || !m->A2 || !m->b2 || !m->mu_w || !m->mu_b || !m->logvar_w || !m->logvar_b)
+    return fail(DP_ERR_ARG, "dp_engine_set_encoder_model: null argument");
+  CK(cudaSetDevice(e->device));
+  std::vector<float> blob;
+  blob.reserve(DP_ENC_BLOB_FLOATS);
+  auto layer = [&](const float* W, const float* b, int out, int in) {  // transposed to [in][out]
+    for (int i = 0; i < in; ++i)
+      for (int o = 0; o < out; ++o) blob.push_back(W[(size_t)o * in + i]);
+    blob.insert(blob.end(), b, b + out);
+  };
+  layer(m->A0, m->b0, DP_ENC_H0, DP_ENC_IN);
+  layer(m->A1, m->b1, DP_ENC_H1, DP_ENC_H0);
+  layer(m->A2, m->b2, DP_ENC_H2, DP_ENC_H1);
+  for (int i = 0; i < DP_ENC_H2; ++i) {  // heads side by side: columns 0..23 mu, 24..47 logvar
+    for (int o = 0; o < DP_L; ++o) blob.push_back(m->mu_w[(size_t)o * DP_ENC_H2 + i]);
+    for (int o = 0; o < DP_L; ++o) blob.push_back(m->logvar_w[(size_t)o * DP_ENC_H2 + i]);
+  }
+  blob.insert(blob.end(), m->mu_b, m->mu_b + DP_L);
+  blob.insert(blob.end(), m->logvar_b, m->logvar_b + DP_L);
+  if (blob.size() != DP_ENC_BLOB_FLOATS) return fail(DP_ERR_STATE, "encoder blob layout");
+  if (!e->d_encoder) CK(cudaMalloc(&e->d_encoder, blob.size() * 4));
+  CK(cudaMemcpy(e->d_encoder, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+  return DP_OK;
+}
+
+extern "C" int dp_engine_encode_host(dp_engine* e, int n, const float* dqs, const float* eps, float* latent) {
+  if (!e || !dqs || !latent || n < 1) return fail(DP_ERR_ARG, "dp_engine_encode_host: null argument");
+  if (!e->d_encoder) return fail(DP_ERR_STATE, "encoder model not set");
+  if (n > e->max_clips) return fail(DP_ERR_ARG, "dp_engine_encode_host: more poses than max_clips");
+  CK(cudaSetDevice(e->device));
+  float *d_dqs = nullptr, *d_eps = nullptr, *d_lat = nullptr;
+  CK(cudaMalloc(&d_dqs, (size_t)n * DP_ENC_IN * 4));
+  CK(cudaMalloc(&d_lat, (size_t)n * DP_L * 4));
+  CK(cudaMemcpyAsync(d_dqs, dqs, (size_t)n * DP_ENC_IN * 4, cudaMemcpyHostToDevice, e->stream));
+  if (eps) {
+    CK(cudaMalloc(&d_eps, (size_t)n * DP_L * 4));
+    CK(cudaMemcpyAsync(d_eps, eps, (size_t)n * DP_L * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  CK(dp_encode_launch(e->d_encoder, d_dqs, d_eps, d_lat, n, e->stream));
+  ++e->launches;
+  CK(cudaMemcpyAsync(latent, d_lat, (size_t)n * DP_L * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(d_dqs); cudaFree(d_eps); cudaFree(d_lat);
   return DP_OK;
 }
 

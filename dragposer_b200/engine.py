@@ -97,6 +97,11 @@ class BatchedDragPose:
         pm = _lib.PoseModelC(*[a.ctypes.data_as(_lib.c_float_p) for a in keep], par.ctypes.data_as(_lib.c_int32_p),
                              self.offsets.ctypes.data_as(_lib.c_float_p))
         _lib.check(self.lib.dp_engine_set_pose_model(self.h, C.byref(pm)))
+        if pose.enc_A:  # folded encoder: clip start-up on the device (encode / set_initial_pose)
+            enc = [_f32(pose.enc_A[0]), _f32(pose.enc_b[0]), _f32(pose.enc_A[1]), _f32(pose.enc_b[1]), _f32(pose.enc_A[2]), _f32(pose.enc_b[2]),
+                   _f32(pose.enc_mu[0]), _f32(pose.enc_mu[1]), _f32(pose.enc_logvar[0]), _f32(pose.enc_logvar[1])]
+            em = _lib.EncoderModelC(*[a.ctypes.data_as(_lib.c_float_p) for a in enc])
+            _lib.check(self.lib.dp_engine_set_encoder_model(self.h, C.byref(em)))
         if temporal is not None:
             blob = pack_temporal(temporal)
             assert blob.size == self.lib.dp_engine_temporal_blob_floats(), (blob.size, self.lib.dp_engine_temporal_blob_floats())
@@ -150,6 +155,21 @@ class BatchedDragPose:
         B = self.n_clips
         a, b, c = _f32(latent_buf).reshape(B, 60, 24), _f32(disp_buf).reshape(B, 60, 3), _f32(height_buf).reshape(B, 60, 6)
         _lib.check(self.lib.dp_engine_set_ring_buffers(self.h, _ptr(a), _ptr(b), _ptr(c)))
+
+    def encode(self, dqs, eps=None):
+        """Folded pose-VAE encoder + reparameterisation on the device: standardised dual quats (n,176) and optional standard-normal
+        draws eps (n,24) -> latent (n,24) = mu + eps * exp(0.5 logvar) (autoencoder.py:19-27,136-143); eps=None gives mu."""
+        x = _f32(dqs).reshape(-1, 176)
+        n = x.shape[0]
+        e = None if eps is None else _f32(eps).reshape(n, 24)
+        out = np.empty((n, 24), F32)
+        _lib.check(self.lib.dp_engine_encode_host(self.h, n, _ptr(x), _ptr(e), _ptr(out)))
+        return out
+
+    def set_initial_pose(self, dqs, global_pos, global_rot, heights, eps=None):
+        """Batched DragPose.set_initial_pose (drag_pose.py:47-64): encode the first pose of every clip on the device, then
+        initialise the clips (ring buffers tiled with the initial latent / heights)."""
+        self.set_initial_state(self.encode(dqs, eps), global_pos, global_rot, heights)
 
     def predict_targets(self, window):
         _lib.check(self.lib.dp_engine_predict_targets(self.h, int(window), None))

@@ -187,6 +187,21 @@ int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double* ms_frame_k
  * [3] Adam + bookkeeping + loop barrier, [4] kinematics + loss + adjoint pass, [5..7] reserved (0). */
 int dp_engine_get_phase_cycles(dp_engine* e, unsigned long long* cycles8);
 
+/* Clip start-up on the device.  Folded pose-VAE encoder: three dense layers + the mu / logvar heads
+ * (autoencoder.py:136-143 folded; python: model.PoseModel.enc_*), HOST pointers, row-major (out,in) like the decoder. */
+typedef struct {
+  const float* A0; const float* b0;         /* (112,176), (112) */
+  const float* A1; const float* b1;         /* (72,112), (72) */
+  const float* A2; const float* b2;         /* (48,72), (48) */
+  const float* mu_w; const float* mu_b;     /* (24,48), (24) */
+  const float* logvar_w; const float* logvar_b;
+} dp_encoder_model;
+int dp_engine_set_encoder_model(dp_engine* e, const dp_encoder_model* m);
+/* latent (n,24) = mu + eps * exp(0.5 logvar) of the standardised dual-quaternion poses dqs (n,176); eps (n,24) are the
+ * caller's standard-normal draws (torch's RNG stream cannot be reproduced on the device), NULL gives the mean.  HOST
+ * pointers; n <= max_clips.  Feed the result to dp_engine_init_clips. */
+int dp_engine_encode_host(dp_engine* e, int n, const float* dqs, const float* eps, float* latent);
+
 /* Number of kernels launched by this engine since creation (bench "gpu_launches"). */
 long long dp_engine_launch_count(const dp_engine* e);
 

@@ -176,6 +176,25 @@ def test_run_frames_pipelined_equals_frame_by_frame(engine_factory, pose_model, 
     assert np.isfinite(outs[0][0]).all()
 
 
+def test_device_encoder_matches_folded_encoder(engine_factory, pose_model):
+    """clip start-up on the device vs the host restatement of the folded encoder (model.PoseModel.encode_np)."""
+    rng = np.random.default_rng(9)
+    n = 300
+    dqs = rng.standard_normal((n, 176)).astype(np.float32)
+    eps = rng.standard_normal((n, 24)).astype(np.float32)
+    eng = engine_factory(512)
+    mu, logvar = pose_model.encode_np(dqs)
+    got_mu = eng.encode(dqs)
+    got = eng.encode(dqs, eps)
+    want = mu + eps * np.exp(np.float32(0.5) * logvar)
+    scale = max(1.0, float(np.abs(want).max()))
+    print(f"device encoder: mu diff {np.abs(got_mu - mu).max():.2e}, latent diff {np.abs(got - want).max():.2e} (|latent| max {scale:.2f})")
+    assert np.abs(got_mu - mu).max() <= 2e-5 * scale and np.abs(got - want).max() <= 2e-5 * scale
+    eng.set_initial_pose(dqs, np.zeros((n, 3)), np.tile([[1.0, 0, 0, 0]], (n, 1)), np.zeros((n, 6)), eps)
+    st = eng.state()
+    assert np.array_equal(st["latent"], got) and np.array_equal(st["latent_buf"][:, 17], got)
+
+
 @pytest.mark.parametrize("n_clips", [5000, 1])
 def test_tcgen05_paths_agree_with_cuda_core_path_multi_wave(engine_factory, pose_model, model_npz, n_clips):
     """More clips than one wave of 32-clip tiles (5000 > 148 x 32) and the single-clip corner, every clip checked: teacher-forced
