@@ -96,17 +96,16 @@ def evaluate_batch(model_path, input_paths, config=None, save=False, seed=2222, 
     lens = [c.n_frames if max_frames is None else min(max_frames, c.n_frames) for c in clips]
     B, T, E = len(clips), max(lens), len(joints)
     tgt_pos, tgt_rot = np.empty((T, B, E, 3), np.float32), np.empty((T, B, E, 3, 3), np.float32)
-    latent0 = np.empty((B, dpm.LATENT), np.float32)
     for b, c in enumerate(clips):
         tp, tr = motion.world_targets(c, pm.mean_q, pm.std_q, parents, offsets, joints, lens[b])
         tgt_pos[: lens[b], b], tgt_rot[: lens[b], b] = tp, tr
         tgt_pos[lens[b]:, b], tgt_rot[lens[b]:, b] = tp[-1], tr[-1]
-        if initial_latents is not None:
-            latent0[b] = np.asarray(initial_latents[b], np.float32).reshape(-1)
-        else:  # mu + eps * exp(0.5 logvar), eps ~ torch.randn (autoencoder.py:19-27), one draw per clip in clip order
-            mu, logvar = pm.encode_np(c.dqs[0].reshape(1, 176))
-            latent0[b] = mu + torch.randn(1, dpm.LATENT).numpy() * np.exp(np.float32(0.5) * logvar)
     eng = BatchedDragPose(pm, offsets, tm, B, device=device)
+    if initial_latents is not None:
+        latent0 = np.stack([np.asarray(z, np.float32).reshape(-1) for z in initial_latents])
+    else:  # mu + eps * exp(0.5 logvar) on the device; eps ~ torch.randn, one draw per clip in clip order (autoencoder.py:19-27)
+        eps = np.concatenate([torch.randn(1, dpm.LATENT).numpy() for _ in clips])
+        latent0 = eng.encode(np.stack([c.dqs[0] for c in clips]), eps)
     eng.set_initial_state(latent0, np.stack([c.global_pos[0] for c in clips]), np.stack([c.global_rot[0] for c in clips]),
                           np.stack([c.heights[0] for c in clips]))
     start = time.time()

@@ -98,3 +98,16 @@ def test_evaluate_batch_world_targets_matches_per_frame_loop(tmp_path, monkeypat
     assert d[:8].max() < 1e-3 and root < 1e-3 and d.max() < 0.05
     assert abs(res[0]["mpjpe"] - one["mpjpe"]) < 5e-3 and abs(res[0]["mpeepe"] - one["mpeepe"]) < 5e-3
     assert os.path.exists(res[2]["out_path"]) and Bvh(res[2]["out_path"]).quaternions().shape[0] == 20
+
+
+def test_evaluate_batch_default_start_uses_device_encoder(tmp_path, monkeypatch):
+    """Without recorded latents evaluate_batch encodes the first poses on the device with torch-drawn eps (seed 2222):
+    runs end to end, finite, and accurate on the excerpt."""
+    from dragposer_b200 import eval_drag
+
+    monkeypatch.chdir(tmp_path)
+    src = os.path.join(G, "example_48f.bvh")
+    res = eval_drag.evaluate_batch(os.path.join(G, "model_dancedb.npz"), [src, src], None, max_frames=16)
+    assert len(res) == 2 and res[0]["poses"].shape == (16, 88) and np.isfinite(res[0]["poses"]).all()
+    assert not np.array_equal(res[0]["poses"], res[1]["poses"])  # two different reparameterisation draws
+    assert res[0]["mpjpe"] < 0.06 and res[1]["mpjpe"] < 0.06
