@@ -73,6 +73,7 @@ SIGNATURES = {
     "dp_engine_last_decoder_path": (C.c_int, [_VP]),
     "dp_engine_set_predictor_path": (C.c_int, [_VP, C.c_int]),
     "dp_engine_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "dp_engine_pose_error_host": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP]),
     "dp_engine_set_encoder_model": (C.c_int, [_VP, C.POINTER(EncoderModelC)]),
     "dp_engine_encode_host": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP]),
     "dp_engine_get_phase_cycles": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),

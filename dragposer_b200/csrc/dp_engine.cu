@@ -735,6 +735,23 @@ extern "C" int dp_engine_encode_host(dp_engine* e, int n, const float* dqs, cons
   return DP_OK;
 }
 
+extern "C" int dp_engine_pose_error_host(dp_engine* e, int n, const float* pose_a, const float* pose_b, float* err) {
+  if (!e || !pose_a || !pose_b || !err || n < 1) return fail(DP_ERR_ARG, "dp_engine_pose_error_host: null argument");
+  if (!e->has_pose) return fail(DP_ERR_STATE, "pose model not set");
+  CK(cudaSetDevice(e->device));
+  float *d_a = nullptr, *d_b = nullptr, *d_e = nullptr;
+  const size_t bytes = (size_t)n * DP_POSE * 4;
+  CK(cudaMalloc(&d_a, bytes)); CK(cudaMalloc(&d_b, bytes)); CK(cudaMalloc(&d_e, (size_t)n * 8));
+  CK(cudaMemcpyAsync(d_a, pose_a, bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(d_b, pose_b, bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(dp_pose_error_launch(e->d_model, d_a, d_b, n, d_e, e->stream));
+  ++e->launches;
+  CK(cudaMemcpyAsync(err, d_e, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_e);
+  return DP_OK;
+}
+
 extern "C" int dp_engine_get_frame_stats(dp_engine* e, int32_t* iters, float* losses) {
   if (!e) return fail(DP_ERR_ARG, "null engine");
   CK(cudaSetDevice(e->device));

@@ -40,3 +40,5 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
                             cudaStream_t st, long long* launches);
 // blob: [A0t (176x112) | b0 | A1t (112x72) | b1 | A2t (72x48) | b2 | head_t (48x48: mu | logvar columns) | head_b (48)], DP_ENC_BLOB_FLOATS
 cudaError_t dp_encode_launch(const float* blob, const float* dqs, const float* eps, float* latent, int n, cudaStream_t st);
+// per row: mean joint distance, mean end-effector distance of two poses in the engine's output format (root at the origin)
+cudaError_t dp_pose_error_launch(const DpModelImage* model, const float* pose_a, const float* pose_b, int n, float* err, cudaStream_t st);

@@ -171,6 +171,15 @@ class BatchedDragPose:
         initialise the clips (ring buffers tiled with the initial latent / heights)."""
         self.set_initial_state(self.encode(dqs, eps), global_pos, global_rot, heights)
 
+    def pose_error(self, pose_a, pose_b):
+        """Per-row MPJPE and MPEEPE (metres) between two sets of poses in the engine's output format (n,88), computed on the
+        device (eval_metrics.py:6-32 with the root at the origin) -> (mpjpe (n,), mpeepe (n,))."""
+        a, b = _f32(pose_a).reshape(-1, 88), _f32(pose_b).reshape(-1, 88)
+        assert a.shape == b.shape
+        err = np.empty((a.shape[0], 2), F32)
+        _lib.check(self.lib.dp_engine_pose_error_host(self.h, a.shape[0], _ptr(a), _ptr(b), _ptr(err)))
+        return err[:, 0], err[:, 1]
+
     def predict_targets(self, window):
         _lib.check(self.lib.dp_engine_predict_targets(self.h, int(window), None))
         return self.state(window)["target_buf"]

@@ -202,6 +202,12 @@ int dp_engine_set_encoder_model(dp_engine* e, const dp_encoder_model* m);
  * pointers; n <= max_clips.  Feed the result to dp_engine_init_clips. */
 int dp_engine_encode_host(dp_engine* e, int n, const float* dqs, const float* eps, float* latent);
 
+/* Accuracy metrics on the device (eval_metrics.py:6-32).  pose_a, pose_b: (n,88) poses in the engine's
+ * output format (standardised root-space quaternions, root slot = standardised world root rotation); err (n,2) receives per
+ * row the mean joint distance (MPJPE) and the mean distance of the sparse end effectors 4, 8, 13, 17, 21 (MPEEPE), both
+ * skeletons with the root at the origin.  HOST pointers. */
+int dp_engine_pose_error_host(dp_engine* e, int n, const float* pose_a, const float* pose_b, float* err);
+
 /* Number of kernels launched by this engine since creation (bench "gpu_launches"). */
 long long dp_engine_launch_count(const dp_engine* e);
 

@@ -111,3 +111,29 @@ def test_evaluate_batch_default_start_uses_device_encoder(tmp_path, monkeypatch)
     assert len(res) == 2 and res[0]["poses"].shape == (16, 88) and np.isfinite(res[0]["poses"]).all()
     assert not np.array_equal(res[0]["poses"], res[1]["poses"])  # two different reparameterisation draws
     assert res[0]["mpjpe"] < 0.06 and res[1]["mpjpe"] < 0.06
+
+
+def test_device_pose_error_matches_host_metrics(tmp_path):
+    """MPJPE / MPEEPE on the device against motion.mpjpe (the host restatement of eval_metrics.py)."""
+    from dragposer_b200 import model, motion
+    from dragposer_b200.bvh import Bvh
+    from dragposer_b200.engine import BatchedDragPose
+
+    g = np.load(os.path.join(G, "ref_eval_bvh.npz"))
+    pm = model.load_folded_npz(os.path.join(G, "model_dancedb.npz"))
+    b = Bvh(os.path.join(G, "example_48f.bvh"))
+    par, off = b.skeleton()
+    tm = model.temporal_from_state(model.random_temporal_state(2222))
+    clip = motion.ClipData(b.quaternions(), b.positions[:, 0, :], par, off, pm.mean_dqs, pm.std_dqs)
+    # ground truth in the engine's pose format: quaternion half of the dual quats, root slot = standardised world root rotation
+    gt = clip.dqs.reshape(48, 22, 8)[:, :, :4].reshape(48, 88).copy()
+    gt[:, :4] = (clip.global_rot - pm.mean_q[:4]) / pm.std_q[:4]
+    eng = BatchedDragPose(pm, off, tm, 64)
+    mp, me = eng.pose_error(g["pose"], gt)
+    eng.close()
+    res_local = motion.result_local_quats(g["pose"], pm.mean_q, pm.std_q, par).astype(np.float64)
+    want_m, want_e = motion.mpjpe(b.quaternions(), res_local, off.astype(np.float64), par)
+    print(f"device MPJPE {mp.mean()*100:.4f} cm (host {want_m*100:.4f}), MPEEPE {me.mean()*100:.4f} cm (host {want_e*100:.4f})")
+    assert abs(mp.mean() - want_m) < 1e-5 and abs(me.mean() - want_e) < 1e-5
+    same_m, same_e = BatchedDragPose(pm, off, tm, 64).pose_error(gt, gt)
+    assert same_m.max() == 0.0 and same_e.max() == 0.0
