@@ -87,8 +87,7 @@ static_assert(sizeof(DpModelImageTC) % 16 == 0, "bulk copy needs a multiple of 1
 
 struct DpFrameArgs {
   const DpModelImage* model;
-  const DpModelImageTC* model_tc;    // bf16x3 pieces
-  const DpModelImageTC* model_tc16;  // fp16x2 pieces of 16 W (w[2] unused)
+  const DpModelImageTC* model_tc;    // tables + bf16x3 weight pieces (the tensor-memory kernel copies only the table prefix)
   const uint32_t* model_tmem;        // fp16x2 pieces of 16 W and 16 W^T as tensor-memory words [DP_TC_TMEM_WORDS][128]
   int n_clips;
   // carried state (HBM)

@@ -35,7 +35,6 @@ struct dp_engine {
   bool has_pose = false, has_temporal = false;
   DpModelImage* d_model = nullptr;
   DpModelImageTC* d_model_tc = nullptr;
-  DpModelImageTC* d_model_tc16 = nullptr;
   uint32_t* d_model_tmem = nullptr;
   float* d_encoder = nullptr;  // folded encoder blob (DP_ENC_BLOB_FLOATS), set by dp_engine_set_encoder_model
   float* d_tblob = nullptr;
@@ -105,7 +104,6 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&e->d_model, sizeof(DpModelImage)));
   CK(cudaMalloc(&e->d_model_tc, sizeof(DpModelImageTC)));
-  CK(cudaMalloc(&e->d_model_tc16, sizeof(DpModelImageTC)));
   CK(cudaMalloc(&e->d_model_tmem, (size_t)DP_TC_TMEM_WORDS * 128 * 4));
   CK(cudaMalloc(&e->d_latent, B * DP_L * 4));
   CK(cudaMalloc(&e->d_gpos, B * 3 * 4));
@@ -165,7 +163,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   cudaStreamSynchronize(e->stream);
   free_stage(e);
   free_pipe(e);
-  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tc16); cudaFree(e->d_model_tmem); cudaFree(e->d_encoder); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
+  cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tmem); cudaFree(e->d_encoder); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
   cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
@@ -300,23 +298,7 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     memcpy(T.height_slot, I.height_slot, sizeof(I.height_slot));
     memcpy(T.pad, I.pad, sizeof(I.pad));
     CK(cudaMemcpy(e->d_model_tc, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
-    // fp16x2 variant: two fp16 pieces of 16 W in the same layout (third piece unused; the kernel copies a prefix)
-    memset(T.w, 0, sizeof(T.w));
-    for (int l = 0; l < 3; ++l) {
-      const int K = dims[l], N = dims[l + 1];
-      for (int o = 0; o < N; ++o)
-        for (int i = 0; i < K; ++i) {
-          float r = 16.0f * A[l][o * K + i];
-          const uint32_t at = woff[l] + (o / 8) * 128 * (kin[l] / 8) + (i / 8) * 128 + (o % 8) * 16 + (i % 8) * 2;
-          for (int p = 0; p < 2; ++p) {
-            const __half h = __float2half_rn(r);
-            memcpy(&T.w[p][at], &h, 2);
-            r -= __half2float(h);
-          }
-        }
-    }
-    CK(cudaMemcpy(e->d_model_tc16, raw_tc.data(), raw_tc.size(), cudaMemcpyHostToDevice));
-    // tensor-memory image of the same fp16 pieces: lane m, word c holds K elements (2c', 2c'+1) of row m of the A operand --
+    // tensor-memory image (fp16x2 pieces of 16 W): lane m, word c holds K elements (2c', 2c'+1) of row m of the A operand --
     // forward layer l: A = 16 W_l (rows = outputs), backward: A = 16 W_l^T (rows = inputs); order and widths as WT<> in
     // dp_frame_tc16.cu: fwd0 (K 32) fwd1 (48) fwd2 (64) bwd2 (96) bwd1 (64) bwd0 (48), two pieces each
     std::vector<uint32_t> tm((size_t)DP_TC_TMEM_WORDS * 128, 0u);
@@ -471,7 +453,6 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   DpFrameArgs a{};
   a.model = e->d_model;
   a.model_tc = e->d_model_tc;
-  a.model_tc16 = e->d_model_tc16;
   a.model_tmem = e->d_model_tmem;
   a.n_clips = e->n_clips;
   a.latent = e->d_latent; a.gpos = e->d_gpos; a.grot = e->d_grot;
@@ -805,7 +786,7 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   CK(cudaMemcpy(d_tr, tgt_rot, N * S * 36, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_adam, 0, 8));
   DpFrameArgs a{};
-  a.model = e->d_model; a.model_tc = e->d_model_tc; a.model_tc16 = e->d_model_tc16; a.model_tmem = e->d_model_tmem; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
+  a.model = e->d_model; a.model_tc = e->d_model_tc; a.model_tmem = e->d_model_tmem; a.n_clips = n; a.latent = d_lat; a.grot = d_g;
   a.target_buf = d_t; a.target_rows = 1; a.target_index = 0;
   a.n_ee = d_ne; a.joints = d_j; a.weights = d_w; a.shared_trackers = shared; a.tgt_pos = d_tp; a.tgt_rot = d_tr;
   a.ee_stride = ee_stride;

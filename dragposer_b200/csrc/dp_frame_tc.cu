@@ -1,4 +1,5 @@
-// dp_frame_tc.cu -- persistent per-frame optimisation kernel with the decoder on tcgen05 tensor cores.
+// dp_frame_tc.cu -- persistent per-frame optimisation kernel with the decoder on tcgen05 tensor cores, bf16x3 split products,
+// weights in shared memory (decoder path 2; the default batch path is dp_frame_tc16.cu, which this design preceded).
 //
 // Same contract as dp_frame_simt.cu (one launch == one frame of DragPose.run, python/src/drag_pose.py:196-414,
 // for every clip) but the six dense layers of an iteration (decoder forward 24->40->60->92 and its
@@ -8,17 +9,15 @@
 //
 // * transposed mapping: the WEIGHTS are the 128-row A operand, the CTA's 32 clips are the N dimension, so
 //   4096 clips occupy 128 SMs (clips-as-M would fill only 32).
-// * precision: split products on kind::f16 (see PREC below): fp16x2 (default) or bf16x3, both ~fp32-exact
-//   (gradient 2.5e-6 / 3.0e-6 relative vs 1.8e-6 for the fp32 kernel; plain TF32 would be 1.8e-3 and bf16x2
-//   1e-4 -- both break the 1e-4 bar).  kind::f16 rather than kind::tf32 because tf32 produces zeros for
-//   MN-major operands in the no-swizzle layout (measured) while f16/bf16 accept them: ONE weight image
-//   serves the forward GEMM (A K-major) and the transposed backward GEMM (A MN-major), 42 KB instead of
-//   155 KB of shared memory.
+// * precision: bf16x3 split products on kind::f16 -- x = x1 + x2 + x3 (bf16), six products
+//   (3,1)(2,2)(1,3)(2,1)(1,2)(1,1) accumulated in fp32: 1.3e-7 relative per GEMM, gradient 3.0e-6 relative (the fp32
+//   kernel: 1.8e-6; plain TF32 would be 1.8e-3 and bf16x2 1e-4 -- both break the 1e-4 bar).  kind::f16 rather than
+//   kind::tf32 because tf32 produces zeros for MN-major operands in the no-swizzle layout (measured) while bf16 accepts
+//   them: ONE weight image serves the forward GEMM (A K-major) and the transposed backward GEMM (A MN-major), 63 KB.
 // * activations never leave the SM: epilogue warps read the accumulator with tcgen05.ld (lane == feature),
 //   apply bias / LeakyReLU (slope bits stay in registers for the backward pass), split to bf16 pieces and
 //   write the next layer's B operand (MN-major image, one STS.128 per 8 clips).
-// * kinematics, loss, adjoint, Adam, early stopping and the frame epilogue are the warp-per-clip code shared
-//   with the fp32 kernel (dp_fk.cuh).
+// * kinematics, loss and adjoint: the packed two-clip pass of dp_fk2.cuh; Adam and early stopping per warp.
 #include "dp_fk2.cuh"
 #include "dp_internal.h"
 #include "dp_umma.cuh"
@@ -26,11 +25,8 @@
 namespace {
 
 // Tile geometry.  NC clips (the UMMA N dimension) per CTA, two clips per warp in the per-clip phases, eight epilogue warps
-// (TMEM lane quarter = warp % 4, clip half = warp / 4).  Two instantiations:
-//   NC = 32, 16 warps, one CTA per SM   (bf16x3: its three-piece image does not fit twice)
-//   NC = 16,  8 warps, TWO CTAs per SM  (fp16x2, default): while one CTA waits for the tensor pipe or sits in a block barrier
-//   the other one runs its kinematics -- the phase clock (dp_engine_get_phase_cycles) showed the single-CTA kernel spending
-//   46 % of an iteration in tensor/epilogue/Adam phases with the CUDA cores mostly idle.
+// (TMEM lane quarter = warp % 4, clip half = warp / 4).  Instantiated for NC = 32: 16 warps, one CTA per SM (the three-piece
+// weight image does not fit twice).
 template <int NC>
 struct Geo {
   static constexpr int kWarps = NC / 2;
@@ -41,25 +37,18 @@ struct Geo {
 };
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kB_SBO = 128;
-// PREC 0: bf16x3 -- x = x1 + x2 + x3 (bf16), six products (3,1)(2,2)(1,3)(2,1)(1,2)(1,1): 1.3e-7 relative per GEMM.
-// PREC 1: fp16x2 -- x = x1 + x2 (fp16, 22 mantissa bits), three products (2,1)(1,2)(1,1): ~5e-7 relative per GEMM at half the
-//         tensor and epilogue work.  fp16's narrow exponent is handled by exact power-of-two scalings: the weight image stores
-//         16 W (undone in every epilogue), and the backward pass carries dL/dy scaled per clip so that its largest component
-//         is in [16, 32) (undone when dL/dz is written); forward activations (|a| < 2^6 here) need no scaling.
-constexpr float kWScale = 16.0f;
 constexpr int kMaxPieces = 3;
 enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
 
-template <int PREC, int NC>
+template <int NC>
 struct SmemTC {
-  static constexpr int NP = PREC ? 2 : 3;  // pieces
+  static constexpr int NP = 3;  // bf16 pieces
   // the first NP pieces of the model image (weights are its last member, see DpModelImageTC)
   __align__(16) unsigned char model[DP_TC_IMAGE_BYTES(NP)];
   __align__(16) unsigned char ping[NP][Geo<NC>::kPingBytes];  // [piece]  z (24) / a1 (60) / dL/dh1 (60)
   __align__(16) unsigned char pong[NP][Geo<NC>::kPongBytes];  // [piece]  a0 (40) / dL/dy (92) / dL/dh0 (40)
   __align__(16) float ybuf[NC][96];                 // y, then dL/dy in place (fp32, one row per clip)
   float zgrad[NC][25];                              // dL/dz from the decoder (fp32)
-  float bscale[NC];                                 // fp16 path: 1 / (per-clip power-of-two scale of dL/dy)
   __align__(16) ClipTrackers trk[NC][32];
   // per-clip optimiser state lives here, not in registers: the packed kinematics pass needs the register file
   __align__(16) float2 st[NC][5][DP_L / 2];         // [ST_Z latent | ST_TL target latent | ST_M, ST_V Adam moments | ST_ZLAST]
@@ -90,30 +79,25 @@ template <> struct Lay<1> { static constexpr int kin = 48, kout = 64; static con
 template <> struct Lay<2> { static constexpr int kin = 64, kout = 96; static constexpr uint32_t off = DP_TC_W2_OFF; };
 
 // the split products of one K step, smallest first
-template <int PREC>
 __device__ __forceinline__ void issue_terms(uint32_t tmem, const UmmaDescBase (&a)[kMaxPieces], const UmmaDescBase (&b)[kMaxPieces], uint32_t ao,
                                             uint32_t bo, uint32_t idesc, bool first) {
-  if (PREC == 0) {  // (3,1) (2,2) (1,3) | (2,1) (1,2) | (1,1)
-    if (first) umma_f16_c<false>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
-    else umma_f16_c<true>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
-    umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[1], bo), idesc);
-    umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[2], bo), idesc);
-    umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
-  } else {          // (2,1) | (1,2) | (1,1)
-    if (first) umma_f16_c<false>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
-    else umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
-  }
+  // (3,1) (2,2) (1,3) | (2,1) (1,2) | (1,1)
+  if (first) umma_f16_c<false>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
+  else umma_f16_c<true>(tmem, umma_desc_at(a[2], ao), umma_desc_at(b[0], bo), idesc);
+  umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[1], bo), idesc);
+  umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[2], bo), idesc);
+  umma_f16_c<true>(tmem, umma_desc_at(a[1], ao), umma_desc_at(b[0], bo), idesc);
   umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[1], bo), idesc);
   umma_f16_c<true>(tmem, umma_desc_at(a[0], ao), umma_desc_at(b[0], bo), idesc);
 }
 
 // forward layer L: A = W_L (K-major: LBO 128 between input 8-groups, SBO between output-row 8-groups)
-template <int L, int PREC, int NC>
-__device__ __forceinline__ void issue_fwd(const SmemTC<PREC, NC>& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
+template <int L, int NC>
+__device__ __forceinline__ void issue_fwd(const SmemTC<NC>& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
   constexpr uint32_t kB_LBO = Geo<NC>::kB_LBO;
-  constexpr int NP = SmemTC<PREC, NC>::NP;
+  constexpr int NP = SmemTC<NC>::NP;
   constexpr uint32_t sbo = 128 * (Lay<L>::kin / 8);
-  constexpr uint32_t fmt = PREC ? 0u : 1u;  // kind::f16 operand format: 0 = fp16, 1 = bf16
+  constexpr uint32_t fmt = 1u;  // kind::f16 operand format: 1 = bf16
   constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);  // B MN-major
   UmmaDescBase a[kMaxPieces], b[kMaxPieces];
 #pragma unroll
@@ -124,16 +108,16 @@ __device__ __forceinline__ void issue_fwd(const SmemTC<PREC, NC>& S, uint32_t tm
 #pragma unroll
   for (int k = 0; k < Lay<L>::kin / 16; ++k) {
     const uint32_t ao = k * 256, bo = k * 2 * kB_LBO;
-    issue_terms<PREC>(tmem, a, b, ao, bo, idesc, k == 0);
+    issue_terms(tmem, a, b, ao, bo, idesc, k == 0);
   }
 }
 // backward of layer L: the SAME weight image read MN-major (M = inputs, K = outputs): LBO / SBO swap roles
-template <int L, int PREC, int NC>
-__device__ __forceinline__ void issue_bwd(const SmemTC<PREC, NC>& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
+template <int L, int NC>
+__device__ __forceinline__ void issue_bwd(const SmemTC<NC>& S, uint32_t tmem, const unsigned char* src, uint32_t piece_stride) {
   constexpr uint32_t kB_LBO = Geo<NC>::kB_LBO;
-  constexpr int NP = SmemTC<PREC, NC>::NP;
+  constexpr int NP = SmemTC<NC>::NP;
   constexpr uint32_t wsbo = 128 * (Lay<L>::kin / 8);
-  constexpr uint32_t fmt = PREC ? 0u : 1u;
+  constexpr uint32_t fmt = 1u;
   constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
   UmmaDescBase a[kMaxPieces], b[kMaxPieces];
 #pragma unroll
@@ -144,7 +128,7 @@ __device__ __forceinline__ void issue_bwd(const SmemTC<PREC, NC>& S, uint32_t tm
 #pragma unroll
   for (int k = 0; k < Lay<L>::kout / 16; ++k) {
     const uint32_t ao = k * 2 * wsbo, bo = k * 2 * kB_LBO;
-    issue_terms<PREC>(tmem, a, b, ao, bo, idesc, k == 0);
+    issue_terms(tmem, a, b, ao, bo, idesc, k == 0);
   }
 }
 
@@ -153,16 +137,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
   return p;
 }
-__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
-  uint32_t p;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi_elem), "f"(lo_elem));
-  return p;
-}
-__device__ __forceinline__ void unpack_f16x2(uint32_t p, float& lo_elem, float& hi_elem) {
-  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo_elem), "=f"(hi_elem) : "r"(p));
-}
 // EC fp32 values (feature k, clips EC*half .. +EC-1) -> split pieces in an MN-major activation image
-template <int PREC, int NC>
+template <int NC>
 __device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_stride, int k, int half, const float (&v)[Geo<NC>::EC]) {
   constexpr int EC = Geo<NC>::EC;
   unsigned char* dst = img + (k >> 3) * Geo<NC>::kB_LBO + (k & 7) * 16 + ((EC / 8) * half) * kB_SBO;
@@ -172,65 +148,49 @@ __device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float x0 = v[8 * g + 2 * i], x1 = v[8 * g + 2 * i + 1];
-      if (PREC == 0) {
-        p1[i] = pack_bf16x2(x0, x1);
-        const float r0 = x0 - __uint_as_float(p1[i] << 16), r1 = x1 - __uint_as_float(p1[i] & 0xffff0000u);
-        p2[i] = pack_bf16x2(r0, r1);
-        const float s0 = r0 - __uint_as_float(p2[i] << 16), s1 = r1 - __uint_as_float(p2[i] & 0xffff0000u);
-        p3[i] = pack_bf16x2(s0, s1);
-      } else {
-        p1[i] = pack_f16x2(x0, x1);
-        float h0, h1;
-        unpack_f16x2(p1[i], h0, h1);
-        p2[i] = pack_f16x2(x0 - h0, x1 - h1);
-      }
+      p1[i] = pack_bf16x2(x0, x1);
+      const float r0 = x0 - __uint_as_float(p1[i] << 16), r1 = x1 - __uint_as_float(p1[i] & 0xffff0000u);
+      p2[i] = pack_bf16x2(r0, r1);
+      const float s0 = r0 - __uint_as_float(p2[i] << 16), s1 = r1 - __uint_as_float(p2[i] & 0xffff0000u);
+      p3[i] = pack_bf16x2(s0, s1);
     }
     *reinterpret_cast<uint4*>(dst + g * kB_SBO) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
     *reinterpret_cast<uint4*>(dst + piece_stride + g * kB_SBO) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-    if (PREC == 0) *reinterpret_cast<uint4*>(dst + 2 * piece_stride + g * kB_SBO) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+    *reinterpret_cast<uint4*>(dst + 2 * piece_stride + g * kB_SBO) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
   }
 }
 // a single fp32 value (feature k, clip n) -> its pieces (used by the Adam lanes for the latent)
-template <int PREC, int NC>
+template <int NC>
 __device__ __forceinline__ void store_piece_scalar(unsigned char* img, uint32_t piece_stride, int k, int n, float x) {
   unsigned char* dst = img + (k >> 3) * Geo<NC>::kB_LBO + (k & 7) * 16 + (n >> 3) * kB_SBO + (n & 7) * 2;
-  if (PREC == 0) {
-    const uint32_t p = pack_bf16x2(x, 0.0f);
-    const float r = x - __uint_as_float(p << 16);
-    const uint32_t q = pack_bf16x2(r, 0.0f);
-    const float s = r - __uint_as_float(q << 16);
-    const uint32_t t = pack_bf16x2(s, 0.0f);
-    *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
-    *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
-    *reinterpret_cast<unsigned short*>(dst + 2 * piece_stride) = (unsigned short)(t & 0xffffu);
-  } else {
-    const uint32_t p = pack_f16x2(x, 0.0f);
-    float h0, h1;
-    unpack_f16x2(p, h0, h1);
-    const uint32_t q = pack_f16x2(x - h0, 0.0f);
-    *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
-    *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
-  }
+  const uint32_t p = pack_bf16x2(x, 0.0f);
+  const float r = x - __uint_as_float(p << 16);
+  const uint32_t q = pack_bf16x2(r, 0.0f);
+  const float s = r - __uint_as_float(q << 16);
+  const uint32_t t = pack_bf16x2(s, 0.0f);
+  *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
+  *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
+  *reinterpret_cast<unsigned short*>(dst + 2 * piece_stride) = (unsigned short)(t & 0xffffu);
 }
 
-template <int PREC, int NC>
+template <int NC>
 struct Ctx {
-  SmemTC<PREC, NC>* S;
+  SmemTC<NC>* S;
   uint32_t tmem;
   int warp, lane;
   uint32_t phase;  // parity of the next MMA completion
 };
 
 // one dense layer on the tensor pipe + its epilogue; every thread of the CTA calls this (ends with __syncthreads)
-template <int L, bool FWD, int PREC, int NC, class Epi>
-__device__ __forceinline__ void tc_layer(Ctx<PREC, NC>& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
-  SmemTC<PREC, NC>& S = *c.S;
+template <int L, bool FWD, int NC, class Epi>
+__device__ __forceinline__ void tc_layer(Ctx<NC>& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
+  SmemTC<NC>& S = *c.S;
   constexpr int EC = Geo<NC>::EC;
   if (c.warp == Geo<NC>::kIssueWarp) {
     tc_fence_after();
     if (elect_one()) {
-      if (FWD) issue_fwd<L, PREC, NC>(S, c.tmem, src, src_stride);
-      else issue_bwd<L, PREC, NC>(S, c.tmem, src, src_stride);
+      if (FWD) issue_fwd<L, NC>(S, c.tmem, src, src_stride);
+      else issue_bwd<L, NC>(S, c.tmem, src, src_stride);
       umma_commit(&S.bar_mma);
     }
     __syncwarp();
@@ -254,10 +214,10 @@ __device__ __forceinline__ void tc_layer(Ctx<PREC, NC>& c, const unsigned char* 
   __syncthreads();
 }
 
-template <int PREC, int NC>
-__global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_frame_tc_kernel(const __grid_constant__ DpFrameArgs A) {
+template <int NC>
+__global__ void __launch_bounds__(Geo<NC>::kWarps * 32, 1) dp_frame_tc_kernel(const __grid_constant__ DpFrameArgs A) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  using Smem = SmemTC<PREC, NC>;
+  using Smem = SmemTC<NC>;
   constexpr int kWarps = Geo<NC>::kWarps, EC = Geo<NC>::EC;
   constexpr uint32_t kPingBytes = Geo<NC>::kPingBytes, kPongBytes = Geo<NC>::kPongBytes;
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -279,9 +239,9 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
     constexpr uint32_t kChunk = 32768;
     mbar_expect_tx(&S.bar_w, kBytes);
     for (uint32_t o = 0; o < kBytes; o += kChunk)
-      tma_bulk_g2s(S.model + o, reinterpret_cast<const unsigned char*>(PREC ? A.model_tc16 : A.model_tc) + o, min(kChunk, kBytes - o), &S.bar_w);
+      tma_bulk_g2s(S.model + o, reinterpret_cast<const unsigned char*>(A.model_tc) + o, min(kChunk, kBytes - o), &S.bar_w);
   }
-  Ctx<PREC, NC> ctx{&S, S.tmem_base, warp, lane, 0u};
+  Ctx<NC> ctx{&S, S.tmem_base, warp, lane, 0u};
   constexpr int CPW = NC / kWarps;  // 2 clips per warp in the per-clip phases
   const int n0 = warp * CPW;        // local clip index (tile column) of this warp's first clip
   const int clip0 = blockIdx.x * A.clips_per_cta + n0;
@@ -334,8 +294,8 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
     }
     S.trk[n0 + c][lane] = row;
     if (lane < DP_L / 2) {  // latent -> B operand of the first layer
-      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z.x);
-      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z.y);
+      store_piece_scalar<NC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z.x);
+      store_piece_scalar<NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z.y);
     }
   }
   const P2 inv3e2 = mk2(inv3e[0], inv3e[1]), lrot9e2 = mk2(lrot9e[0], lrot9e[1]);
@@ -343,27 +303,26 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
   fence_proxy_async();
   mbar_wait(&S.bar_w, 0);  // model image (weights, statistics, skeleton tables) has landed
 
-  constexpr float wsc = PREC ? 1.0f / kWScale : 1.0f;  // undoes the weight-image scaling of the fp16 path
   unsigned neg0 = 0, neg1 = 0;  // LeakyReLU slope bits of (feature k, this thread's 16 clips) for the backward pass
   auto forward = [&]() {
-    tc_layer<0, true, PREC, NC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<0, true, NC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b0[k];
       neg0 = 0;
 #pragma unroll
-      for (int i = 0; i < EC; ++i) { v[i] = fmaf(v[i], wsc, b); neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces<PREC, NC>(&S.pong[0][0], kPongBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) { v[i] += b; neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces<NC>(&S.pong[0][0], kPongBytes, k, half, v);
     });
-    tc_layer<1, true, PREC, NC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<1, true, NC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b1[k];
       neg1 = 0;
 #pragma unroll
-      for (int i = 0; i < EC; ++i) { v[i] = fmaf(v[i], wsc, b); neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces<PREC, NC>(&S.ping[0][0], kPingBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) { v[i] += b; neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces<NC>(&S.ping[0][0], kPingBytes, k, half, v);
     });
-    tc_layer<2, true, PREC, NC>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<2, true, NC>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b2[k];
 #pragma unroll
-      for (int i = 0; i < EC; ++i) S.ybuf[EC * half + i][k] = fmaf(v[i], wsc, b);
+      for (int i = 0; i < EC; ++i) S.ybuf[EC * half + i][k] = v[i] + b;
     });
   };
   auto backward = [&]() {
@@ -373,24 +332,24 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
         float v[EC];
 #pragma unroll
         for (int i = 0; i < EC; ++i) v[i] = S.ybuf[EC * half + i][k];
-        store_pieces<PREC, NC>(&S.pong[0][0], kPongBytes, k, half, v);
+        store_pieces<NC>(&S.pong[0][0], kPongBytes, k, half, v);
       }
       fence_proxy_async();
     }
     __syncthreads();
-    tc_layer<2, false, PREC, NC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<2, false, NC>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
-      for (int i = 0; i < EC; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
-      store_pieces<PREC, NC>(&S.ping[0][0], kPingBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f : 1.0f;
+      store_pieces<NC>(&S.ping[0][0], kPingBytes, k, half, v);
     });
-    tc_layer<1, false, PREC, NC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<1, false, NC>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
-      for (int i = 0; i < EC; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f * wsc : wsc;
-      store_pieces<PREC, NC>(&S.pong[0][0], kPongBytes, k, half, v);
+      for (int i = 0; i < EC; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f : 1.0f;
+      store_pieces<NC>(&S.pong[0][0], kPongBytes, k, half, v);
     });
-    tc_layer<0, false, PREC, NC>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<0, false, NC>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
-      for (int i = 0; i < EC; ++i) S.zgrad[EC * half + i][k] = v[i] * (PREC ? wsc * S.bscale[EC * half + i] : 1.0f);
+      for (int i = 0; i < EC; ++i) S.zgrad[EC * half + i][k] = v[i];
     });
   };
 
@@ -423,31 +382,6 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
       phase_done(4);
       nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x;
       nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y;
-      if (PREC) {  // bring the largest |dL/dy| component of each clip into [16, 32) with an exact power of two
-        float4* row0 = reinterpret_cast<float4*>(&S.ybuf[n0][0]);
-        float4* row1 = reinterpret_cast<float4*>(&S.ybuf[n0 + 1][0]);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 y0 = lane < 23 ? row0[lane] : zero4, y1 = lane < 23 ? row1[lane] : zero4;
-        float mx0 = fmaxf(fmaxf(fabsf(y0.x), fabsf(y0.y)), fmaxf(fabsf(y0.z), fabsf(y0.w)));
-        float mx1 = fmaxf(fmaxf(fabsf(y1.x), fabsf(y1.y)), fmaxf(fabsf(y1.z), fabsf(y1.w)));
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) {
-          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, sh));
-          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, sh));
-        }
-        int e0 = (int)((__float_as_uint(mx0) >> 23) & 0xffu) - 127, e1 = (int)((__float_as_uint(mx1) >> 23) & 0xffu) - 127;  // floor(log2)
-        e0 = mx0 > 0.f ? max(-100, min(100, e0)) : 4;
-        e1 = mx1 > 0.f ? max(-100, min(100, e1)) : 4;
-        const float sc0 = __uint_as_float((uint32_t)(127 + 4 - e0) << 23), sc1 = __uint_as_float((uint32_t)(127 + 4 - e1) << 23);
-        if (lane < 23) {
-          row0[lane] = make_float4(y0.x * sc0, y0.y * sc0, y0.z * sc0, y0.w * sc0);
-          row1[lane] = make_float4(y1.x * sc1, y1.y * sc1, y1.z * sc1, y1.w * sc1);
-        }
-        if (lane == 0) {
-          S.bscale[n0] = __uint_as_float((uint32_t)(127 - 4 + e0) << 23);
-          S.bscale[n0 + 1] = __uint_as_float((uint32_t)(127 - 4 + e1) << 23);
-        }
-      }
     }
     __syncthreads();
     phase_done(1);
@@ -493,8 +427,8 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
       // EVERY clip (stopped and padding clips included) so that no column ever feeds back on its own garbage -- a
       // non-finite value in a K-padding row would poison the column through 0 x NaN
       if (lane < DP_L / 2) {
-        store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane, n, z.x);
-        store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n, z.y);
+        store_piece_scalar<NC>(&S.ping[0][0], kPingBytes, 2 * lane, n, z.x);
+        store_piece_scalar<NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n, z.y);
       }
       if (active[c]) {
         const float total = (nlp[c] + nlr[c]) + nlt;
@@ -517,8 +451,8 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
   for (int c = 0; c < CPW; ++c)
     if (lane < DP_L / 2) {
       const float2 zl = S.st[n0 + c][ST_ZLAST][lane];
-      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zl.x);
-      store_piece_scalar<PREC, NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zl.y);
+      store_piece_scalar<NC>(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zl.x);
+      store_piece_scalar<NC>(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zl.y);
     }
   fence_proxy_async();
   __syncthreads();
@@ -596,9 +530,9 @@ __global__ void __launch_bounds__(Geo<NC>::kWarps * 32, NC == 16 ? 2 : 1) dp_fra
 
 cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream) {
   static bool configured = false;
-  const size_t smem = sizeof(SmemTC<0, 32>) + 1024;
+  const size_t smem = sizeof(SmemTC<32>) + 1024;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<0, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -608,6 +542,6 @@ cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_
   cpc = cpc < 1 ? 1 : (cpc > 32 ? 32 : cpc);
   if (args.n_clips > num_sms * 32) cpc = 32;  // several waves anyway: use full tiles
   a.clips_per_cta = cpc;
-  dp_frame_tc_kernel<0, 32><<<(args.n_clips + cpc - 1) / cpc, Geo<32>::kWarps * 32, smem, stream>>>(a);
+  dp_frame_tc_kernel<32><<<(args.n_clips + cpc - 1) / cpc, Geo<32>::kWarps * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

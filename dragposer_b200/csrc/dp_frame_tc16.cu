@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   tc_fence_after();
   if (threadIdx.x == 0) {
     mbar_expect_tx(&S.bar_w, (uint32_t)sizeof(S.model));
-    tma_bulk_g2s(S.model, A.model_tc16, (uint32_t)sizeof(S.model), &S.bar_w);
+    tma_bulk_g2s(S.model, A.model_tc, (uint32_t)sizeof(S.model), &S.bar_w);
   }
   const uint32_t tmem = S.tmem_base;
   {  // weight pieces -> tensor memory: warp w fills lanes 32 (w % 4) .. +31, columns 88 (w / 4) .. +87 (coalesced reads)
