@@ -90,6 +90,36 @@ def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_mode
 
 
 @pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("n_trk", [2, 22], ids=["two-trackers", "every-joint-tracked"])
+def test_gradient_tracker_count_extremes_vs_float64(engine_factory, pose_model, model_npz, path, n_trk):
+    """Mask handling at its extremes: the smallest set the reference can run (E = 2) and all 22 joints tracked, per-clip
+    tracker tables (not shared), random weights; loss values, gradient and joint positions against the float64 port."""
+    rng = np.random.default_rng(100 + n_trk)
+    n = 24
+    offsets = model_npz["offsets"]
+    joints = np.stack([rng.permutation(22)[:n_trk] for _ in range(n)]).astype(np.int32)
+    joints.sort(axis=1)
+    weights = rng.uniform(0.2, 1.5, (n, n_trk, 2)).astype(np.float32)
+    lat = (0.4 * rng.standard_normal((n, 24))).astype(np.float32)
+    lat_t = lat + (0.1 * rng.standard_normal((n, 24))).astype(np.float32)
+    p_t, R_t = synthetic.pose_fk_np(pose_model, offsets, pose_model.decode_np(lat_t))
+    tp = np.take_along_axis(p_t, joints[:, :, None], 1).astype(np.float32)
+    tr = np.take_along_axis(R_t, joints[:, :, None, None], 1).astype(np.float32)
+    grot = np.tile(np.float32([1, 0, 0, 0]), (n, 1))
+    tl = (0.3 * rng.standard_normal((n, 24))).astype(np.float32)
+    eng = engine_factory(64)
+    r = eng.eval_gradient(lat, grot, tl, tp, tr, joints, weights, lambda_rot=1.0, lambda_temporal=0.05, decoder_path=path)
+    pw64 = port.PortWeights(model_npz, dtype=torch.float64)
+    t64 = port.loss_and_grad(pw64, lat, grot, tp, tr, tl, joints, weights, lambda_rot=1.0, lambda_temporal=0.05, dtype=torch.float64)
+    rel = np.linalg.norm(r["grad"] - t64["grad"], axis=1) / np.linalg.norm(t64["grad"], axis=1)
+    worst = rel.max()
+    assert worst <= GRAD_REL
+    np.testing.assert_allclose(r["pos"], t64["pos"], atol=2e-6)
+    np.testing.assert_allclose(np.stack([r["lp"], r["lr"], r["lt"]]), np.stack([t64["lp"], t64["lr"], t64["lt"]]), rtol=1e-4, atol=1e-7)  # losses are sums of squared small differences
+    print(f"decoder path {path}, {n_trk} trackers per clip: worst gradient rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
 @pytest.mark.parametrize("tag,opt,n_frames", [("fixed", FIXED, 2), ("early", EARLY, 6)])
 def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights, tag, opt, n_frames, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
