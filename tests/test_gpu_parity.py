@@ -206,6 +206,31 @@ def test_run_frames_pipelined_equals_frame_by_frame(engine_factory, pose_model, 
     assert np.isfinite(outs[0][0]).all()
 
 
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
+def test_clip_order_is_exact(engine_factory, pose_model, model_npz, path):
+    """Clip indexing: shuffling the clips of a batch shuffles the results and nothing else, bit for bit (a clip's arithmetic does
+    not depend on which warp half, tile column, CTA or predictor part it lands in).  2 frames, variable tracker mask, 2100 clips
+    (more than the 2048 that split the predictor into two parts)."""
+    cfg = synthetic.config_3_trackers()
+    B, T = 2100, 2
+    wl = synthetic.make_workload(pose_model, model_npz["offsets"], cfg, B, T, variable_mask=True)
+    perm = np.random.default_rng(1).permutation(B)
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window, max_iter=15,
+              joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight, decoder_path=path)
+    outs = []
+    for order in (np.arange(B), perm):
+        eng = engine_factory(B)
+        eng.set_initial_state(wl["latent0"][order], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+        for t in range(T):
+            res = eng.run(wl["tgt_pos"][t][order], wl["tgt_rot"][t][order], wl["joints_tb"][t][order], wl["weights_tb"][t][order],
+                          n_ee=wl["n_ee"][t][order], **kw)
+        iters, losses = eng.frame_stats()
+        outs.append((res[0], res[1], iters, losses))
+        eng.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a[perm], b)
+
+
 def test_device_encoder_matches_folded_encoder(engine_factory, pose_model):
     """clip start-up on the device vs the host restatement of the folded encoder (model.PoseModel.encode_np)."""
     rng = np.random.default_rng(9)
