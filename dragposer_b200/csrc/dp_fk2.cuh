@@ -110,10 +110,12 @@ struct FkOut2 {
 // ybuf* / trk*: the two clips' 96-float y rows (dL/dy is written in place) and tracker rows; groot: their previous world
 // root rotations, 2 x 4 floats in shared memory (re-read where needed instead of held in registers); scr: 16 float2 of
 // per-pair scratch for the warp-uniform R_0, r and d, parked in shared memory between the forward and the adjoint half.
-template <bool ADJOINT, bool EPILOGUE, class MODEL>
+// SCALE (fp16 tensor-core path): dL/dy of each clip is multiplied by the exact power of two that brings its largest
+// component into [16, 32) before it is written; inv_scale[0..1] receive the two inverse factors.
+template <bool ADJOINT, bool EPILOGUE, bool SCALE = false, class MODEL>
 DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restrict__ ybuf_b, const ClipTrackers* __restrict__ trk_a,
                       const ClipTrackers* __restrict__ trk_b, const float* __restrict__ groot, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
-                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3]) {
+                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -279,17 +281,43 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
     const P2 kk = dt * inv * inv * rcp2(n);
     const P2 o0 = sq.x * mad(-u[0], kk, qb[0] * inv), o1 = sq.y * mad(-u[1], kk, qb[1] * inv);
     const P2 o2 = sq.z * mad(-u[2], kk, qb[2] * inv), o3 = sq.w * mad(-u[3], kk, qb[3] * inv);
-    if (is_joint) {
-      reinterpret_cast<float4*>(ybuf_a)[lane] = make_float4(o0.v.x, o1.v.x, o2.v.x, o3.v.x);
-      reinterpret_cast<float4*>(ybuf_b)[lane] = make_float4(o0.v.y, o1.v.y, o2.v.y, o3.v.y);
-    }
+    P2 dbar[3] = {splat(0.f), splat(0.f), splat(0.f)};
     if (is_root) {
-      P2 dbar[3], R0s[9];
+      P2 R0s[9], t[3];
 #pragma unroll
       for (int i = 0; i < 9; ++i) R0s[i] = ld2(i);
-      mat_t_vec(R0s, cb, dbar);
-      reinterpret_cast<float4*>(ybuf_a)[DP_J] = make_float4(dbar[0].v.x * M.std_d[0], dbar[1].v.x * M.std_d[1], dbar[2].v.x * M.std_d[2], 0.0f);
-      reinterpret_cast<float4*>(ybuf_b)[DP_J] = make_float4(dbar[0].v.y * M.std_d[0], dbar[1].v.y * M.std_d[1], dbar[2].v.y * M.std_d[2], 0.0f);
+      mat_t_vec(R0s, cb, t);
+      dbar[0] = M.std_d[0] * t[0]; dbar[1] = M.std_d[1] * t[1]; dbar[2] = M.std_d[2] * t[2];
+    }
+    P2 sc = splat(1.0f);
+    if (SCALE) {  // per-clip max |dL/dy| over the warp (lanes >= 22 hold zeros), then the power of two 2^(4 - floor(log2 max))
+      float ma = fmaxf(fmaxf(fabsf(o0.v.x), fabsf(o1.v.x)), fmaxf(fabsf(o2.v.x), fabsf(o3.v.x)));
+      float mb = fmaxf(fmaxf(fabsf(o0.v.y), fabsf(o1.v.y)), fmaxf(fabsf(o2.v.y), fabsf(o3.v.y)));
+      ma = fmaxf(ma, fmaxf(fabsf(dbar[0].v.x), fmaxf(fabsf(dbar[1].v.x), fabsf(dbar[2].v.x))));
+      mb = fmaxf(mb, fmaxf(fabsf(dbar[0].v.y), fmaxf(fabsf(dbar[1].v.y), fabsf(dbar[2].v.y))));
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, sh));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, sh));
+      }
+      int ea = (int)((__float_as_uint(ma) >> 23) & 0xffu) - 127, eb = (int)((__float_as_uint(mb) >> 23) & 0xffu) - 127;  // floor(log2)
+      ea = ma > 0.f ? max(-100, min(100, ea)) : 4;
+      eb = mb > 0.f ? max(-100, min(100, eb)) : 4;
+      sc = mk2(__uint_as_float((uint32_t)(127 + 4 - ea) << 23), __uint_as_float((uint32_t)(127 + 4 - eb) << 23));
+      if (is_root) {
+        inv_scale[0] = __uint_as_float((uint32_t)(127 - 4 + ea) << 23);
+        inv_scale[1] = __uint_as_float((uint32_t)(127 - 4 + eb) << 23);
+      }
+    }
+    if (is_joint) {
+      const P2 s0 = SCALE ? o0 * sc : o0, s1 = SCALE ? o1 * sc : o1, s2 = SCALE ? o2 * sc : o2, s3 = SCALE ? o3 * sc : o3;
+      reinterpret_cast<float4*>(ybuf_a)[lane] = make_float4(s0.v.x, s1.v.x, s2.v.x, s3.v.x);
+      reinterpret_cast<float4*>(ybuf_b)[lane] = make_float4(s0.v.y, s1.v.y, s2.v.y, s3.v.y);
+    }
+    if (is_root) {
+      const P2 d0 = SCALE ? dbar[0] * sc : dbar[0], d1 = SCALE ? dbar[1] * sc : dbar[1], d2 = SCALE ? dbar[2] * sc : dbar[2];
+      reinterpret_cast<float4*>(ybuf_a)[DP_J] = make_float4(d0.v.x, d1.v.x, d2.v.x, 0.0f);
+      reinterpret_cast<float4*>(ybuf_b)[DP_J] = make_float4(d0.v.y, d1.v.y, d2.v.y, 0.0f);
     }
     __syncwarp();
   }

@@ -330,36 +330,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     phase_done(0);
     float nlp[CPW] = {0.f, 0.f}, nlr[CPW] = {0.f, 0.f};
     if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
-      const FkOut2 o = fk_loss2<true, false>(M, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0], &S.trk[n0 + 1][0], &S.groot[n0][0], &S.fkscr[warp][0], inv3e2,
-                                             lrot9e2, lane, nullptr, nullptr, nullptr, nullptr);
+      // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is written)
+      const FkOut2 o = fk_loss2<true, false, true>(M, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0], &S.trk[n0 + 1][0], &S.groot[n0][0],
+                                                   &S.fkscr[warp][0], inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0]);
       phase_done(4);
-      nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x;
-      nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y;
-      {  // bring the largest |dL/dy| component of each clip into [16, 32) with an exact power of two
-        float4* row0 = reinterpret_cast<float4*>(&S.ybuf[n0][0]);
-        float4* row1 = reinterpret_cast<float4*>(&S.ybuf[n0 + 1][0]);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 y0 = lane < 23 ? row0[lane] : zero4, y1 = lane < 23 ? row1[lane] : zero4;
-        float mx0 = fmaxf(fmaxf(fabsf(y0.x), fabsf(y0.y)), fmaxf(fabsf(y0.z), fabsf(y0.w)));
-        float mx1 = fmaxf(fmaxf(fabsf(y1.x), fabsf(y1.y)), fmaxf(fabsf(y1.z), fabsf(y1.w)));
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) {
-          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, sh));
-          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, sh));
-        }
-        int e0 = (int)((__float_as_uint(mx0) >> 23) & 0xffu) - 127, e1 = (int)((__float_as_uint(mx1) >> 23) & 0xffu) - 127;  // floor(log2)
-        e0 = mx0 > 0.f ? max(-100, min(100, e0)) : 4;
-        e1 = mx1 > 0.f ? max(-100, min(100, e1)) : 4;
-        const float sc0 = __uint_as_float((uint32_t)(127 + 4 - e0) << 23), sc1 = __uint_as_float((uint32_t)(127 + 4 - e1) << 23);
-        if (lane < 23) {
-          row0[lane] = make_float4(y0.x * sc0, y0.y * sc0, y0.z * sc0, y0.w * sc0);
-          row1[lane] = make_float4(y1.x * sc1, y1.y * sc1, y1.z * sc1, y1.w * sc1);
-        }
-        if (lane == 0) {
-          S.bscale[n0] = __uint_as_float((uint32_t)(127 - 4 + e0) << 23);
-          S.bscale[n0 + 1] = __uint_as_float((uint32_t)(127 - 4 + e1) << 23);
-        }
-      }
+      if (active[0]) { nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x; }
+      if (active[1]) { nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y; }
     }
     group_sync(gid);
     phase_done(1);
