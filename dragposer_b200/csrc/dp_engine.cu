@@ -60,10 +60,6 @@ struct dp_engine {
   float adam_lr = -1.0f;
   TpWork tw{};
   // staging for the host-pointer path
-  int stage_stride = 0;
-  int32_t *h_nee = nullptr, *d_nee = nullptr, *h_joints = nullptr, *d_joints = nullptr;
-  float *h_w = nullptr, *d_w = nullptr, *h_tp = nullptr, *d_tp = nullptr, *h_tr = nullptr, *d_tr = nullptr;
-  float *h_pose = nullptr, *d_pose = nullptr, *h_gp = nullptr, *d_gp = nullptr;
   // double-buffered staging of dp_engine_run_frames_host: one contiguous block per slot and direction
   struct FramePipe {
     int stride = 0;
@@ -129,10 +125,6 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
     CK(cudaStreamCreateWithFlags(&e->tw.st_extra[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->tw.ev_join[i], cudaEventDisableTiming));
   }
-  CK(cudaMalloc(&e->d_pose, B * DP_POSE * 4));
-  CK(cudaMalloc(&e->d_gp, B * 3 * 4));
-  CK(cudaMallocHost(&e->h_pose, B * DP_POSE * 4));
-  CK(cudaMallocHost(&e->h_gp, B * 3 * 4));
   *out = e;
   return DP_OK;
 }
@@ -149,19 +141,10 @@ static void free_pipe(dp_engine* e) {
   e->pipe = dp_engine::FramePipe();
 }
 
-static void free_stage(dp_engine* e) {
-  cudaFreeHost(e->h_nee); cudaFreeHost(e->h_joints); cudaFreeHost(e->h_w); cudaFreeHost(e->h_tp); cudaFreeHost(e->h_tr);
-  cudaFree(e->d_nee); cudaFree(e->d_joints); cudaFree(e->d_w); cudaFree(e->d_tp); cudaFree(e->d_tr);
-  e->h_nee = e->h_joints = nullptr; e->d_nee = e->d_joints = nullptr;
-  e->h_w = e->h_tp = e->h_tr = e->d_w = e->d_tp = e->d_tr = nullptr;
-  e->stage_stride = 0;
-}
-
 extern "C" int dp_engine_destroy(dp_engine* e) {
   if (!e) return DP_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  free_stage(e);
   free_pipe(e);
   cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tmem); cudaFree(e->d_encoder); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
@@ -171,7 +154,6 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   for (int i = 0; i < DP_PRED_MAX_PARTS - 1; ++i)
     if (e->tw.st_extra[i]) { cudaStreamSynchronize(e->tw.st_extra[i]); cudaStreamDestroy(e->tw.st_extra[i]); cudaEventDestroy(e->tw.ev_join[i]); }
   if (e->tw.ev_fork) cudaEventDestroy(e->tw.ev_fork);
-  cudaFree(e->d_pose); cudaFree(e->d_gp); cudaFreeHost(e->h_pose); cudaFreeHost(e->h_gp);
   cudaStreamDestroy(e->stream);
   delete e;
   return DP_OK;
@@ -517,53 +499,6 @@ extern "C" int dp_engine_run_frame_device(dp_engine* e, const dp_run_params* p, 
                                      out_gpos, stream);
 }
 
-static int ensure_stage(dp_engine* e, int ee_stride) {
-  if (e->stage_stride >= ee_stride) return DP_OK;
-  free_stage(e);
-  const size_t B = (size_t)e->max_clips, S = (size_t)ee_stride;
-  CK(cudaMallocHost(&e->h_nee, B * 4)); CK(cudaMalloc(&e->d_nee, B * 4));
-  CK(cudaMallocHost(&e->h_joints, B * S * 4)); CK(cudaMalloc(&e->d_joints, B * S * 4));
-  CK(cudaMallocHost(&e->h_w, B * S * 2 * 4)); CK(cudaMalloc(&e->d_w, B * S * 2 * 4));
-  CK(cudaMallocHost(&e->h_tp, B * S * 3 * 4)); CK(cudaMalloc(&e->d_tp, B * S * 3 * 4));
-  CK(cudaMallocHost(&e->h_tr, B * S * 9 * 4)); CK(cudaMalloc(&e->d_tr, B * S * 9 * 4));
-  e->stage_stride = ee_stride;
-  return DP_OK;
-}
-
-extern "C" int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, const int32_t* joints,
-                                        const float* weights, int shared, const float* tgt_pos, const float* tgt_rot,
-                                        int ee_stride, float* out_pose, float* out_gpos) {
-  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || !out_gpos)
-    return fail(DP_ERR_ARG, "dp_engine_run_frame_host: null argument");
-  int rc = check_params(e, p, ee_stride);
-  if (rc) return rc;
-  CK(cudaSetDevice(e->device));
-  rc = ensure_stage(e, ee_stride);
-  if (rc) return rc;
-  rc = ensure_adam(e, p->max_iter, p->learning_rate);
-  if (rc) return rc;
-  cudaStream_t st = e->stream;
-  const size_t B = (size_t)e->n_clips, S = (size_t)ee_stride;
-  const size_t nj = shared ? S : B * S;
-  if (n_ee) { memcpy(e->h_nee, n_ee, B * 4); CK(cudaMemcpyAsync(e->d_nee, e->h_nee, B * 4, cudaMemcpyHostToDevice, st)); }
-  memcpy(e->h_joints, joints, nj * 4);
-  memcpy(e->h_w, weights, nj * 2 * 4);
-  memcpy(e->h_tp, tgt_pos, B * S * 3 * 4);
-  memcpy(e->h_tr, tgt_rot, B * S * 9 * 4);
-  CK(cudaMemcpyAsync(e->d_joints, e->h_joints, nj * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(e->d_w, e->h_w, nj * 2 * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(e->d_tp, e->h_tp, B * S * 3 * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(e->d_tr, e->h_tr, B * S * 9 * 4, cudaMemcpyHostToDevice, st));
-  rc = run_one(e, p, n_ee ? e->d_nee : nullptr, e->d_joints, e->d_w, shared, e->d_tp, e->d_tr, ee_stride, e->d_pose, e->d_gp, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(e->h_pose, e->d_pose, B * DP_POSE * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(e->h_gp, e->d_gp, B * 3 * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  memcpy(out_pose, e->h_pose, B * DP_POSE * 4);
-  memcpy(out_gpos, e->h_gp, B * 3 * 4);
-  return DP_OK;
-}
-
 // Offsets of the per-frame inputs inside one staging block (all 16-byte aligned): n_ee | joints | weights | tgt_pos | tgt_rot
 struct PipeLayout {
   size_t nee, joints, w, tp, tr, total;
@@ -593,6 +528,46 @@ static int ensure_pipe(dp_engine* e, int ee_stride) {
   CK(cudaStreamCreateWithFlags(&e->pipe.cs_in, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->pipe.cs_out, cudaStreamNonBlocking));
   e->pipe.stride = ee_stride;
+  return DP_OK;
+}
+
+extern "C" int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, const int32_t* joints,
+                                        const float* weights, int shared, const float* tgt_pos, const float* tgt_rot,
+                                        int ee_stride, float* out_pose, float* out_gpos) {
+  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || !out_gpos)
+    return fail(DP_ERR_ARG, "dp_engine_run_frame_host: null argument");
+  int rc = check_params(e, p, ee_stride);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  rc = ensure_pipe(e, ee_stride);
+  if (rc) return rc;
+  rc = ensure_adam(e, p->max_iter, p->learning_rate);
+  if (rc) return rc;
+  // one contiguous pinned block in, one out: a single copy each way (this is the B = 1 latency path of the DLL)
+  dp_engine::FramePipe& P = e->pipe;
+  cudaStream_t st = e->stream;
+  const size_t B = (size_t)e->n_clips, S = (size_t)ee_stride;
+  const size_t nj = shared ? S : B * S;
+  const PipeLayout L((size_t)e->max_clips, (size_t)P.stride);
+  unsigned char* h = P.h_in[0];
+  if (n_ee) memcpy(h + L.nee, n_ee, B * 4);
+  memcpy(h + L.joints, joints, nj * 4);
+  memcpy(h + L.w, weights, nj * 8);
+  memcpy(h + L.tp, tgt_pos, B * S * 12);
+  memcpy(h + L.tr, tgt_rot, B * S * 36);
+  // only the used prefix of every section travels when the batch is small: copy up to the end of the last section in use
+  const size_t in_bytes = B == (size_t)e->max_clips ? L.total : L.tr + B * S * 36;
+  CK(cudaMemcpyAsync(P.d_in[0], h, in_bytes, cudaMemcpyHostToDevice, st));
+  unsigned char* d = P.d_in[0];
+  float* d_pose = P.d_out[0];
+  rc = run_one(e, p, n_ee ? reinterpret_cast<const int32_t*>(d + L.nee) : nullptr, reinterpret_cast<const int32_t*>(d + L.joints),
+               reinterpret_cast<const float*>(d + L.w), shared, reinterpret_cast<const float*>(d + L.tp),
+               reinterpret_cast<const float*>(d + L.tr), ee_stride, d_pose, d_pose + B * DP_POSE, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(P.h_out[0], d_pose, B * (DP_POSE + 3) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(out_pose, P.h_out[0], B * DP_POSE * 4);
+  memcpy(out_gpos, P.h_out[0] + B * DP_POSE, B * 3 * 4);
   return DP_OK;
 }
 
