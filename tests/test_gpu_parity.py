@@ -287,16 +287,17 @@ def test_tcgen05_paths_agree_with_cuda_core_path_multi_wave(engine_factory, pose
         assert np.isfinite(out[path][0]).all() and np.median(dq) < 1e-5 and np.percentile(dq, 99) < 1e-3 and dq.max() < 5e-2 and dg < 1e-4
 
 
-@pytest.mark.parametrize("n_clips", [1, 37, 300])
+@pytest.mark.parametrize("n_clips", [1, 37, 300, 2101])
 def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory, n_clips):
-    """Every decoder length (T = 1 + W/4 up to 30 tokens), ragged last tiles: tcgen05 kernels vs the fp32 CUDA-core kernels."""
+    """Every decoder length (T = 1 + W/4 up to 30 tokens), ragged last tiles, and a batch large enough (>= 2048 clips) to run the
+    predictor as two parts on two streams: tcgen05 kernels vs the fp32 CUDA-core kernels."""
     g = np.load(os.path.join(golden_dir, "ref_temporal.npz"))
     rng = np.random.default_rng(5)
     reps = -(-n_clips // g["latent_buf"].shape[0])
     lat = np.tile(g["latent_buf"], (reps, 1, 1))[:n_clips] + rng.normal(0, 0.05, (n_clips, 60, 24)).astype(np.float32)
     disp = np.tile(g["disp_buf"], (reps, 1, 1))[:n_clips]
     hgt = np.tile(g["height_buf"], (reps, 1, 1))[:n_clips]
-    eng = engine_factory(512)
+    eng = engine_factory(max(512, n_clips))
     eng.set_initial_state(np.zeros((n_clips, 24)), np.zeros((n_clips, 3)), np.tile([[1.0, 0, 0, 0]], (n_clips, 1)), np.zeros((n_clips, 6)))
     eng.set_ring_buffers(lat, disp, hgt)
     for W in (0, 4, 28, 60, 116):
