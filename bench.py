@@ -253,8 +253,6 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "clip-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    line["config"]["l2"] = "n/a (CPU arm)"
-    line["config"]["parallelism"] = f"{cores} single-threaded worker processes, one clip each"
     if not args.no_latency:
         line["latency"] = port_latency()
     print(json.dumps(line))
