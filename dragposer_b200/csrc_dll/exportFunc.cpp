@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <random>
 #include <sstream>
@@ -127,7 +128,7 @@ bool parse_bvh_hierarchy(const std::string& path, std::vector<int32_t>& parents,
   return true;
 }
 
-bool read_dpm(const std::string& path, Model& m, std::string& err) {
+bool read_dpm(const std::string& path, Model& m, bool& trained_temporal, std::string& err) {
   std::ifstream f(path, std::ios::binary);
   if (!f) {
     err = "cannot open " + path;
@@ -138,10 +139,13 @@ bool read_dpm(const std::string& path, Model& m, std::string& err) {
   f.read(magic, 4);
   f.read(reinterpret_cast<char*>(&version), 4);
   f.read(reinterpret_cast<char*>(&n), 4);
-  if (!f || memcmp(magic, "DPM1", 4) != 0 || version != 1) {
+  if (!f || memcmp(magic, "DPM1", 4) != 0 || (version != 1 && version != 2)) {
     err = path + " is not a DPM1 model file";
     return false;
   }
+  uint32_t flags = 0;  // version 2: bit 0 = the predictor was read from a temporal.pt (export_model.py)
+  if (version >= 2) f.read(reinterpret_cast<char*>(&flags), 4);
+  trained_temporal = (flags & 1u) != 0;
   std::vector<float> flat(n);
   f.read(reinterpret_cast<char*>(flat.data()), (std::streamsize)n * 4);
   if (!f) {
@@ -207,6 +211,11 @@ void quat_to_matrix(const quaternion& q, float* m) {  // pymotion quat.to_matrix
 }
 
 bool file_exists(const std::string& p) { return std::ifstream(p).good(); }
+long long file_mtime(const std::string& p) {
+  std::error_code ec;
+  const auto t = std::filesystem::last_write_time(p, ec);
+  return ec ? 0 : (long long)t.time_since_epoch().count();
+}
 
 }  // namespace
 
@@ -241,20 +250,25 @@ DP_EXPORT void load_models(DragPoser* d, char* modelPath) {
   std::string dir(modelPath);
   while (dir.size() > 1 && (dir.back() == '/' || dir.back() == '\\')) dir.pop_back();
   std::string dpm = dir.size() > 4 && dir.substr(dir.size() - 4) == ".dpm" ? dir : dir + "/model.dpm";
+  // The reference checkpoint layout (generator.pt, data.pt, temporal.pt: PyTorch pickles) is converted OFFLINE by
+  // `python -m dragposer_b200.export_model <dir>`; this library never spawns an interpreter or a shell.  A model
+  // directory that is read-only can keep its model.dpm in $DRAGPOSER_MODEL_CACHE.
   if (!file_exists(dpm)) {
-    // one-time conversion of the reference checkpoint layout (generator.pt, data.pt[, temporal.pt]) by the
-    // Python packer; set DRAGPOSER_MODEL_CACHE to a writable directory when the model directory is read-only
-    const char* py = getenv("DRAGPOSER_PYTHON");
-    const char* cache = getenv("DRAGPOSER_MODEL_CACHE");
-    if (cache) dpm = std::string(cache) + "/model.dpm";
+    if (const char* cache = getenv("DRAGPOSER_MODEL_CACHE")) dpm = std::string(cache) + "/model.dpm";
     if (!file_exists(dpm)) {
-      std::string cmd = std::string(py ? py : "python3") + " -m dragposer_b200.export_model \"" + dir + "\" \"" + dpm + "\" 1>&2";
-      log_line("load_models: converting checkpoint: " + cmd);
-      if (system(cmd.c_str()) != 0 || !file_exists(dpm)) { d->fail("load_models: could not convert " + dir + " (see stderr)"); return; }
+      d->fail("load_models: " + dpm + " not found -- convert the checkpoint once with: python -m dragposer_b200.export_model \"" + dir + "\"");
+      return;
     }
   }
+  const std::string tpt = dir + "/temporal.pt";
+  if (file_exists(tpt) && file_mtime(tpt) > file_mtime(dpm)) {
+    d->fail("load_models: " + dpm + " is older than " + tpt + " -- re-run python -m dragposer_b200.export_model");
+    return;
+  }
   std::string err;
-  if (!read_dpm(dpm, d->model, err)) { d->fail("load_models: " + err); return; }
+  bool trained = false;
+  if (!read_dpm(dpm, d->model, trained, err)) { d->fail("load_models: " + err); return; }
+  if (!trained) log_line("load_models: " + dpm + " carries the random-init temporal predictor (exported with --random-temporal), not a trained temporal.pt");
   if (d->engine) { dp_engine_destroy(d->engine); d->engine = nullptr; }
   int dev = 0;
   if (const char* s = getenv("DRAGPOSER_DEVICE")) dev = atoi(s);

@@ -21,7 +21,8 @@ from .bvh import Bvh
 from .drag_pose import DragPose
 
 
-def evaluate(model_path, input_path, config=None, verbose=False, max_frames=None, save=True, seed=2222, quiet=False, initial_latent=None):
+def evaluate(model_path, input_path, config=None, verbose=False, max_frames=None, save=True, seed=2222, quiet=False, initial_latent=None,
+             random_temporal=False):
     torch.manual_seed(seed)  # eval_drag.py:23-25
     np.random.seed(seed)
     cfg = synthetic.TrackerConfig.load(config) if config else synthetic.config_6_trackers()  # defaults: eval_drag.py:68-131
@@ -30,7 +31,7 @@ def evaluate(model_path, input_path, config=None, verbose=False, max_frames=None
     rots = bvh.quaternions()
     pm = dpm.load_pose_model(model_path, parents)
     tdir = model_path if os.path.isdir(model_path) else os.path.dirname(model_path)
-    tm = dpm.load_temporal_model(tdir)
+    tm = dpm.load_temporal_model(tdir, allow_random=random_temporal)  # eval_drag.py:58-59 raises when temporal.pt is missing
     clip = motion.ClipData(rots, bvh.positions[:, 0, :], parents, offsets, pm.mean_dqs, pm.std_dqs)
     joints, weights = cfg.joints, cfg.tracker_weights
     drag = DragPose(pm, tm, offsets=offsets)
@@ -70,7 +71,7 @@ def evaluate(model_path, input_path, config=None, verbose=False, max_frames=None
 
 
 def evaluate_batch(model_path, input_paths, config=None, save=False, seed=2222, quiet=True, initial_latents=None, max_frames=None,
-                   device=0):
+                   device=0, random_temporal=False):
     """Many BVH clips at once: every clip becomes one row of a BatchedDragPose, the ground-truth tracker
     targets of ALL frames are built once in world coordinates (motion.world_targets) and the whole sequence runs through
     run_frames with targets_world=True, so nothing on the host depends on the previous frame's result.  Clips must share the
@@ -89,7 +90,7 @@ def evaluate_batch(model_path, input_paths, config=None, save=False, seed=2222, 
             raise ValueError("evaluate_batch: all clips must share one skeleton")
     pm = dpm.load_pose_model(model_path, parents)
     tdir = model_path if os.path.isdir(model_path) else os.path.dirname(model_path)
-    tm = dpm.load_temporal_model(tdir)
+    tm = dpm.load_temporal_model(tdir, allow_random=random_temporal)
     joints, weights = cfg.joints, cfg.tracker_weights
     rots = [b.quaternions() for b in bvhs]
     clips = [motion.ClipData(r, b.positions[:, 0, :], parents, offsets, pm.mean_dqs, pm.std_dqs) for r, b in zip(rots, bvhs)]
@@ -178,10 +179,13 @@ def main():
     ap.add_argument("--verbose", action="store_true", default=False, help="print additional information")
     ap.add_argument("--batch", action="store_true", default=False,
                     help="directory input: run all clips together as one batch (one engine row per clip, world-space targets)")
+    ap.add_argument("--random-temporal", action="store_true", default=False,
+                    help="temporal.pt is missing: run with the seed-2222 random-init predictor instead of failing like the reference")
     args = ap.parse_args()
+    rt = args.random_temporal
     if os.path.isdir(args.input_path) and args.batch:
         files = [os.path.join(args.input_path, fn) for fn in sorted(os.listdir(args.input_path)) if fn.endswith(".bvh")]
-        for fn, r in zip(files, evaluate_batch(args.model_path, files, args.config, save=True, quiet=True)):
+        for fn, r in zip(files, evaluate_batch(args.model_path, files, args.config, save=True, quiet=True, random_temporal=rt)):
             print("Evaluate {} ------------------------".format(fn))
             print("Evaluate Loss: {}".format(r["mpjpe"] + r["mpeepe"]))
             print("Mean Per Joint Position Error: {}".format(r["mpjpe"]))
@@ -191,9 +195,9 @@ def main():
         for fn in sorted(os.listdir(args.input_path)):
             if fn.endswith(".bvh"):
                 print("Evaluate {} ------------------------".format(os.path.join(args.input_path, fn)))
-                evaluate(args.model_path, os.path.join(args.input_path, fn), args.config, args.verbose)
+                evaluate(args.model_path, os.path.join(args.input_path, fn), args.config, args.verbose, random_temporal=rt)
     else:
-        evaluate(args.model_path, args.input_path, args.config, args.verbose)
+        evaluate(args.model_path, args.input_path, args.config, args.verbose, random_temporal=rt)
 
 
 if __name__ == "__main__":

@@ -232,6 +232,7 @@ class TemporalModel:
     sd: dict  # name -> float32 ndarray, nn.Transformer key names (Temporal.state_dict())
     means_latent: np.ndarray
     stds_latent: np.ndarray
+    trained: bool = False  # read from a temporal.pt (as opposed to the seeded random-init stand-in)
 
 
 def positional_table(max_len=PE_LEN, d=D_MODEL):
@@ -279,16 +280,28 @@ def temporal_from_state(sd, means_latent=None, stds_latent=None) -> TemporalMode
     return TemporalModel(arr, ml, sl)
 
 
-def load_temporal_model(model_dir, allow_random=True) -> TemporalModel:
-    """Read `temporal.pt` (`train_temporal.py:474-482`); when the blob is absent
-    (it is missing from the reference mount) fall back to the seeded random
-    predictor with means 0 / stds 1 -- BASELINE.json allows random-init weights."""
+def load_temporal_model(model_dir, allow_random=False) -> TemporalModel:
+    """Read `temporal.pt` (`train_temporal.py:474-482`, written by `train.py:311-319`: {"model_state_dict", "means_latent",
+    "stds_latent"}).  A missing file raises like the reference's `torch.load` does; only callers that pass
+    `allow_random=True` (bench, tests, smoke, `--random-temporal` on the CLIs -- the blob is absent from the reference
+    checkout and BASELINE.json allows random-init weights) get the seed-2222 random-init predictor with means 0 / stds 1."""
     import torch
 
     path = os.path.join(model_dir, "temporal.pt")
     if os.path.isfile(path):
         ck = torch.load(path, map_location="cpu", weights_only=True)
-        return temporal_from_state(ck["model_state_dict"], ck["means_latent"], ck["stds_latent"])
+        tm = temporal_from_state(ck["model_state_dict"], ck["means_latent"], ck["stds_latent"])
+        tm.trained = True
+        return tm
     if not allow_random:
-        raise FileNotFoundError(path)
+        raise FileNotFoundError(f"{path} (pass allow_random=True / --random-temporal to run with a random-init predictor)")
     return temporal_from_state(random_temporal_state())
+
+
+def save_temporal_model(tm: TemporalModel, path):
+    """Writes a predictor in the reference's `temporal.pt` format (train.py:311-319)."""
+    import torch
+
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in tm.sd.items()},
+                "means_latent": torch.from_numpy(np.asarray(tm.means_latent, np.float32).copy()),
+                "stds_latent": torch.from_numpy(np.asarray(tm.stds_latent, np.float32).copy())}, path)

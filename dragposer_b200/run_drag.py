@@ -26,11 +26,13 @@ class RunDrag:
         self.offsets = torch.from_numpy(offsets)
         return len(self.parents)
 
-    def load_models(self, model_path):
-        """Directory with generator.pt + data.pt (+ temporal.pt), or a folded .npz."""
+    def load_models(self, model_path, temporal=None):
+        """Directory with generator.pt + data.pt + temporal.pt (run_drag.py:40-59), or a folded .npz with temporal.pt next
+        to it.  Like the reference, a missing temporal.pt raises; `temporal` = an explicit TemporalModel (tests, benches:
+        the seeded random-init predictor) overrides the file."""
         self.pose_model = dpm.load_pose_model(model_path, self.parents)
         tdir = model_path if os.path.isdir(model_path) else os.path.dirname(model_path)
-        self.temporal_model = dpm.load_temporal_model(tdir)
+        self.temporal_model = temporal if temporal is not None else dpm.load_temporal_model(tdir)
         self.means = {"dqs": self.pose_model.mean_dqs}
         self.stds = {"dqs": self.pose_model.std_dqs}
 
@@ -46,13 +48,17 @@ class RunDrag:
         self.weights = weights[self.mask_indices].astype(np.float32)
         return len(self.mask_indices)
 
-    def init_drag_pose(self, initial_global_pos, initial_global_rot, eps=None):
-        """Encodes the zero (= mean) standardised pose, heights 0 (run_drag.py:77-96)."""
+    def init_drag_pose(self, initial_global_pos, initial_global_rot, eps=None, initial_latent=None):
+        """Encodes the zero (= mean) standardised pose, heights 0 (run_drag.py:77-96).  `eps` / `initial_latent` reproduce a
+        recorded reparameterisation draw (the reference takes it from torch's RNG stream)."""
         if self.drag is not None:
             self.drag.close()
         self.drag = DragPose(self.pose_model, self.temporal_model, offsets=self.offsets)
-        self.drag.set_initial_pose(np.zeros((1, len(self.parents) * 8, 1), np.float32), np.asarray(initial_global_pos).reshape(1, 3, 1),
-                                   np.asarray(initial_global_rot).reshape(1, 4, 1), np.zeros(6, np.float32), eps=eps)
+        gp, gr = np.asarray(initial_global_pos).reshape(1, 3, 1), np.asarray(initial_global_rot).reshape(1, 4, 1)
+        if initial_latent is not None:
+            self.drag.set_initial_latent(initial_latent, gp, gr, np.zeros(6, np.float32))
+        else:
+            self.drag.set_initial_pose(np.zeros((1, len(self.parents) * 8, 1), np.float32), gp, gr, np.zeros(6, np.float32), eps=eps)
 
     def set_optim_params(self, stop_eps_pos, stop_eps_rot, max_iter, lr):
         self.stop_eps_pos, self.stop_eps_rot, self.max_iter, self.learning_rate = stop_eps_pos, stop_eps_rot, max_iter, lr

@@ -310,12 +310,151 @@ def golden_eval_bvh(ref, n_frames=48):
     np.savez_compressed(os.path.join(OUT, "ref_eval_bvh.npz"), latent0=latent0, pose=np.stack(poses), gpos=np.stack(gps), iters=np.asarray(its, np.int32))
 
 
+def _eval_loop(ref, n_frames, filename, seed=4242):
+    """The evaluation loop of python/src/eval_drag.py:62-224 (6-tracker config) on the first n_frames of example.bvh through the
+    reference's own objects; returns (latent0, results_pose (1,88,F), results_global_pos (1,3,F), iterations)."""
+    rh.activate()
+    import train
+    from motion_data import TestMotionData
+    from pymotion.ops.forward_kinematics_torch import fk
+    from utils import from_root_quat
+
+    cfg = ref.load_config("6_trackers_config.json")
+    mask = torch.tensor(cfg["mask"])
+    weights = torch.tensor(cfg["weights"], dtype=torch.float32)
+    ds = TestMotionData(train.param, train.scale, "cpu", height_indices=[0, 4, 8, 13, 17, 21])
+    ds.set_means_stds(ref.means, ref.stds)
+    ds.add_motion(ref.offsets_np, ref.pos[:n_frames, 0, :], ref.rots[:n_frames], ref.parents, ref.bvh, filename)
+    ds.normalize()
+    nm = ds.get_item(0)
+    mask_indices = torch.nonzero(mask).squeeze()
+    weights = weights[mask_indices]
+    drag = ref.new_drag()
+    inp = nm["dqs"].unsqueeze(0).permute(0, 2, 1)
+    gpos, grot, heights = nm["global_pos"], nm["global_rot"], nm["heights"]
+    torch.manual_seed(seed)
+    drag.set_initial_pose(torch.tile(inp[..., 0:1], (1, 1, 1)), gpos[..., 0:1], grot[..., 0:1], heights[0])
+    latent0 = drag.latent.detach().numpy()[0].copy()
+    results_pose = torch.zeros((1, 88, n_frames))
+    results_gpos = torch.zeros((1, 3, n_frames))
+    its = []
+    rec = Recorder(drag)
+    for i in range(n_frames):
+        tq = inp[..., i : i + 1].clone().reshape((1, -1, 8, 1))[..., :4, :].flatten(1, 2)
+        tq = tq * drag.stds_dqs + drag.means_dqs
+        tq[:, :4, :] = grot[..., i : i + 1]
+        loc = from_root_quat(tq.permute(0, 2, 1).reshape((1, 1, -1, 4)), drag.parents)
+        disp = (gpos[..., i : i + 1] - drag.current_global_pos.detach().clone()).permute(0, 2, 1)
+        p, R = fk(loc, disp, ref.offsets, drag.parents)
+        pose, gp = drag.run(target_ee_pos=p[0, 0, mask_indices, :], target_ee_rot=R[0, 0, mask_indices, :, :], mask_joints=mask_indices,
+                            weights_joints=weights, offsets=ref.offsets, stop_eps_pos=0.01 * 0.01, stop_eps_rot=0.01, max_iter=100,
+                            min_loss_incr=0.00001, learning_rate=1e-2, lambda_rot=1, lambda_temporal=cfg["lambda_temporal"],
+                            temporal_future_window=cfg["temporal_future_window"], height_indices=[0, 4, 8, 13, 17, 21],
+                            joint_adjustment_indices=tuple(cfg["joint_adjustment_indices"]), joint_adjustment_weight=cfg["joint_adjustment_weight"])
+        results_pose[..., i] = pose.detach()
+        results_gpos[..., i] = gp.detach()
+        its.append(len(rec.take()))
+    return latent0, results_pose, results_gpos, np.asarray(its, np.int32), inp
+
+
+def _reference_result_and_metrics(ref, results_pose, results_gpos, gt_dir, gt_name, n_frames):
+    """eval_drag.py:228-247: train.result_to_bvh (writes data/eval_<name> under a scratch cwd) and eval_metrics.eval_pos_error
+    on the ground-truth / result BVH pair, unmodified.  Returns (mpjpe, mpeepe, text of the written BVH)."""
+    rh.activate()
+    import tempfile
+
+    import eval_metrics
+    import train
+
+    bvh = train.get_bvh_from_disk(gt_dir, gt_name)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        os.makedirs("data")
+        try:
+            import contextlib
+            import io
+
+            with contextlib.redirect_stdout(io.StringIO()):
+                path, fn = train.result_to_bvh(results_pose, None, ref.means, ref.stds, bvh, gt_name, save=True,
+                                               res_global_pos=results_gpos, are_root_rot_incr=False)
+                mpjpe, mpeepe = eval_metrics.eval_pos_error(train.get_bvh_from_disk(gt_dir, gt_name), train.get_bvh_from_disk(path, fn),
+                                                            "cpu", downsample_gt=1)
+            text = open(os.path.join(path, fn)).read()
+        finally:
+            os.chdir(cwd)
+    return mpjpe, mpeepe, text
+
+
+def golden_encoder(ref, n=48):
+    """Encoder.forward (autoencoder.py:136-143) of the shipped generator on real frames: every 100th frame of example.bvh,
+    standardised dual quaternions exactly as eval_drag feeds them (TestMotionData), -> mu, logvar; plus one seeded
+    reparameterisation draw (autoencoder.py:19-22)."""
+    rh.activate()
+    import train
+    from motion_data import TestMotionData
+
+    ds = TestMotionData(train.param, train.scale, "cpu", height_indices=[0, 4, 8, 13, 17, 21])
+    ds.set_means_stds(ref.means, ref.stds)
+    ds.add_motion(ref.offsets_np, ref.pos[:, 0, :], ref.rots, ref.parents, ref.bvh, "example.bvh")
+    ds.normalize()
+    nm = ds.get_item(0)
+    frames = np.arange(n) * 100
+    x = nm["dqs"][frames].unsqueeze(-1)  # (n,176,1)
+    enc = ref.generator.autoencoder.encoder
+    with torch.no_grad():
+        mu, logvar = enc(x)
+        torch.manual_seed(99)
+        latent, mu2, logvar2 = ref.generator.autoencoder.forward_encoder(x)
+    torch.manual_seed(99)
+    eps = torch.randn_like(logvar)
+    assert torch.equal(mu, mu2)
+    np.savez_compressed(os.path.join(OUT, "ref_encoder.npz"), frames=frames, dqs=x[..., 0].numpy(), mu=mu.numpy(), logvar=logvar.numpy(),
+                        eps=eps.numpy(), latent=latent.numpy())
+
+
+def golden_result_path(ref):
+    """Result path on the 48-frame excerpt: train.result_to_bvh output and eval_metrics.eval_pos_error values for the poses recorded in
+    ref_eval_bvh.npz (train.py:437-509, eval_metrics.py:6-32)."""
+    g = np.load(os.path.join(OUT, "ref_eval_bvh.npz"))
+    F_ = g["pose"].shape[0]
+    rp = torch.from_numpy(g["pose"].T.copy())[None]
+    rg = torch.from_numpy(g["gpos"].T.copy())[None]
+    mpjpe, mpeepe, text = _reference_result_and_metrics(ref, rp, rg, OUT, "example_48f.bvh", F_)
+    with open(os.path.join(OUT, "ref_eval_48f_result.bvh"), "w") as fh:
+        fh.write(text)
+    np.savez_compressed(os.path.join(OUT, "ref_eval_metrics.npz"), mpjpe=np.float64(mpjpe), mpeepe=np.float64(mpeepe))
+    print("excerpt: reference MPJPE %.6f MPEEPE %.6f" % (mpjpe, mpeepe))
+
+
+def golden_eval_full(ref):
+    """BASELINE config #1, the known answer of SURVEY section 4: the reference's evaluation on ALL frames of example.bvh with the
+    6-tracker config (early stopping on, seed-2222 random-init predictor) -- about 6 minutes on one core.  Records the metrics of
+    eval_metrics.eval_pos_error, the per-frame iteration counts and root positions, and ships the clip itself gzip-compressed
+    (motion data: CC BY-SA 4.0, LICENSE_data) so the GPU box can run the same evaluation."""
+    import gzip
+    import shutil
+    import time
+
+    n_frames = ref.rots.shape[0]
+    t0 = time.time()
+    latent0, rp, rg, its, _ = _eval_loop(ref, n_frames, "example.bvh")
+    secs = time.time() - t0
+    mpjpe, mpeepe, _ = _reference_result_and_metrics(ref, rp, rg, os.path.dirname(rh.EXAMPLE_BVH), "example.bvh", n_frames)
+    with open(rh.EXAMPLE_BVH, "rb") as src, gzip.GzipFile(os.path.join(OUT, "example_full.bvh.gz"), "wb", compresslevel=9, mtime=0) as dst:
+        shutil.copyfileobj(src, dst)
+    np.savez_compressed(os.path.join(OUT, "ref_eval_full.npz"), latent0=latent0, mpjpe=np.float64(mpjpe), mpeepe=np.float64(mpeepe),
+                        iters=its.astype(np.int16), gpos=rg[0].numpy().T.copy(), pose_every_100=rp[0].numpy().T[::100].copy(),
+                        seconds_one_core=np.float64(secs))
+    print("full clip: %d frames in %.1f s, mean %.2f iterations, reference MPJPE %.6f MPEEPE %.6f" % (n_frames, secs, its.mean(), mpjpe, mpeepe))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ref = build()
     pm = save_model_fixture(ref)
-    which = sys.argv[1:] or ["trace", "frames3", "temporal", "rundrag", "evalbvh"]
+    which = sys.argv[1:] or ["trace", "frames3", "temporal", "rundrag", "evalbvh", "encoder", "resultpath"]
     if "trace" in which:
         golden_iter_traces(ref, pm)
     if "frames3" in which:
@@ -326,4 +465,10 @@ if __name__ == "__main__":
         golden_rundrag(ref)
     if "evalbvh" in which:
         golden_eval_bvh(ref)
+    if "encoder" in which:
+        golden_encoder(ref)
+    if "resultpath" in which:
+        golden_result_path(ref)
+    if "evalfull" in which:  # not in the default list: ~6 minutes
+        golden_eval_full(ref)
     print("golden fixtures written to", OUT)

@@ -44,7 +44,7 @@ def dll(tmp_path_factory):
     lib.dp_last_message.restype = C.c_char_p
     lib.dp_set_initial_latent.argtypes = [V, C.POINTER(C.c_float)]
     d = tmp_path_factory.mktemp("model")
-    export_model.export(os.path.join(ROOT, "tests", "golden", "model_dancedb.npz"), str(d / "model.dpm"))
+    export_model.export(os.path.join(ROOT, "tests", "golden", "model_dancedb.npz"), str(d / "model.dpm"), allow_random_temporal=True)
     return lib, str(d)
 
 

@@ -24,7 +24,7 @@ def test_eval_drag_on_bvh_excerpt_matches_reference(tmp_path, monkeypatch):
                                    joint_adjustment_indices=[0, 0], joint_adjustment_weight=1.0, lambda_temporal=0.02,
                                    temporal_future_window=0)))
     res = eval_drag.evaluate(os.path.join(G, "model_dancedb.npz"), os.path.join(G, "example_48f.bvh"), str(cfg), quiet=True,
-                             initial_latent=g["latent0"])
+                             initial_latent=g["latent0"], random_temporal=True)
     d_it = np.abs(res["iterations"] - g["iters"])
     # iteration counts: exact (+-1) while the trajectories still coincide, statistically equal afterwards (see below)
     assert d_it[:8].max() <= 1 and (d_it <= 1).mean() >= 0.9 and d_it.max() <= 5, (res["iterations"], g["iters"])
@@ -80,8 +80,8 @@ def test_evaluate_batch_world_targets_matches_per_frame_loop(tmp_path, monkeypat
     m = next(i for i, l in enumerate(lines) if l.strip().startswith("Frames:"))
     short.write_text("\n".join(lines[:m] + ["Frames: 20"] + lines[m + 1 : m + 2 + 20]) + "\n")
     npz = os.path.join(G, "model_dancedb.npz")
-    one = eval_drag.evaluate(npz, src, str(cfg), quiet=True, initial_latent=g["latent0"], save=False)
-    res = eval_drag.evaluate_batch(npz, [src, src, str(short)], str(cfg), initial_latents=[g["latent0"]] * 3, save=True)
+    one = eval_drag.evaluate(npz, src, str(cfg), quiet=True, initial_latent=g["latent0"], save=False, random_temporal=True)
+    res = eval_drag.evaluate_batch(npz, [src, src, str(short)], str(cfg), initial_latents=[g["latent0"]] * 3, save=True, random_temporal=True)
     assert len(res) == 3 and res[0]["poses"].shape == (48, 88) and res[2]["poses"].shape == (20, 88)
     assert np.array_equal(res[0]["poses"], res[1]["poses"])  # identical rows give identical results
     assert np.array_equal(res[2]["poses"][:20], res[0]["poses"][:20])  # padding of the short clip does not leak into its frames
@@ -107,7 +107,7 @@ def test_evaluate_batch_default_start_uses_device_encoder(tmp_path, monkeypatch)
 
     monkeypatch.chdir(tmp_path)
     src = os.path.join(G, "example_48f.bvh")
-    res = eval_drag.evaluate_batch(os.path.join(G, "model_dancedb.npz"), [src, src], None, max_frames=16)
+    res = eval_drag.evaluate_batch(os.path.join(G, "model_dancedb.npz"), [src, src], None, max_frames=16, random_temporal=True)
     assert len(res) == 2 and res[0]["poses"].shape == (16, 88) and np.isfinite(res[0]["poses"]).all()
     assert not np.array_equal(res[0]["poses"], res[1]["poses"])  # two different reparameterisation draws
     assert res[0]["mpjpe"] < 0.06 and res[1]["mpjpe"] < 0.06

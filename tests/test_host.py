@@ -105,11 +105,12 @@ def test_bvh_reader_and_rotations():
 
 
 def test_export_model_roundtrip(tmp_path, pose_model):
-    out = export_model.export(os.path.join(ROOT, "tests", "golden", "model_dancedb.npz"), str(tmp_path / "m.dpm"))
+    out = export_model.export(os.path.join(ROOT, "tests", "golden", "model_dancedb.npz"), str(tmp_path / "m.dpm"), allow_random_temporal=True)
     raw = open(out, "rb").read()
     assert raw[:4] == b"DPM1"
-    n = int(np.frombuffer(raw[8:12], np.uint32)[0])
-    flat = np.frombuffer(raw[12:], np.float32)
+    version, n, flags = (int(v) for v in np.frombuffer(raw[4:16], np.uint32))
+    assert version == 2 and flags == 0  # bit 0 clear: the predictor is the random-init stand-in, not a temporal.pt
+    flat = np.frombuffer(raw[16:], np.float32)
     assert flat.size == n == sum(c for _, c in export_model.DPM_FIELDS) + 1283976 + 48
     assert np.array_equal(flat[:960].reshape(40, 24), pose_model.A[0])
 
