@@ -32,7 +32,6 @@ MAX_ITER = 100
 
 KERNEL_NAMES = {
     1: "dp_frame_simt_kernel (persistent per-frame loop; fp32 CUDA-core decoder)",
-    2: "dp_frame_tc_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, bf16x3 split, weights in shared memory)",
     3: "dp_frame_tc16_kernel (persistent per-frame loop; decoder GEMMs on tcgen05, fp16x2 split, weights in tensor memory)",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture whose
@@ -444,7 +443,7 @@ def main():
     ap.add_argument("--trackers", default="6", choices=["6", "3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 C-ABI latency measurement")
-    ap.add_argument("--decoder-path", type=int, default=0, choices=[0, 1, 2, 3], help="0 auto, 1 fp32 CUDA-core decoder, 2 tcgen05 bf16x3, 3 tcgen05 fp16x2")
+    ap.add_argument("--decoder-path", type=int, default=0, choices=[0, 1, 3], help="0 auto, 1 fp32 CUDA-core decoder, 3 tcgen05 fp16x2")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -379,6 +379,8 @@ static int ensure_adam(dp_engine* e, int max_iter, float lr) {
     tab[k - 1] = (float)(lrd / (1.0 - std::pow(0.9, (double)k)));
     tab[max_iter + k - 1] = (float)(1.0 / std::pow(1.0 - std::pow(0.999, (double)k), 0.5));  // kernels multiply by the reciprocal
   }
+  // earlier frames may still be reading the table on a caller-supplied stream (run_frames_device): settle the whole device first
+  CK(cudaDeviceSynchronize());
   if (e->adam_iters != max_iter) {
     cudaFree(e->d_adam);
     e->d_adam = nullptr;
@@ -401,8 +403,18 @@ static int check_params(const dp_engine* e, const dp_run_params* p, int ee_strid
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
   if (p->joint_adjust_joint >= DP_JOINTS || (p->joint_adjust_joint >= 0 && (p->joint_adjust_slot < 0 || p->joint_adjust_slot >= ee_stride)))
     return fail(DP_ERR_ARG, "joint adjustment indices out of range");
-  if (p->decoder_path < 0 || p->decoder_path > 3)
-    return fail(DP_ERR_ARG, "decoder_path must be 0 (auto), 1 (fp32), 2 (tcgen05 bf16x3) or 3 (tcgen05 fp16x2)");
+  if (p->decoder_path != 0 && p->decoder_path != 1 && p->decoder_path != 3)
+    return fail(DP_ERR_ARG, "decoder_path must be 0 (auto), 1 (fp32 CUDA cores) or 3 (tcgen05 fp16x2); 2 (bf16x3) was removed");
+  return DP_OK;
+}
+
+// host-side tracker counts: 1 <= n_ee[c] <= ee_stride, and the joint-adjustment slot must be an active tracker of every clip
+static int check_n_ee(const int32_t* n_ee, size_t count, int ee_stride, const dp_run_params* p) {
+  if (!n_ee) return DP_OK;
+  const int need = (p && p->joint_adjust_joint >= 0) ? p->joint_adjust_slot + 1 : 1;
+  for (size_t i = 0; i < count; ++i)
+    if (n_ee[i] < need || n_ee[i] > ee_stride)
+      return fail(DP_ERR_ARG, "n_ee entries must lie in [1, ee_stride] and cover the joint-adjustment slot");
   return DP_OK;
 }
 
@@ -413,6 +425,9 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   if (e->target_rows != W + 1) {  // drag_pose.py:237-244: fresh zero buffer when the window changes
     CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (W + 1) * DP_L * 4, st));
     e->target_rows = W + 1;
+    // The reference keeps current_index: rows of the zero buffer are used until the index wraps to 0.  An index beyond the new
+    // buffer is an IndexError there (and stays one on every later frame); here the cycle restarts and the predictor runs now.
+    if (e->current_index > W) e->current_index = 0;
   }
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   if (e->profiling) {
@@ -458,7 +473,6 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   // kernel is the low-latency path for small batches (B = 1 streaming)
   const int path = p->decoder_path ? p->decoder_path : (e->n_clips >= 512 ? DP_AUTO_TC_PATH : 1);
   if (path == 3) CK(dp_frame_tc16_launch(a, e->num_sms, st));
-  else if (path == 2) CK(dp_frame_tc_launch(a, e->num_sms, st));
   else CK(dp_frame_simt_launch(a, e->num_sms, st));
   e->last_path = path;
   ++e->launches;
@@ -550,6 +564,7 @@ extern "C" int dp_engine_run_frame_host(dp_engine* e, const dp_run_params* p, co
   const size_t nj = shared ? S : B * S;
   const PipeLayout L((size_t)e->max_clips, (size_t)P.stride);
   unsigned char* h = P.h_in[0];
+  if ((rc = check_n_ee(n_ee, B, ee_stride, p)) != DP_OK) return rc;
   if (n_ee) memcpy(h + L.nee, n_ee, B * 4);
   memcpy(h + L.joints, joints, nj * 4);
   memcpy(h + L.w, weights, nj * 8);
@@ -581,6 +596,7 @@ extern "C" int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, i
   CK(cudaSetDevice(e->device));
   rc = ensure_pipe(e, ee_stride);
   if (rc) return rc;
+  if ((rc = check_n_ee(n_ee, (size_t)n_frames * (size_t)e->n_clips, ee_stride, p)) != DP_OK) return rc;
   rc = ensure_adam(e, p->max_iter, p->learning_rate);
   if (rc) return rc;
   dp_engine::FramePipe& P = e->pipe;
@@ -742,6 +758,7 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
     return fail(DP_ERR_ARG, "dp_engine_eval_gradient: null argument");
   if (!e->has_pose) return fail(DP_ERR_STATE, "pose model not set");
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
+  if (int rcn = check_n_ee(n_ee, (size_t)n, ee_stride, nullptr)) return rcn;
   CK(cudaSetDevice(e->device));
   CK(cudaDeviceSynchronize());
   const size_t N = (size_t)n, S = (size_t)ee_stride, nj = shared ? S : N * S;
@@ -751,7 +768,7 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   CK(cudaMalloc(&d_j, nj * 4)); CK(cudaMalloc(&d_w, nj * 8)); CK(cudaMalloc(&d_tp, N * S * 12)); CK(cudaMalloc(&d_tr, N * S * 36));
   CK(cudaMalloc(&d_grad, N * DP_L * 4)); CK(cudaMalloc(&d_loss, N * 12)); CK(cudaMalloc(&d_pos, N * DP_J * 12));
   CK(cudaMalloc(&d_adam, 8));
-  if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaMemcpyHostToDevice)); }
+if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaMemcpyHostToDevice)); }
   CK(cudaMemcpy(d_lat, latents, N * DP_L * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_g, grot, N * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_t, tgt_latent, N * DP_L * 4, cudaMemcpyHostToDevice));
@@ -769,7 +786,6 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
   a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
   if (decoder_path == 3) CK(dp_frame_tc16_launch(a, e->num_sms, e->stream));
-  else if (decoder_path == 2) CK(dp_frame_tc_launch(a, e->num_sms, e->stream));
   else CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
   ++e->launches;
   CK(cudaStreamSynchronize(e->stream));

@@ -489,13 +489,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
 }  // namespace
 
 cudaError_t dp_frame_tc16_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   const size_t smem = sizeof(SmemT) + 1024;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dp_frame_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = dp_ensure_smem(dp_frame_tc16_kernel, smem, configured); e != cudaSuccess) return e;
   // spread the clips over every SM: 4096 clips -> 28 per CTA (two groups of 14) on 147 SMs
   DpFrameArgs a = args;
   int cpc = (args.n_clips + num_sms - 1) / num_sms;

@@ -1,7 +1,23 @@
 // dp_internal.h -- declarations shared by the engine translation units.
 #pragma once
+#include <atomic>
+
 #include "dp_common.cuh"
 #include "dp_temporal.cuh"
+
+// Opt-in to more than 48 KB of dynamic shared memory.  Function attributes are per device (context): an engine on a second GPU of
+// the same process needs its own call, so the "already done" bit is kept per device; racing threads at worst repeat the call.
+template <class Kernel>
+inline cudaError_t dp_ensure_smem(Kernel kernel, size_t smem, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 #define DP_PRED_MAX_PARTS 4
 #define DP_PRED_PARTS_DEFAULT 2
@@ -19,7 +35,6 @@ struct TpWork {
 #define DP_FF_PART_FLOATS ((size_t)8 * 296 * 128 * TP_D / 2)
 
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);
-cudaError_t dp_frame_tc_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);    // bf16x3, weights in shared memory
 cudaError_t dp_frame_tc16_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);  // fp16x2, weights in tensor memory
 // fftiles: (TP_NENC + TP_NDEC) x FFT_LAYER_BYTES pre-tiled fp16x2 FF weights (encoder layers first) followed by
 // the attention images (ATT_LAYER_BYTES each): TP_NENC encoder self-attention blocks, TP_NDEC decoder self-attention blocks,

@@ -235,12 +235,8 @@ __global__ void __launch_bounds__(MHA_THREADS) tp_mha_ln_kernel(const float* __r
 template <int MQ, int MKV>
 static cudaError_t launch_mha_t(const float* blob, const TpAttn& A, const TpNorm& N, const float* xq, int T, int q_stride, const float* xkv,
                                 int S, int kv_stride, float* out, int B, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tp_mha_ln_kernel<MQ, MKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MhaSmem<MQ, MKV>));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = dp_ensure_smem(tp_mha_ln_kernel<MQ, MKV>, sizeof(MhaSmem<MQ, MKV>), configured); e != cudaSuccess) return e;
   int G = MQ / T < MKV / S ? MQ / T : MKV / S;
   G = G < 1 ? 1 : G;
   tp_mha_ln_kernel<MQ, MKV><<<(B + G - 1) / G, MHA_THREADS, sizeof(MhaSmem<MQ, MKV>), st>>>(blob, A, N, xq, T, q_stride, xkv, S, kv_stride, out, B, G);

@@ -327,13 +327,9 @@ void dp_attn_tc_pack(const float* w_in_t, const float* b_in, const float* w_out_
 template <int SMAX>
 static cudaError_t launch_attn_t(const unsigned char* wimg, const float* blob, const TpNorm& N1, const float* xq, int T, int q_stride,
                                  const float* xkv, int S, int kv_stride, int n_clips, float* out, cudaStream_t st) {
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   const size_t smem = sizeof(Smem) + 1024;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tp_attn_tc_kernel<SMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = dp_ensure_smem(tp_attn_tc_kernel<SMAX>, smem, configured); e != cudaSuccess) return e;
   const int G = kTM / (T > S ? T : S);
   // debug: DP_ATTN_TRACE=n prints the phase clock of CTA 0 of the n-th launch
   static const int want_trace = getenv("DP_ATTN_TRACE") ? atoi(getenv("DP_ATTN_TRACE")) : 0;

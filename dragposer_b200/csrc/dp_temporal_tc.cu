@@ -334,13 +334,9 @@ void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned
 cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const TpFF& F, const TpNorm& N1, const TpNorm& N2, int has_n2,
                             const float* x, int n_rows, int T, int row_stride, float* out, float* part, size_t part_floats, int num_sms,
                             cudaStream_t st, long long* launches) {
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0};
   const size_t smem = sizeof(Smem) + 1024;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tp_ff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = dp_ensure_smem(tp_ff_tc_kernel, smem, configured); e != cudaSuccess) return e;
   const int tiles = (n_rows + kTM - 1) / kTM;
   // hidden split: largest power of two that still leaves every CTA resident at once (two CTAs per SM) and >= 4 chunks each
   int n_split = 1;

@@ -281,11 +281,11 @@ class BatchedDragPose:
         return dict(grad=grad, lp=losses[:, 0], lr=losses[:, 1], lt=losses[:, 2], pos=pos)
 
     def last_decoder_path(self):
-        """1 = fp32 CUDA-core frame kernel, 2 = tcgen05 frame kernel."""
+        """1 = fp32 CUDA-core frame kernel, 3 = tcgen05 (fp16x2) frame kernel."""
         return int(self.lib.dp_engine_last_decoder_path(self.h))
 
     def set_predictor_path(self, path):
-        """0 = tcgen05 3xTF32 feed-forward (default), 1 = fp32 CUDA-core feed-forward."""
+        """0 = tcgen05 fp16x2 attention + feed-forward (default), 1 = fp32 CUDA-core kernels (cross-check)."""
         _lib.check(self.lib.dp_engine_set_predictor_path(self.h, int(path)))
 
     def set_profiling(self, on=True):

@@ -29,6 +29,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this header's entry points are exported */
+#endif
 
 #define DP_JOINTS 22
 #define DP_LATENT 24
@@ -61,7 +64,7 @@ typedef struct {
   int32_t joint_adjust_joint;       /* -1 = joint adjustment off */
   int32_t joint_adjust_slot;        /* end-effector slot the joint is snapped towards */
   float joint_adjust_weight;
-  int32_t decoder_path;             /* 0 = auto, 1 = fp32 CUDA-core decoder, 2 = tcgen05 bf16x3, 3 = tcgen05 fp16x2 */
+  int32_t decoder_path;             /* 0 = auto, 1 = fp32 CUDA-core decoder, 3 = tcgen05 fp16x2 (2, the bf16x3 kernel of round 1, was removed) */
   int32_t targets_world;            /* 0: tgt_pos is relative to the clip's current global position (what DragPose.run takes);
                                        1: tgt_pos is world-absolute and the kernel subtracts the current global position itself
                                        (eval_drag.py:164-202 -- lets whole BVH clips stream without a per-frame host step) */
@@ -168,7 +171,7 @@ int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf, const floa
  * current ring buffers, as drag_pose.py:246-290 does when current_index == 0. */
 int dp_engine_predict_targets(dp_engine* e, int window, void* stream);
 
-/* Decoder path the last frame actually ran: 1 = fp32 CUDA-core kernel, 2 / 3 = tcgen05 kernel (bf16x3 / fp16x2), 0 = none yet.
+/* Decoder path the last frame actually ran: 1 = fp32 CUDA-core kernel, 3 = tcgen05 kernel (fp16x2), 0 = none yet.
  * dp_run_params.decoder_path = 0 picks tcgen05 (fp16x2) for batches >= 512 clips (the measured crossover) and fp32 below. */
 int dp_engine_last_decoder_path(const dp_engine* e);
 
@@ -211,6 +214,9 @@ int dp_engine_pose_error_host(dp_engine* e, int n, const float* pose_a, const fl
 /* Number of kernels launched by this engine since creation (bench "gpu_launches"). */
 long long dp_engine_launch_count(const dp_engine* e);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,7 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dragposer_b200 import _lib
-lib = _lib.load()
+lib = C.CDLL(os.path.join(ROOT, "scripts", "probes", "libdp_probe.so"))  # python -m dragposer_b200.build --probes
 fn = lib.dp_selftest_umma_rate
 fn.restype = C.c_longlong
 fn.argtypes = [C.c_int] * 4

@@ -32,7 +32,7 @@ def pose_positions(pw, pose_std, root_pos=None):
     return pos.numpy()
 
 
-@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
     eng = engine_factory(512)
@@ -66,7 +66,7 @@ def test_gradient_teacher_forced_vs_reference(golden_dir, engine_factory, port_w
     print(f"worst grad rel err vs reference fp32 {worst_rel:.2e}, vs float64 truth {worst_f64:.2e}")
 
 
-@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_model, model_npz, path):
     """20 random states (like SURVEY's probe): relative error <= 1e-4 with no floor, for both decoder paths."""
     rng = np.random.default_rng(11)
@@ -89,7 +89,7 @@ def test_gradient_random_states_vs_float64(golden_dir, engine_factory, pose_mode
     np.testing.assert_allclose(r["pos"], t64["pos"], atol=2e-6)
 
 
-@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 @pytest.mark.parametrize("n_trk", [2, 22], ids=["two-trackers", "every-joint-tracked"])
 def test_gradient_tracker_count_extremes_vs_float64(engine_factory, pose_model, model_npz, path, n_trk):
     """Mask handling at its extremes: the smallest set the reference can run (E = 2) and all 22 joints tracked, per-clip
@@ -119,7 +119,7 @@ def test_gradient_tracker_count_extremes_vs_float64(engine_factory, pose_model, 
     print(f"decoder path {path}, {n_trk} trackers per clip: worst gradient rel err {worst:.2e}")
 
 
-@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 @pytest.mark.parametrize("tag,opt,n_frames", [("fixed", FIXED, 2), ("early", EARLY, 6)])
 def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights, tag, opt, n_frames, path):
     g = np.load(os.path.join(golden_dir, "ref_trace_6trk.npz"))
@@ -253,7 +253,7 @@ def test_device_encoder_matches_folded_encoder(engine_factory, pose_model):
 @pytest.mark.parametrize("n_clips", [5000, 1])
 def test_tcgen05_paths_agree_with_cuda_core_path_multi_wave(engine_factory, pose_model, model_npz, n_clips):
     """More clips than one wave of 32-clip tiles (5000 > 148 x 32) and the single-clip corner, every clip checked: teacher-forced
-    gradients and joint positions of both tensor-core frame kernels against the fp32 CUDA-core kernel (deterministic), then a
+    gradients and joint positions of the tensor-core frame kernel against the fp32 CUDA-core kernel (deterministic), then a
     short optimisation run (robust statistic: an early Adam step is lr * sign(g), so a gradient component inside the fp32 noise
     can flip a +-lr kick between implementations on a few clips out of thousands)."""
     rng = np.random.default_rng(3)
@@ -267,7 +267,7 @@ def test_tcgen05_paths_agree_with_cuda_core_path_multi_wave(engine_factory, pose
               stop_eps_pos=-1.0, stop_eps_rot=-1.0, min_loss_incr=-float("inf"), learning_rate=1e-2,
               joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
     grads, out = {}, {}
-    for path in (1, 2, 3):
+    for path in (1, 3):
         eng = engine_factory(n_clips)
         grads[path] = eng.eval_gradient(lat, grot, tl, wl["tgt_pos"][0], wl["tgt_rot"][0], wl["joints"], wl["weights"], lambda_rot=1.0,
                                         lambda_temporal=0.02, decoder_path=path)
@@ -276,7 +276,7 @@ def test_tcgen05_paths_agree_with_cuda_core_path_multi_wave(engine_factory, pose
             out[path] = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], decoder_path=path, **kw)
         assert eng.last_decoder_path() == path
         eng.close()
-    for path in (2, 3):
+    for path in (3,):
         rel = np.linalg.norm(grads[path]["grad"] - grads[1]["grad"], axis=1) / np.linalg.norm(grads[1]["grad"], axis=1)
         dpos = np.abs(grads[path]["pos"] - grads[1]["pos"]).max()
         dq = np.abs((out[path][0] - out[1][0]) * pose_model.std_q).max(axis=1)  # quaternion components per clip
@@ -312,7 +312,7 @@ def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory,
         assert np.isfinite(tc[:, rows]).all() and err <= 2e-5
 
 
-@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory, port_weights, path):
     g = np.load(os.path.join(golden_dir, "ref_frames_3trk.npz"))
     cfg = synthetic.config_3_trackers()
@@ -335,7 +335,7 @@ def test_frames_3_trackers_variable_mask_vs_reference(golden_dir, engine_factory
     np.testing.assert_allclose(tb[:, :16], g["target_buf"][:, :16], atol=5e-4)
 
 
-@pytest.mark.parametrize("path", [1, 2, 3], ids=["fp32", "tcgen05-bf16x3", "tcgen05-fp16x2"])
+@pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 def test_batch_256_clips_vs_oracle(engine_factory, pose_model, model_npz, port_weights, temporal_model, path):
     """BASELINE config 2: 256 synthetic clips, 6 trackers, against the CPU oracle (batched port)."""
     B, T = 256, 2
