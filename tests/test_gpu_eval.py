@@ -137,3 +137,41 @@ def test_device_pose_error_matches_host_metrics(tmp_path):
     assert abs(mp.mean() - want_m) < 1e-5 and abs(me.mean() - want_e) < 1e-5
     same_m, same_e = BatchedDragPose(pm, off, tm, 64).pose_error(gt, gt)
     assert same_m.max() == 0.0 and same_e.max() == 0.0
+
+
+def test_full_clip_known_answer_matches_reference(tmp_path, monkeypatch):
+    """BASELINE config #1 / SURVEY section 4 known answer: the whole of example.bvh (5 052 frames, 6-tracker config, early stopping
+    on) through both drop-in evaluation paths, against the metrics the UNMODIFIED reference produced for the same clip and the same
+    start latent (oracle/make_golden.py evalfull: train.result_to_bvh + eval_metrics.eval_pos_error).  Late-clip poses are not
+    comparable frame by frame; the accuracy metrics, the root track (snapped to the hip tracker by the joint
+    adjustment every frame) and the iteration statistics are."""
+    import gzip
+    import json
+    import shutil
+
+    from dragposer_b200 import eval_drag, synthetic
+
+    monkeypatch.chdir(tmp_path)
+    g = np.load(os.path.join(G, "ref_eval_full.npz"))
+    src = tmp_path / "example.bvh"
+    with gzip.open(os.path.join(G, "example_full.bvh.gz"), "rb") as fi, open(src, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    c = synthetic.config_6_trackers()
+    cfg = tmp_path / "6.json"
+    cfg.write_text(json.dumps(dict(mask=c.mask.tolist(), weights=c.weights.tolist(), enable_joint_adjustment=True,
+                                   joint_adjustment_indices=[0, 0], joint_adjustment_weight=1.0, lambda_temporal=0.02,
+                                   temporal_future_window=0)))
+    npz = os.path.join(G, "model_dancedb.npz")
+    ref_m, ref_e, ref_it = float(g["mpjpe"]), float(g["mpeepe"]), g["iters"].astype(np.float64)
+    one = eval_drag.evaluate(npz, str(src), str(cfg), quiet=True, initial_latent=g["latent0"], save=True, random_temporal=True)
+    assert one["poses"].shape == (5052, 88) and os.path.exists(one["out_path"])
+    bat = eval_drag.evaluate_batch(npz, [str(src)], str(cfg), initial_latents=[g["latent0"]], random_temporal=True)[0]
+    for name, r in (("eval_drag.evaluate (per-frame DragPose.run)", one), ("eval_drag.evaluate_batch (world targets, run_frames)", bat)):
+        root = np.abs(r["global_pos"] - g["gpos"]).max()
+        print(f"{name}: MPJPE {r['mpjpe']*100:.3f} cm (reference {ref_m*100:.3f}), MPEEPE {r['mpeepe']*100:.3f} cm (reference {ref_e*100:.3f}), "
+              f"root track max diff {root*1e3:.3f} mm" + (f", mean iterations {r['iterations'].mean():.2f} (reference {ref_it.mean():.2f}), "
+              f"{5052 / r['time']:.0f} frames/s (reference: {5052 / float(g['seconds_one_core']):.1f} on one core)" if "iterations" in r else ""))
+        assert abs(r["mpjpe"] - ref_m) < 3e-3 and abs(r["mpeepe"] - ref_e) < 3e-3
+        assert root < 2e-3
+    assert abs(one["iterations"].mean() - ref_it.mean()) < 0.1 * ref_it.mean()
+    assert np.abs(one["iterations"][:8] - g["iters"][:8]).max() <= 1
