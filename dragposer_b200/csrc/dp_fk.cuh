@@ -18,13 +18,25 @@ struct FkOut {
   float lp, lr;        // weighted position loss, lambda-scaled rotation loss (warp-uniform)
 };
 
+// default sink of the adjoint: dL/dy overwrites y in place (all reads of y precede the writes)
+struct FkEmitInPlace {
+  float* ybuf;
+  int lane;
+  __device__ __forceinline__ void operator()(const float4& yb, const float4& db) const {
+    if (lane < DP_J) reinterpret_cast<float4*>(ybuf)[lane] = yb;
+    if (lane == 0) reinterpret_cast<float4*>(ybuf)[DP_J] = db;
+    __syncwarp();
+  }
+};
+
 // Forward kinematics + masked tracker loss (+ adjoint) for ONE clip; lane == joint.
-// y / ybar alias the same 96-float shared buffer (all reads of y precede the writes).
-template <bool ADJOINT, bool EPILOGUE, class MODEL>
-__device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybuf, const ClipTrackers* __restrict__ trk,
+// The adjoint hands dL/dy to `emit(yb, db)`, called convergently by all 32 lanes: yb = dL/dy[4 lane .. 4 lane + 3] (zeros on
+// lanes >= 22), db = dL/d(displacement outputs y[88..91]) on lane 0 (zeros elsewhere).
+template <bool ADJOINT, bool EPILOGUE, class MODEL, class EMIT>
+__device__ __forceinline__ FkOut fk_loss(const MODEL& M, const float* __restrict__ ybuf, const ClipTrackers* __restrict__ trk,
                                          const float g[4], float inv3e, float lrot9e, int lane,
                                          // epilogue outputs
-                                         float q_out[4], float r_out[4], float p_out[3], float d_out[3]) {
+                                         float q_out[4], float r_out[4], float p_out[3], float d_out[3], EMIT emit) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
   const float4 yv = is_joint ? reinterpret_cast<const float4*>(ybuf)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,14 +190,20 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
     yb.y = (qb[1] * inv - u[1] * kk) * sq.y;
     yb.z = (qb[2] * inv - u[2] * kk) * sq.z;
     yb.w = (qb[3] * inv - u[3] * kk) * sq.w;
-    if (is_joint) reinterpret_cast<float4*>(ybuf)[lane] = yb;
+    float4 db4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (is_root) {
       float db[3];
       mat_t_vec(R0, cb, db);
-      reinterpret_cast<float4*>(ybuf)[DP_J] = make_float4(db[0] * M.std_d[0], db[1] * M.std_d[1], db[2] * M.std_d[2], 0.0f);
+      db4 = make_float4(db[0] * M.std_d[0], db[1] * M.std_d[1], db[2] * M.std_d[2], 0.0f);
     }
-    __syncwarp();
+    emit(yb, db4);
   }
   return out;
+}
+template <bool ADJOINT, bool EPILOGUE, class MODEL>
+__device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybuf, const ClipTrackers* __restrict__ trk,
+                                         const float g[4], float inv3e, float lrot9e, int lane, float q_out[4], float r_out[4],
+                                         float p_out[3], float d_out[3]) {
+  return fk_loss<ADJOINT, EPILOGUE>(M, ybuf, trk, g, inv3e, lrot9e, lane, q_out, r_out, p_out, d_out, FkEmitInPlace{ybuf, lane});
 }
 

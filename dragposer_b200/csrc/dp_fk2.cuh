@@ -107,14 +107,35 @@ struct FkOut2 {
   P2 lp, lr;  // weighted position loss, lambda-scaled rotation loss of the two clips (warp-uniform)
 };
 
-// ybuf* / trk*: the two clips' 96-float y rows (dL/dy is written in place) and tracker rows; groot: their previous world
+// Per-lane skeleton indices packed into bytes, read from the model tables ONCE per launch (they were eight shared-memory loads per
+// pass): source lanes of the pulls, a lane's own number where there is nothing to pull (so "take" == src != lane).
+struct FkLaneIdx {
+  uint32_t a;  // parent | jump[0] << 8 | jump[1] << 16 | jump[2] << 24
+  uint32_t b;  // jump[3] | last << 8 | child[0] << 16 | child[1] << 24
+  uint32_t c;  // child[2] | child[3] << 8 | n_jump << 16 | n_child << 24
+};
+template <class MODEL>
+DP_DI FkLaneIdx fk_lane_idx(const MODEL& M, int lane) {
+  auto src = [&](int v) { return (uint32_t)(v >= 0 ? v : lane) & 0xffu; };
+  FkLaneIdx r;
+  r.a = (lane == 0 ? 0u : src(M.parent[lane])) | src(M.jump[0][lane]) << 8 | src(M.jump[1][lane]) << 16 | src(M.jump[2][lane]) << 24;
+  r.b = src(M.jump[3][lane]) | ((uint32_t)M.last[lane] & 0xffu) << 8 | src(M.child[0][lane]) << 16 | src(M.child[1][lane]) << 24;
+  r.c = src(M.child[2][lane]) | src(M.child[3][lane]) << 8 | ((uint32_t)M.pad[0] & 0xffu) << 16 | ((uint32_t)M.pad[1] & 0xffu) << 24;
+  return r;
+}
+DP_DI int fk_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
+
+// ybuf* / trk*: the two clips' 96-float y rows (dL/dy is written in place) and tracker tables -- structure of arrays, float4
+// [4][32] = {tp.xyz w_pos | TR row 0, w_rot | TR row 1 | TR row 2} x lane, so that a warp's 16-byte loads are bank-conflict free
+// (the array-of-structures rows of dp_fk.cuh are 64 bytes apart: four-way conflicts, 96 of the 214 shared-memory wavefronts of a
+// pass in the round-1 profile); groot: their previous world
 // root rotations, 2 x 4 floats in shared memory (re-read where needed instead of held in registers); scr: 16 float2 of
 // per-pair scratch for the warp-uniform R_0, r and d, parked in shared memory between the forward and the adjoint half.
 // SCALE (fp16 tensor-core path): dL/dy of each clip is multiplied by the exact power of two that brings its largest
 // component into [16, 32) before it is written; inv_scale[0..1] receive the two inverse factors.
 template <bool ADJOINT, bool EPILOGUE, bool SCALE = false, class MODEL>
-DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restrict__ ybuf_b, const ClipTrackers* __restrict__ trk_a,
-                      const ClipTrackers* __restrict__ trk_b, const float* __restrict__ groot, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
+DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, float* __restrict__ ybuf_a, float* __restrict__ ybuf_b, const float4* __restrict__ trk_a,
+                      const float4* __restrict__ trk_b, const float* __restrict__ groot, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
                       P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
@@ -150,7 +171,7 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
   const P2 d[3] = {mad(M.std_d[0], mk2(da.x, db.x), splat(M.mean_d[0])), mad(M.std_d[1], mk2(da.y, db.y), splat(M.mean_d[1])),
                    mad(M.std_d[2], mk2(da.z, db.z), splat(M.mean_d[2]))};
   // c_j = R_parent o_j ; p_j = sum of c over the ancestor chain (log-step pointer jumping); p_0 = R_0 d (drag_pose.py:102)
-  const int par = is_root ? 0 : M.parent[lane];
+  const int par = fk_byte(ix.a, 0);
   const float4 off = *reinterpret_cast<const float4*>(M.off[lane]);
   P2 p[3];
   {
@@ -168,23 +189,35 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
 #pragma unroll
     for (int i = 0; i < 3; ++i) scr[13 + i] = d[i].v;
   }
-  const int n_jump = M.pad[0], n_child = M.pad[1];  // rounds this skeleton needs (3 and 3 for the 22-joint body)
+  const int n_jump = fk_byte(ix.c, 2), n_child = fk_byte(ix.c, 3);  // rounds this skeleton needs (3 and 3 for the 22-joint body)
 #pragma unroll
   for (int rd = 0; rd < DP_JUMP_ROUNDS; ++rd) {
     if (rd >= n_jump) break;
-    const int a = M.jump[rd][lane];
-    const int src = a >= 0 ? a : lane;
-    const float take = a >= 0 ? 1.0f : 0.0f;  // multiplicative mask: one FFMA2 instead of a predicated add plus two moves
+    const int src = rd < 3 ? fk_byte(ix.a, rd + 1) : fk_byte(ix.b, 0);
+    const float take = src != lane ? 1.0f : 0.0f;  // multiplicative mask: one FFMA2 instead of a predicated add plus two moves
     const P2 t0 = shfl(p[0], src), t1 = shfl(p[1], src), t2 = shfl(p[2], src);
     p[0] = mad(take, t0, p[0]); p[1] = mad(take, t1, p[1]); p[2] = mad(take, t2, p[2]);
   }
   // masked tracker loss (drag_pose.py:116-124); untracked lanes carry zero weights
-  const ClipTrackers ta = trk_a[lane], tb = trk_b[lane];
-  const P2 ep[3] = {p[0] - mk2(ta.pw.x, tb.pw.x), p[1] - mk2(ta.pw.y, tb.pw.y), p[2] - mk2(ta.pw.z, tb.pw.z)};
-  const P2 wp = mk2(ta.pw.w, tb.pw.w), wr = mk2(ta.r0.w, tb.r0.w);
-  const P2 eR[9] = {R[0] - mk2(ta.r0.x, tb.r0.x), R[1] - mk2(ta.r0.y, tb.r0.y), R[2] - mk2(ta.r0.z, tb.r0.z),
-                    R[3] - mk2(ta.r1.x, tb.r1.x), R[4] - mk2(ta.r1.y, tb.r1.y), R[5] - mk2(ta.r1.z, tb.r1.z),
-                    R[6] - mk2(ta.r2.x, tb.r2.x), R[7] - mk2(ta.r2.y, tb.r2.y), R[8] - mk2(ta.r2.z, tb.r2.z)};
+  P2 ep[3], eR[9], wp, wr;
+  {
+    const float4 a = trk_a[lane], b = trk_b[lane];
+    ep[0] = p[0] - mk2(a.x, b.x); ep[1] = p[1] - mk2(a.y, b.y); ep[2] = p[2] - mk2(a.z, b.z);
+    wp = mk2(a.w, b.w);
+  }
+  {
+    const float4 a = trk_a[32 + lane], b = trk_b[32 + lane];
+    eR[0] = R[0] - mk2(a.x, b.x); eR[1] = R[1] - mk2(a.y, b.y); eR[2] = R[2] - mk2(a.z, b.z);
+    wr = mk2(a.w, b.w);
+  }
+  {
+    const float4 a = trk_a[64 + lane], b = trk_b[64 + lane];
+    eR[3] = R[3] - mk2(a.x, b.x); eR[4] = R[4] - mk2(a.y, b.y); eR[5] = R[5] - mk2(a.z, b.z);
+  }
+  {
+    const float4 a = trk_a[96 + lane], b = trk_b[96 + lane];
+    eR[6] = R[6] - mk2(a.x, b.x); eR[7] = R[7] - mk2(a.y, b.y); eR[8] = R[8] - mk2(a.z, b.z);
+  }
   P2 sp = mad(ep[2], ep[2], mad(ep[1], ep[1], ep[0] * ep[0]));
   P2 sr = eR[0] * eR[0];
 #pragma unroll
@@ -222,7 +255,7 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
       const float take = lane >= o ? 1.0f : 0.0f;
       P[0] = mad(take, t0, P[0]); P[1] = mad(take, t1, P[1]); P[2] = mad(take, t2, P[2]);
     }
-    const int last = M.last[lane];
+    const int last = fk_byte(ix.b, 1);
     P2 cb[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -235,8 +268,7 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
 #pragma unroll
     for (int k = 0; k < DP_MAX_CHILD; ++k) {
       if (k >= n_child) break;
-      const int ch = M.child[k][lane];
-      const int src = ch >= 0 ? ch : lane;
+      const int src = k == 0 ? fk_byte(ix.b, 2) : k == 1 ? fk_byte(ix.b, 3) : fk_byte(ix.c, k - 2);
       const P2 t0 = shfl(cb[0], src), t1 = shfl(cb[1], src), t2 = shfl(cb[2], src);
       const float4 co = *reinterpret_cast<const float4*>(M.coff[k][lane]);  // zero offsets where there is no k-th child
       Rb[0] = mad(co.x, t0, Rb[0]); Rb[1] = mad(co.y, t0, Rb[1]); Rb[2] = mad(co.z, t0, Rb[2]);
@@ -295,14 +327,13 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, float* __restrict__ ybuf_a, float* __restr
       float mb = fmaxf(fmaxf(fabsf(o0.v.y), fabsf(o1.v.y)), fmaxf(fabsf(o2.v.y), fabsf(o3.v.y)));
       ma = fmaxf(ma, fmaxf(fabsf(dbar[0].v.x), fmaxf(fabsf(dbar[1].v.x), fabsf(dbar[2].v.x))));
       mb = fmaxf(mb, fmaxf(fabsf(dbar[0].v.y), fmaxf(fabsf(dbar[1].v.y), fabsf(dbar[2].v.y))));
-#pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) {
-        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, sh));
-        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, sh));
-      }
-      int ea = (int)((__float_as_uint(ma) >> 23) & 0xffu) - 127, eb = (int)((__float_as_uint(mb) >> 23) & 0xffu) - 127;  // floor(log2)
-      ea = ma > 0.f ? max(-100, min(100, ea)) : 4;
-      eb = mb > 0.f ? max(-100, min(100, eb)) : 4;
+      // only floor(log2 max) is needed: the warp maximum of the biased exponent fields, ONE integer REDUX per clip instead of
+      // five dependent shuffles (a zero / denormal maximum has field 0: no scaling)
+      const unsigned fa = __reduce_max_sync(0xffffffffu, (__float_as_uint(ma) >> 23) & 0xffu);
+      const unsigned fb = __reduce_max_sync(0xffffffffu, (__float_as_uint(mb) >> 23) & 0xffu);
+      int ea = (int)fa - 127, eb = (int)fb - 127;
+      ea = fa > 0u ? max(-100, min(100, ea)) : 4;
+      eb = fb > 0u ? max(-100, min(100, eb)) : 4;
       sc = mk2(__uint_as_float((uint32_t)(127 + 4 - ea) << 23), __uint_as_float((uint32_t)(127 + 4 - eb) << 23));
       if (is_root) {
         inv_scale[0] = __uint_as_float((uint32_t)(127 - 4 + ea) << 23);

@@ -22,7 +22,11 @@ namespace {
 constexpr int NC = 32;            // clip columns per CTA: two groups of 16 (UMMA N = 16)
 constexpr int kWarps = 16;     // two groups of 8 warps
 constexpr int EC = 8;             // clips per epilogue thread: a group's 8 warps = 4 TMEM lane quarters x 2 clip halves
-constexpr uint32_t kB_LBO = 128 * (NC / 8);  // activation image: K 8-groups 512 B apart, clip 8-groups 128 B apart
+// activation image (B operand, MN-major, no swizzle): element (feature k, clip column n) of a piece at
+//   (k / 8) * kB_LBO + (k % 8) * 16 + (n / 8) * kB_SBO + (n % 8) * 2 bytes.
+// The K 8-groups are padded from 512 to 528 bytes: at 512 every 8-group starts in the same bank and the 32 lanes of an epilogue
+// warp (consecutive features, one 16-byte store each) collide four ways; 528 moves each group on by four banks.
+constexpr uint32_t kB_LBO = 128 * (NC / 8) + 16;
 constexpr uint32_t kB_SBO = 128;
 constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // per fp16 piece
 constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scaled per clip into [16, 32) (see dp_frame_tc.cu)
@@ -38,7 +42,7 @@ struct SmemT {
   __align__(16) float ybuf[NC][96];                 // y, then dL/dy in place (fp32, one row per clip)
   float zgrad[NC][25];                              // dL/dz from the decoder (fp32)
   float bscale[NC];                                 // 1 / (per-clip power-of-two scale of dL/dy)
-  __align__(16) ClipTrackers trk[NC][32];
+  __align__(16) float4 trk[NC][4][32];              // tracker tables, structure of arrays (dp_fk2.cuh)
   __align__(16) float2 st[NC][5][DP_L / 2];         // [ST_Z latent | ST_TL target latent | ST_M, ST_V Adam moments | ST_ZLAST]
   __align__(16) float groot[NC][4];                 // previous world root rotation g (wxyz)
   __align__(16) float2 fkscr[NC / 2][16];           // per clip pair: R_0, r, d parked between the two halves of the kinematics pass
@@ -203,7 +207,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     const int clip = clip0 + c;
     valid[c] = clip < A.n_clips && 2 * wg + c < cpg && gid * cpg + 2 * wg + c < A.clips_per_cta;
     const int cc = valid[c] ? clip : 0;
-    const int ne = A.n_ee ? A.n_ee[cc] : A.ee_stride;
+    int ne = A.n_ee ? A.n_ee[cc] : A.ee_stride;
+    ne = max(1, min(ne, A.ee_stride));
     inv3e[c] = 1.0f / (3.0f * (float)ne);
     lrot9e[c] = A.lambda_rot / (9.0f * (float)ne);
     if (lane < 4) S.groot[n0 + c][lane] = A.grot[cc * 4 + lane];
@@ -240,7 +245,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
         row.r2 = make_float4(tr[6], tr[7], tr[8], 0.f);
       }
     }
-    S.trk[n0 + c][lane] = row;
+    S.trk[n0 + c][0][lane] = row.pw;
+    S.trk[n0 + c][1][lane] = row.r0;
+    S.trk[n0 + c][2][lane] = row.r1;
+    S.trk[n0 + c][3][lane] = row.r2;
     if (lane < DP_L / 2) {  // latent -> B operand of the first layer
       store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z.x);
       store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z.y);
@@ -254,6 +262,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   __syncthreads();         // tensor-memory weights written by all warps; latent pieces and tracker rows of both groups in place
   tc_fence_after();
 
+  const FkLaneIdx lane_idx = fk_lane_idx(M, lane);  // skeleton indices of this lane, in registers for the whole launch
   constexpr float wsc = 1.0f / kWScale;  // undoes the weight-image scaling
   const int cg0 = 2 * gid;               // first clip 8-group of this group in the activation images
   unsigned neg0 = 0, neg1 = 0;           // LeakyReLU slope bits of (feature k, this thread's 8 clips) for the backward pass
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     float nlp[CPW] = {0.f, 0.f}, nlr[CPW] = {0.f, 0.f};
     if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
       // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is written)
-      const FkOut2 o = fk_loss2<true, false, true>(M, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0], &S.trk[n0 + 1][0], &S.groot[n0][0],
+      const FkOut2 o = fk_loss2<true, false, true>(M, lane_idx, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0][0], &S.trk[n0 + 1][0][0], &S.groot[n0][0],
                                                    &S.fkscr[warp][0], inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0]);
       phase_done(4);
       if (active[0]) { nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x; }
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   forward();
   P2 q2[4], r2[4], p2[3], d2[3];
   if (valid[0] || valid[1])
-    fk_loss2<false, true>(M, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0], &S.trk[n0 + 1][0], &S.groot[n0][0], &S.fkscr[warp][0], inv3e2, lrot9e2, lane, q2, r2, p2, d2);
+    fk_loss2<false, true>(M, lane_idx, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0][0], &S.trk[n0 + 1][0][0], &S.groot[n0][0], &S.fkscr[warp][0], inv3e2, lrot9e2, lane, q2, r2, p2, d2);
 #pragma unroll
   for (int c = 0; c < CPW; ++c) {
     if (!valid[c]) continue;

@@ -12,7 +12,7 @@ pm = model.load_folded_npz(npz); off = np.load(npz)["offsets"]
 tm = model.temporal_from_state(model.random_temporal_state(2222))
 cfg = synthetic.config_6_trackers()
 wl = synthetic.make_workload(pm, off, cfg, B, T)
-for path in (3, 2):
+for path in (3,):
     eng = BatchedDragPose(pm, off, tm, B)
     eng.set_initial_state(wl["latent0"], np.zeros((B, 3), np.float32), np.tile(np.float32([1, 0, 0, 0]), (B, 1)), np.zeros((B, 6), np.float32))
     opts = RunOptions(stop_eps_pos=-1.0, stop_eps_rot=-1.0, max_iter=ITERS, min_loss_incr=-float("inf"), learning_rate=1e-2, lambda_rot=1,
