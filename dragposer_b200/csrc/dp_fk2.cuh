@@ -133,10 +133,15 @@ DP_DI int fk_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
 // per-pair scratch for the warp-uniform R_0, r and d, parked in shared memory between the forward and the adjoint half.
 // SCALE (fp16 tensor-core path): dL/dy of each clip is multiplied by the exact power of two that brings its largest
 // component into [16, 32) before it is written; inv_scale[0..1] receive the two inverse factors.
-template <bool ADJOINT, bool EPILOGUE, bool SCALE = false, class MODEL>
-DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, float* __restrict__ ybuf_a, float* __restrict__ ybuf_b, const float4* __restrict__ trk_a,
+// The adjoint hands dL/dy to `emit(o, db)`, called convergently by all 32 lanes: o[i] = dL/dy[4 lane + i] of the two clips (zeros on
+// lanes >= 22), db[i] = dL/dy[88 + i] on lane 0 (zeros elsewhere), both already multiplied by the SCALE factor.
+struct FkEmitNone {
+  DP_DI void operator()(const P2 (&)[4], const P2 (&)[3]) const {}
+};
+template <bool ADJOINT, bool EPILOGUE, bool SCALE = false, class MODEL, class EMIT = FkEmitNone>
+DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float* __restrict__ ybuf_a, const float* __restrict__ ybuf_b, const float4* __restrict__ trk_a,
                       const float4* __restrict__ trk_b, const float* __restrict__ groot, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
-                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr) {
+                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr, EMIT emit = EMIT()) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -340,15 +345,10 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, float* __restrict__ yb
         inv_scale[1] = __uint_as_float((uint32_t)(127 - 4 + eb) << 23);
       }
     }
-    if (is_joint) {
-      const P2 s0 = SCALE ? o0 * sc : o0, s1 = SCALE ? o1 * sc : o1, s2 = SCALE ? o2 * sc : o2, s3 = SCALE ? o3 * sc : o3;
-      reinterpret_cast<float4*>(ybuf_a)[lane] = make_float4(s0.v.x, s1.v.x, s2.v.x, s3.v.x);
-      reinterpret_cast<float4*>(ybuf_b)[lane] = make_float4(s0.v.y, s1.v.y, s2.v.y, s3.v.y);
-    }
-    if (is_root) {
-      const P2 d0 = SCALE ? dbar[0] * sc : dbar[0], d1 = SCALE ? dbar[1] * sc : dbar[1], d2 = SCALE ? dbar[2] * sc : dbar[2];
-      reinterpret_cast<float4*>(ybuf_a)[DP_J] = make_float4(d0.v.x, d1.v.x, d2.v.x, 0.0f);
-      reinterpret_cast<float4*>(ybuf_b)[DP_J] = make_float4(d0.v.y, d1.v.y, d2.v.y, 0.0f);
+    {
+      const P2 o[4] = {SCALE ? o0 * sc : o0, SCALE ? o1 * sc : o1, SCALE ? o2 * sc : o2, SCALE ? o3 * sc : o3};
+      const P2 db[3] = {SCALE ? dbar[0] * sc : dbar[0], SCALE ? dbar[1] * sc : dbar[1], SCALE ? dbar[2] * sc : dbar[2]};
+      emit(o, db);
     }
     __syncwarp();
   }

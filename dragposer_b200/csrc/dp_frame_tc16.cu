@@ -29,6 +29,13 @@ constexpr int EC = 8;             // clips per epilogue thread: a group's 8 warp
 constexpr uint32_t kB_LBO = 128 * (NC / 8) + 16;
 constexpr uint32_t kB_SBO = 128;
 constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // per fp16 piece
+// dL/dy image (B operand of the first backward layer only), K-MAJOR: element (clip column n, feature k) of a piece at
+//   (n / 8) * kD_SBO + (k / 8) * kD_LBO + (n % 8) * 16 + (k % 8) * 2 bytes,
+// so that the kinematics lane of joint j stores its four values dL/dy[4j .. 4j+3] of a clip as ONE 8-byte word per piece -- the
+// adjoint writes the tensor-core operand itself and the backward layers start after a single group barrier (round 1 wrote fp32
+// rows, and the epilogue warps re-read them transposed, split them and stored them behind a second barrier).  kD_LBO is padded
+// from 128 to 144 bytes for the same bank reason as kB_LBO.
+constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kDyBytes = (NC / 8) * kD_SBO;
 constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scaled per clip into [16, 32) (see dp_frame_tc.cu)
 enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
 // tensor-memory columns: accumulators of group g at 16 g; then the weight pieces (two K elements per 32-bit word)
@@ -39,7 +46,8 @@ struct SmemT {
   __align__(16) unsigned char model[DP_TC_IMAGE_BYTES(0)];   // biases, statistics, skeleton tables (no weight pieces)
   __align__(16) unsigned char ping[2][kPingBytes];  // [piece]  z (24) / a1 (60) / dL/dh1 (60)
   __align__(16) unsigned char pong[2][kPongBytes];  // [piece]  a0 (40) / dL/dy (92) / dL/dh0 (40)
-  __align__(16) float ybuf[NC][96];                 // y, then dL/dy in place (fp32, one row per clip)
+  __align__(16) unsigned char dyimg[2][kDyBytes];   // [piece]  dL/dy (92), K-major
+  __align__(16) float ybuf[NC][96];                 // y (fp32, one row per clip)
   float zgrad[NC][25];                              // dL/dz from the decoder (fp32)
   float bscale[NC];                                 // 1 / (per-clip power-of-two scale of dL/dy)
   __align__(16) float4 trk[NC][4][32];              // tracker tables, structure of arrays (dp_fk2.cuh)
@@ -110,6 +118,34 @@ template <> struct WT<1, false> { static constexpr uint32_t p1 = 240, p2 = 272, 
 template <> struct WT<0, false> { static constexpr uint32_t p1 = 304, p2 = 328, ksteps = 3; };   // K = 48
 static_assert(WT<0, false>::p2 + 24 == DP_TC_TMEM_WORDS, "tensor-memory weight map");
 
+// sink of the kinematics adjoint: the (scaled) dL/dy of the warp's two clips as fp16 pieces of the K-major operand image
+struct EmitDyPieces {
+  unsigned char* img;
+  int n0, lane;
+  static __device__ __forceinline__ void put(unsigned char* dst, float x0, float x1, float x2, float x3) {
+    const uint32_t a = pack_f16x2(x0, x1), b = pack_f16x2(x2, x3);
+    float h0, h1, h2, h3;
+    unpack_f16x2(a, h0, h1);
+    unpack_f16x2(b, h2, h3);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(a, b);
+    *reinterpret_cast<uint2*>(dst + kDyBytes) = make_uint2(pack_f16x2(x0 - h0, x1 - h1), pack_f16x2(x2 - h2, x3 - h3));
+  }
+  __device__ __forceinline__ void operator()(const P2 (&o)[4], const P2 (&db)[3]) const {
+    // clips n0 and n0 + 1 share an 8-group (n0 is even): rows (n0 % 8) and (n0 % 8) + 1 of the same core matrices
+    unsigned char* base = img + (n0 >> 3) * kD_SBO + (n0 & 7) * 16;
+    if (lane < DP_J) {
+      unsigned char* dst = base + (lane >> 1) * kD_LBO + (lane & 1) * 8;  // k = 4 lane: 8-group lane / 2, first or second half
+      put(dst, o[0].v.x, o[1].v.x, o[2].v.x, o[3].v.x);
+      put(dst + 16, o[0].v.y, o[1].v.y, o[2].v.y, o[3].v.y);
+    }
+    if (lane == 0) {  // k = 88 .. 91 (91 is the unused pad output: zero)
+      unsigned char* dst = base + 11 * kD_LBO;
+      put(dst, db[0].v.x, db[1].v.x, db[2].v.x, 0.0f);
+      put(dst + 16, db[0].v.y, db[1].v.y, db[2].v.y, 0.0f);
+    }
+  }
+};
+
 struct Ctx {
   SmemT* S;
   uint32_t tmem;
@@ -119,19 +155,22 @@ struct Ctx {
 
 // one dense layer of one group on the tensor pipe + its epilogue; every thread of the group calls this (ends with the
 // group barrier).  A = weight pieces in tensor memory, B = the group's 16 clip columns of the activation image.
-template <int L, bool FWD, class Epi>
+// B_KMAJOR: the B operand is the K-major dL/dy image instead of an MN-major activation image.
+template <int L, bool FWD, bool B_KMAJOR = false, class Epi>
 __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
   SmemT& S = *c.S;
   if (c.wg == 0) {
     tc_fence_after();
     if (elect_one()) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | (8u << 24);  // fp16 x fp16 -> fp32, B MN-major, N 16, M 128
-      const uint32_t b_base = smem_u32(src) + (uint32_t)c.gid * 2 * kB_SBO;
-      const UmmaDescBase b1 = umma_desc_base(b_base, kB_LBO, kB_SBO), b2 = umma_desc_base(b_base + src_stride, kB_LBO, kB_SBO);
+      // fp16 x fp16 -> fp32, N 16, M 128; bit 16: B is MN-major
+      constexpr uint32_t idesc = (1u << 4) | (B_KMAJOR ? 0u : (1u << 16)) | ((uint32_t)(16 >> 3) << 17) | (8u << 24);
+      constexpr uint32_t lbo = B_KMAJOR ? kD_LBO : kB_LBO, sbo = B_KMAJOR ? kD_SBO : kB_SBO;
+      const uint32_t b_base = smem_u32(src) + (uint32_t)c.gid * 2 * sbo;  // the group's 16 clip columns = two 8-groups
+      const UmmaDescBase b1 = umma_desc_base(b_base, lbo, sbo), b2 = umma_desc_base(b_base + src_stride, lbo, sbo);
       const uint32_t d = c.tmem + kT_D + 16 * c.gid, a1 = c.tmem + kT_W + WT<L, FWD>::p1, a2 = c.tmem + kT_W + WT<L, FWD>::p2;
 #pragma unroll
       for (int k = 0; k < (int)WT<L, FWD>::ksteps; ++k) {  // (2,1) | (1,2) | (1,1), smallest first
-        const uint32_t bo = k * 2 * kB_LBO;
+        const uint32_t bo = k * 2 * lbo;  // K = 16 per instruction: two 8-groups of K
         if (k == 0) umma_f16_ts_c<false>(d, a2 + 8 * k, umma_desc_at(b1, bo), idesc);
         else umma_f16_ts_c<true>(d, a2 + 8 * k, umma_desc_at(b1, bo), idesc);
         umma_f16_ts_c<true>(d, a1 + 8 * k, umma_desc_at(b2, bo), idesc);
@@ -170,8 +209,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&S.tmem_base, kT_COLS);
-  for (int i = threadIdx.x; i < (int)(sizeof(S.ping) + sizeof(S.pong)) / 16; i += kWarps * 32)
-    reinterpret_cast<uint4*>(&S.ping[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);  // ping and pong are contiguous; pad rows must stay finite
+  static_assert(offsetof(SmemT, dyimg) == offsetof(SmemT, ping) + sizeof(S.ping) + sizeof(S.pong), "operand images are contiguous");
+  for (int i = threadIdx.x; i < (int)(sizeof(S.ping) + sizeof(S.pong) + sizeof(S.dyimg)) / 16; i += kWarps * 32)
+    reinterpret_cast<uint4*>(&S.ping[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);  // pad rows / columns must stay finite
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,19 +327,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
       for (int i = 0; i < EC; ++i) S.ybuf[8 * (cg0 + half) + i][k] = fmaf(v[i], wsc, b);
     });
   };
-  auto backward = [&]() {
-    {  // dL/dy (fp32 rows written by the kinematics warps) -> B operand
-      const int k = (wg & 3) * 32 + lane, half = wg >> 2;
-      if (k < DP_Y) {
-        float v[EC];
-#pragma unroll
-        for (int i = 0; i < EC; ++i) v[i] = S.ybuf[8 * (cg0 + half) + i][k];
-        store_pieces(&S.pong[0][0], kPongBytes, k, cg0 + half, v);
-      }
-      fence_proxy_async();
-    }
-    group_sync(gid);
-    tc_layer<2, false>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
+  auto backward = [&]() {  // dL/dy pieces were written by the kinematics warps (EmitDyPieces)
+    tc_layer<2, false, true>(ctx, &S.dyimg[0][0], kDyBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
 #pragma unroll
       for (int i = 0; i < EC; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
       store_pieces(&S.ping[0][0], kPingBytes, k, cg0 + half, v);
@@ -341,11 +370,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
       // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is written)
       const FkOut2 o = fk_loss2<true, false, true>(M, lane_idx, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0][0], &S.trk[n0 + 1][0][0], &S.groot[n0][0],
-                                                   &S.fkscr[warp][0], inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0]);
+                                                   &S.fkscr[warp][0], inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0],
+                                                   EmitDyPieces{&S.dyimg[0][0], n0, lane});
       phase_done(4);
       if (active[0]) { nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x; }
       if (active[1]) { nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y; }
     }
+    fence_proxy_async();  // the dL/dy pieces are read by the tensor core (async proxy)
     group_sync(gid);
     phase_done(1);
     backward();
