@@ -52,7 +52,7 @@ void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned
 // part: workspace of part_floats floats for the hidden-split mode used when the row count cannot fill the device (or null)
 cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const TpFF& F, const TpNorm& N1, const TpNorm& N2, int has_n2,
                             const float* x, int n_rows, int T, int row_stride, float* out, float* part, size_t part_floats, int num_sms,
-                            cudaStream_t st, long long* launches);
+                            cudaStream_t st, long long* launches, const TpFfTail* tail = nullptr);
 // blob: [A0t (176x112) | b0 | A1t (112x72) | b1 | A2t (72x48) | b2 | head_t (48x48: mu | logvar columns) | head_b (48)], DP_ENC_BLOB_FLOATS
 cudaError_t dp_encode_launch(const float* blob, const float* dqs, const float* eps, float* latent, int n, cudaStream_t st);
 // per row: mean joint distance, mean end-effector distance of two poses in the engine's output format (root at the origin)

@@ -7,6 +7,9 @@
 // The encoder memory is computed once per call (the reference recomputes the identical
 // value on every autoregressive step).  The step-function "lerp" of drag_pose.py:282-289
 // is applied while writing target_buf: prediction@i lands in rows i-4..i-1 (and row W).
+#include <cstdlib>
+#include <cstring>
+
 #include "dp_common.cuh"
 #include "dp_temporal.cuh"
 #include "dp_internal.h"
@@ -25,54 +28,51 @@ __device__ __forceinline__ void layer_norm_row(float v0, float v1, bool has1, co
   o1 = has1 ? d1 * rstd * w[lane + 32] + b[lane + 32] : 0.0f;
 }
 
-// ---- encoder token embedding + first decoder token
-__global__ void tp_embed_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ mu,
-                                const float* __restrict__ sigma, const float* __restrict__ latent_buf,
-                                const float* __restrict__ disp_buf, const float* __restrict__ height_buf, int head,
-                                float* __restrict__ enc, float* __restrict__ dec_lat) {
-  __shared__ float x[TP_S][TP_ENC_IN + 3];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int idx = tid; idx < TP_S * TP_ENC_IN; idx += blockDim.x) {
-    const int k = idx / TP_ENC_IN, i = idx % TP_ENC_IN;
+// ---- encoder token embedding + first decoder token (drag_pose.py:249-266, temporal_transformer.py:62-66): ring buffers -> 14 x 33
+// inputs per clip -> Linear(33, 48) + positional encoding.  A CTA takes nine clips (126 tokens): the inputs are staged in shared
+// memory, a thread owns one output feature and keeps its 33 weights in registers for 21 tokens.  (Round 1 launched one 192-thread CTA
+// per clip: 31 us at 4 096 clips, most of it CTA turnover.)
+#define EMB_CLIPS 9
+#define EMB_THREADS 288
+#define EMB_XS (TP_ENC_IN + 3)
+__global__ void __launch_bounds__(EMB_THREADS) tp_embed_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ mu,
+                                                               const float* __restrict__ sigma, const float* __restrict__ latent_buf,
+                                                               const float* __restrict__ disp_buf, const float* __restrict__ height_buf, int head,
+                                                               int n_clips, float* __restrict__ enc, float* __restrict__ dec_lat) {
+  __shared__ float xs[EMB_CLIPS * TP_S * EMB_XS];
+  const int tid = threadIdx.x, clip0 = blockIdx.x * EMB_CLIPS;
+  const int g_here = min(EMB_CLIPS, n_clips - clip0), rows = g_here * TP_S;
+  for (int idx = tid; idx < rows * TP_ENC_IN; idx += EMB_THREADS) {
+    const int r = idx / TP_ENC_IN, i = idx % TP_ENC_IN, k = r % TP_S;
+    const size_t b = (size_t)(clip0 + r / TP_S);
     const int slot = (head + 4 * k) % DP_PAST;
     float v;
     if (i < TP_LAT) {
-      v = (latent_buf[((size_t)b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
+      v = (latent_buf[(b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
     } else if (i < TP_LAT + 3) {
       v = 0.0f;
-      for (int r = 0; r < 4; ++r) v += disp_buf[((size_t)b * DP_PAST + (head + 4 * k + r) % DP_PAST) * 3 + (i - TP_LAT)];
+      for (int q = 0; q < 4; ++q) v += disp_buf[(b * DP_PAST + (head + 4 * k + q) % DP_PAST) * 3 + (i - TP_LAT)];
     } else {
-      v = height_buf[((size_t)b * DP_PAST + slot) * DP_NH + (i - TP_LAT - 3)];
+      v = height_buf[(b * DP_PAST + slot) * DP_NH + (i - TP_LAT - 3)];
     }
-    x[k][i] = v;
+    xs[r * EMB_XS + i] = v;
   }
-  if (tid < TP_LAT) {
-    const int slot = (head + 56) % DP_PAST;
-    dec_lat[((size_t)b * TP_MAXT) * TP_LAT + tid] = (latent_buf[((size_t)b * DP_PAST + slot) * DP_L + tid] - mu[tid]) / sigma[tid];
+  for (int idx = tid; idx < g_here * TP_LAT; idx += EMB_THREADS) {
+    const size_t b = (size_t)(clip0 + idx / TP_LAT);
+    const int i = idx % TP_LAT, slot = (head + 56) % DP_PAST;
+    dec_lat[b * TP_MAXT * TP_LAT + i] = (latent_buf[(b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
   }
   __syncthreads();
-  // 192 threads = 48 features x 4 token groups: a thread owns feature f of tokens kg, kg + 4, kg + 8 (, kg + 12), so every weight
-  // it loads feeds up to four tokens
-  const float* W = blob + L.enc_in_w;
-  const int f = tid % TP_D, kg = tid / TP_D;
-  if (kg < 4) {
-    const float bias = blob[L.enc_in_b + f];
-    float a0 = bias, a1 = bias, a2 = bias, a3 = bias;
-    const bool has3 = kg + 12 < TP_S;
+  const int f = tid % TP_D, rg = tid / TP_D;  // 6 row groups
+  float w[TP_ENC_IN];
 #pragma unroll
-    for (int i = 0; i < TP_ENC_IN; ++i) {
-      const float w = W[i * TP_D + f];
-      a0 = fmaf(x[kg][i], w, a0);
-      a1 = fmaf(x[kg + 4][i], w, a1);
-      a2 = fmaf(x[kg + 8][i], w, a2);
-      if (has3) a3 = fmaf(x[kg + 12][i], w, a3);
-    }
-    float* dst = enc + (size_t)b * TP_S * TP_D + f;
-    const float* pe = blob + L.pe + f;
-    dst[kg * TP_D] = a0 + pe[kg * TP_D];
-    dst[(kg + 4) * TP_D] = a1 + pe[(kg + 4) * TP_D];
-    dst[(kg + 8) * TP_D] = a2 + pe[(kg + 8) * TP_D];
-    if (has3) dst[(kg + 12) * TP_D] = a3 + pe[(kg + 12) * TP_D];
+  for (int i = 0; i < TP_ENC_IN; ++i) w[i] = blob[L.enc_in_w + i * TP_D + f];
+  const float bias = blob[L.enc_in_b + f];
+  for (int r = rg; r < rows; r += EMB_THREADS / TP_D) {
+    float a = bias;
+#pragma unroll
+    for (int i = 0; i < TP_ENC_IN; ++i) a = fmaf(xs[r * EMB_XS + i], w[i], a);
+    enc[((size_t)clip0 * TP_S + r) * TP_D + f] = a + blob[L.pe + (r % TP_S) * TP_D + f];
   }
 }
 
@@ -89,6 +89,23 @@ __global__ void tp_dec_embed_kernel(const float* __restrict__ blob, TpLayout L, 
     for (int i = 0; i < TP_LAT; ++i) a = fmaf(x[t][i], W[i * TP_D + f], a);
     dec[((size_t)b * TP_MAXT + t) * TP_D + f] = a + blob[L.pe + t * TP_D + f];
   }
+}
+
+// ---- single-token decoder pass, first kernel: embedding of the one decoder token + the first layer's self-attention block
+// (one key: row-local, see TpFfTail); one warp per clip.
+__global__ void __launch_bounds__(256) tp_dec_start_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ dec_lat, int n_clips,
+                                                           float* __restrict__ dec) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= n_clips) return;
+  const float lat = lane < TP_LAT ? dec_lat[(size_t)b * TP_MAXT * TP_LAT + lane] : 0.0f;
+  float x0, x1;
+  tp_warp_matvec<TP_LAT>(lat, 0.0f, blob + L.dec_in_w, TP_D, 0, blob + L.dec_in_b, TP_D, lane, x0, x1);
+  x0 += blob[L.pe + lane];
+  if (lane + 32 < TP_D) x1 += blob[L.pe + lane + 32];
+  tp_self_attn_single(blob, L.dec[0].sa, L.dec[0].n1, lane, x0, x1);
+  float* dst = dec + (size_t)b * TP_MAXT * TP_D;
+  dst[lane] = x0;
+  if (lane + 32 < TP_D) dst[lane + 32] = x1;
 }
 
 // ---- out = LayerNorm(xq + MHA(xq, xkv, xkv)); one CTA (160 threads) per clip.
@@ -381,11 +398,11 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
                             size_t part_floats, const unsigned char* fftiles, cudaStream_t st, long long* launches) {
   cudaError_t err = cudaSuccess;
 
-  tp_embed_kernel<<<B, 192, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, w.enc, w.dec_lat);
-  ++*launches;
   float* e = w.enc;
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
+  tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, w.enc, w.dec_lat);
+  ++*launches;
   for (int l = 0; l < TP_NENC; ++l) {
     if (fftiles)
       err = dp_attn_tc_launch(fftiles + DP_TC_ATT_OFFSET + (size_t)l * ATT_LAYER_BYTES, blob, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, B, e2, st);
@@ -404,7 +421,37 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
     *launches += 2;
   }
   int T = 1;
+  static const int fused_dec = getenv("DP_PRED_FUSED_DEC") ? atoi(getenv("DP_PRED_FUSED_DEC")) : 1;
   for (int i = 0; i <= window; i += 4, ++T) {
+    if (fftiles && fused_dec && T == 1) {
+      // single-token pass: embedding + self-attention of layer 0 in one small kernel, then per layer { cross-attention, feed-forward
+      // with the next layer's self-attention (or the prediction head) fused into its finishing kernel }: 10 launches instead of 17
+      const unsigned char* att = fftiles + DP_TC_ATT_OFFSET;
+      tp_dec_start_kernel<<<(B + 7) / 8, 256, 0, st>>>(blob, L, w.dec_lat, B, w.dec2);
+      ++*launches;
+      for (int l = 0; l < TP_NDEC; ++l) {
+        err = dp_attn_tc_launch(att + (size_t)(TP_NENC + TP_NDEC + l) * ATT_LAYER_BYTES, blob, L.dec[l].n2, w.dec2, 1, TP_MAXT, e, TP_S, TP_S, B, w.dec, st);
+        if (err != cudaSuccess) return err;
+        ++*launches;
+        TpFfTail tail;
+        memset(&tail, 0, sizeof(tail));
+        if (l + 1 < TP_NDEC) {
+          tail.next_self_attn = 1;
+          tail.sa = L.dec[l + 1].sa;
+          tail.n1 = L.dec[l + 1].n1;
+        } else {
+          tail.out_head = 1;
+          tail.out_w = L.out_w; tail.out_b = L.out_b;
+          tail.mu = mu; tail.sigma = sigma;
+          tail.dec_lat = w.dec_lat; tail.target_buf = target_buf;
+          tail.step_i = i; tail.window = window;
+        }
+        err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm, l == TP_NDEC - 1, w.dec, B, 1,
+                              TP_MAXT, w.dec2, w.ffpart, part_floats, w.num_sms, st, launches, &tail);
+        if (err != cudaSuccess) return err;
+      }
+      continue;
+    }
     tp_dec_embed_kernel<<<B, 128, 0, st>>>(blob, L, w.dec_lat, T, w.dec);
     ++*launches;
     float* d = w.dec;

@@ -69,7 +69,79 @@ inline TpLayout tp_layout() {
   return L;
 }
 
+// Optional work fused behind the feed-forward block of a SINGLE-TOKEN decoder pass (T == 1: the first autoregressive step, the only
+// one when temporal_future_window == 0): the finished row goes straight through the next decoder layer's self-attention block
+// (one key: softmax == 1, so the block is LN(x + W_o (W_v x + b_v) + b_o), a row-local map) and / or through the prediction head
+// of drag_pose.py:275-289.  Saves the 32-CTA attention launch and the head launch of every layer of the pass.
+struct TpFfTail {
+  int next_self_attn;
+  TpAttn sa;
+  TpNorm n1;
+  int out_head;
+  size_t out_w, out_b;
+  const float* mu;
+  const float* sigma;
+  float* dec_lat;
+  float* target_buf;
+  int step_i, window;
+};
+
 #ifdef __CUDACC__
+// ---- one warp owns one 48-wide row: lane holds features lane and lane + 32 (< 48)
+__device__ __forceinline__ float tp_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void tp_ln_row_warp(float& v0, float& v1, const float* __restrict__ w, const float* __restrict__ b, int lane) {
+  const bool has1 = lane + 32 < TP_D;
+  const float mean = tp_warp_sum(v0 + (has1 ? v1 : 0.0f)) * (1.0f / TP_D);
+  const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.0f;
+  const float rstd = rsqrtf(tp_warp_sum(d0 * d0 + d1 * d1) * (1.0f / TP_D) + 1e-5f);
+  v0 = d0 * rstd * w[lane] + b[lane];
+  v1 = has1 ? d1 * rstd * w[lane + 32] + b[lane + 32] : 0.0f;
+}
+// y = bias + x W for a [K][ldw] weight block starting at column col0 (blob layout: [in][out]); K <= 48 inputs held like a row
+template <int K>
+__device__ __forceinline__ void tp_warp_matvec(float x0, float x1, const float* __restrict__ W, int ldw, int col0, const float* __restrict__ bias,
+                                               int n_out, int lane, float& y0, float& y1) {
+  const bool has0 = lane < n_out, has1 = lane + 32 < n_out;
+  y0 = has0 ? bias[lane] : 0.0f;
+  y1 = has1 ? bias[lane + 32] : 0.0f;
+#pragma unroll 8
+  for (int i = 0; i < K; ++i) {
+    const float xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
+    const float* w = W + (size_t)i * ldw + col0;
+    if (has0) y0 = fmaf(xi, w[lane], y0);
+    if (has1) y1 = fmaf(xi, w[lane + 32], y1);
+  }
+}
+// self-attention block of a single token (its only key is itself): x <- LN(x + W_o (W_v x + b_v) + b_o)
+__device__ __forceinline__ void tp_self_attn_single(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N, int lane, float& x0, float& x1) {
+  float v0, v1, o0, o1;
+  tp_warp_matvec<TP_D>(x0, x1, blob + A.w_in, 3 * TP_D, 2 * TP_D, blob + A.b_in + 2 * TP_D, TP_D, lane, v0, v1);
+  tp_warp_matvec<TP_D>(v0, v1, blob + A.w_out, TP_D, 0, blob + A.b_out, TP_D, lane, o0, o1);
+  x0 += o0;
+  x1 += o1;
+  tp_ln_row_warp(x0, x1, blob + N.w, blob + N.b, lane);
+}
+// prediction head on a finished last-token row (drag_pose.py:275-289): appends the standardised prediction to the decoder inputs
+// and writes the de-standardised one into target_buf with the step-function up-sampling
+__device__ __forceinline__ void tp_out_head_row(const float* __restrict__ blob, const TpFfTail& t, int b, int T, int lane, float x0, float x1) {
+  float a, unused;
+  tp_warp_matvec<TP_D>(x0, x1, blob + t.out_w, TP_LAT, 0, blob + t.out_b, TP_LAT, lane, a, unused);
+  if (lane >= TP_LAT) return;
+  if (T < TP_MAXT) t.dec_lat[((size_t)b * TP_MAXT + T) * TP_LAT + lane] = a;
+  const float val = a * t.sigma[lane] + t.mu[lane];
+  float* tb = t.target_buf + (size_t)b * (t.window + 1) * TP_LAT;
+  if (t.window == 0) {
+    tb[lane] = val;
+  } else if (t.step_i >= 4) {
+    for (int r = t.step_i - 4; r < t.step_i; ++r) tb[r * TP_LAT + lane] = val;
+    if (t.step_i == t.window) tb[t.window * TP_LAT + lane] = val;
+  }
+}
+
 // LayerNorm of one 48-wide row held by one thread (eps 1e-5, torch nn.LayerNorm)
 __device__ __forceinline__ void ln48(float (&v)[TP_D], const float* __restrict__ w, const float* __restrict__ b) {
   float s = 0.f;
