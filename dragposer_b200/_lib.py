@@ -31,6 +31,8 @@ class RunParams(C.Structure):
         ("joint_adjust_weight", C.c_float),
         ("decoder_path", C.c_int32),
         ("targets_world", C.c_int32),
+        ("extension_losses", C.c_int32),
+        ("floor_level", C.c_float),
     ]
 
 
@@ -65,7 +67,7 @@ SIGNATURES = {
     "dp_engine_get_frame_stats": (C.c_int, [_VP, _VP, _VP]),
     "dp_engine_enable_trace": (C.c_int, [_VP, C.c_int]),
     "dp_engine_get_trace": (C.c_int, [_VP, _VP, C.c_int]),
-    "dp_engine_eval_gradient": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_float, C.c_float, C.c_int, _VP, _VP, _VP]),
+    "dp_engine_eval_gradient": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_float, C.c_float, C.c_int, _VP, _VP, _VP, C.c_int, C.c_float, _VP]),
     "dp_engine_get_state": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int)]),
     "dp_engine_set_ring_buffers": (C.c_int, [_VP, _VP, _VP, _VP]),
     "dp_engine_predict_targets": (C.c_int, [_VP, C.c_int, _VP]),

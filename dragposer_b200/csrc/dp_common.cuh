@@ -131,6 +131,9 @@ struct DpFrameArgs {
   float* eval_pos;    // (B,22,3)
   // optional phase clock of CTA 0 (tcgen05 kernel), 8 counters, see dp_engine_get_phase_cycles
   unsigned long long* phase_cycles;
+  // extension losses (drag_pose.py:129-183), fp32 CUDA-core kernel only: bit mask (0 = none) and floor height
+  int ext_mask;
+  float floor_level;
 };
 
 // ---------------------------------------------------------------- small math helpers

@@ -403,6 +403,9 @@ static int check_params(const dp_engine* e, const dp_run_params* p, int ee_strid
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
   if (p->joint_adjust_joint >= DP_JOINTS || (p->joint_adjust_joint >= 0 && (p->joint_adjust_slot < 0 || p->joint_adjust_slot >= ee_stride)))
     return fail(DP_ERR_ARG, "joint adjustment indices out of range");
+  if (p->extension_losses < 0 || p->extension_losses > 15) return fail(DP_ERR_ARG, "extension_losses must be a mask of DP_EXT_* bits");
+  if (p->extension_losses && p->decoder_path == 3)
+    return fail(DP_ERR_UNSUPPORTED, "the extension losses run on the fp32 CUDA-core frame kernel: use decoder_path 0 or 1");
   if (p->decoder_path != 0 && p->decoder_path != 1 && p->decoder_path != 3)
     return fail(DP_ERR_ARG, "decoder_path must be 0 (auto), 1 (fp32 CUDA cores) or 3 (tcgen05 fp16x2); 2 (bf16x3) was removed");
   return DP_OK;
@@ -471,7 +474,9 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   if (e->profiling) CK(cudaEventRecord(ev[1], st));
   // auto: tensor-core decoder from 512 clips (measured crossover: 0.63 vs 0.66 ms per frame at 512, 0.63 vs 0.39 at 256); the fp32 warp-per-clip
   // kernel is the low-latency path for small batches (B = 1 streaming)
-  const int path = p->decoder_path ? p->decoder_path : (e->n_clips >= 512 ? DP_AUTO_TC_PATH : 1);
+  a.ext_mask = p->extension_losses;
+  a.floor_level = p->floor_level;
+  const int path = p->extension_losses ? 1 : (p->decoder_path ? p->decoder_path : (e->n_clips >= 512 ? DP_AUTO_TC_PATH : 1));
   if (path == 3) CK(dp_frame_tc16_launch(a, e->num_sms, st));
   else CK(dp_frame_simt_launch(a, e->num_sms, st));
   e->last_path = path;
@@ -753,12 +758,15 @@ extern "C" int dp_engine_get_trace(dp_engine* e, float* rows, int max_iter) {
 extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents, const float* grot, const float* tgt_latent,
                                        const int32_t* n_ee, const int32_t* joints, const float* weights, int shared,
                                        const float* tgt_pos, const float* tgt_rot, int ee_stride, float lambda_rot,
-                                       float lambda_temporal, int decoder_path, float* grad, float* losses, float* positions) {
+                                       float lambda_temporal, int decoder_path, float* grad, float* losses, float* positions,
+                                       int extension_losses, float floor_level, const float* global_pos) {
   if (!e || !latents || !grot || !tgt_latent || !joints || !weights || !tgt_pos || !tgt_rot || n < 1)
     return fail(DP_ERR_ARG, "dp_engine_eval_gradient: null argument");
   if (!e->has_pose) return fail(DP_ERR_STATE, "pose model not set");
   if (ee_stride < 1 || ee_stride > DP_JOINTS) return fail(DP_ERR_ARG, "ee_stride out of range");
   if (int rcn = check_n_ee(n_ee, (size_t)n, ee_stride, nullptr)) return rcn;
+  if (extension_losses < 0 || extension_losses > 15) return fail(DP_ERR_ARG, "extension_losses must be a mask of DP_EXT_* bits");
+  if (extension_losses && decoder_path == 3) return fail(DP_ERR_UNSUPPORTED, "the extension losses run on the fp32 CUDA-core frame kernel");
   CK(cudaSetDevice(e->device));
   CK(cudaDeviceSynchronize());
   const size_t N = (size_t)n, S = (size_t)ee_stride, nj = shared ? S : N * S;
@@ -768,7 +776,13 @@ extern "C" int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents
   CK(cudaMalloc(&d_j, nj * 4)); CK(cudaMalloc(&d_w, nj * 8)); CK(cudaMalloc(&d_tp, N * S * 12)); CK(cudaMalloc(&d_tr, N * S * 36));
   CK(cudaMalloc(&d_grad, N * DP_L * 4)); CK(cudaMalloc(&d_loss, N * 12)); CK(cudaMalloc(&d_pos, N * DP_J * 12));
   CK(cudaMalloc(&d_adam, 8));
-if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaMemcpyHostToDevice)); }
+  if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaMemcpyHostToDevice)); }
+  float* d_gp = nullptr;
+  if (extension_losses) {
+    CK(cudaMalloc(&d_gp, N * 12));
+    if (global_pos) CK(cudaMemcpy(d_gp, global_pos, N * 12, cudaMemcpyHostToDevice));
+    else CK(cudaMemset(d_gp, 0, N * 12));
+  }
   CK(cudaMemcpy(d_lat, latents, N * DP_L * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_g, grot, N * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_t, tgt_latent, N * DP_L * 4, cudaMemcpyHostToDevice));
@@ -785,6 +799,7 @@ if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaM
   a.eps_pos = -1.0; a.eps_rot = -1.0; a.min_incr = -std::numeric_limits<double>::infinity();
   a.max_iter = 1; a.lambda_rot = lambda_rot; a.lambda_t = lambda_temporal; a.adj_joint = -1;
   a.adam_tab = d_adam; a.out_losses = d_loss; a.eval_only = 1; a.eval_grad = d_grad; a.eval_pos = d_pos;
+  a.gpos = d_gp; a.ext_mask = extension_losses; a.floor_level = floor_level;
   if (decoder_path == 3) CK(dp_frame_tc16_launch(a, e->num_sms, e->stream));
   else CK(dp_frame_simt_launch(a, e->num_sms, e->stream));
   ++e->launches;
@@ -793,7 +808,7 @@ if (n_ee) { CK(cudaMalloc(&d_ne, N * 4)); CK(cudaMemcpy(d_ne, n_ee, N * 4, cudaM
   if (losses) CK(cudaMemcpy(losses, d_loss, N * 12, cudaMemcpyDeviceToHost));
   if (positions) CK(cudaMemcpy(positions, d_pos, N * DP_J * 12, cudaMemcpyDeviceToHost));
   cudaFree(d_lat); cudaFree(d_g); cudaFree(d_t); cudaFree(d_j); cudaFree(d_w); cudaFree(d_tp); cudaFree(d_tr);
-  cudaFree(d_grad); cudaFree(d_loss); cudaFree(d_pos); cudaFree(d_adam); cudaFree(d_ne);
+  cudaFree(d_grad); cudaFree(d_loss); cudaFree(d_pos); cudaFree(d_adam); cudaFree(d_ne); cudaFree(d_gp);
   return DP_OK;
 }
 

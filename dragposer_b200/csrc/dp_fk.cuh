@@ -16,6 +16,16 @@ __device__ __forceinline__ float lrelu(float x) { return x > 0.0f ? x : 0.2f * x
 
 struct FkOut {
   float lp, lr;        // weighted position loss, lambda-scaled rotation loss (warp-uniform)
+  float le;            // sum of the enabled extension losses (0 when none)
+};
+
+// The reference's "Additional Losses" (python/src/drag_pose.py:129-183, commented out as shipped: the documented extension point for
+// constraints expressed as losses; y axis = 1, joints of the 22-joint body).  mask bits: 1 feet on the floor (toes 4, 8),
+// 2 head / hips facing the same way, 4 head above the hips, 8 hips between the feet (ankles 3, 7).  mask == 0 costs nothing.
+struct FkExtra {
+  int mask;
+  float floor_level;
+  float gpos_y;        // y of the clip's current global position (the positions here are relative to the previous root)
 };
 
 // default sink of the adjoint: dL/dy overwrites y in place (all reads of y precede the writes)
@@ -36,7 +46,8 @@ template <bool ADJOINT, bool EPILOGUE, class MODEL, class EMIT>
 __device__ __forceinline__ FkOut fk_loss(const MODEL& M, const float* __restrict__ ybuf, const ClipTrackers* __restrict__ trk,
                                          const float g[4], float inv3e, float lrot9e, int lane,
                                          // epilogue outputs
-                                         float q_out[4], float r_out[4], float p_out[3], float d_out[3], EMIT emit) {
+                                         float q_out[4], float r_out[4], float p_out[3], float d_out[3], EMIT emit,
+                                         const FkExtra X = FkExtra{0, 0.0f, 0.0f}) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
   const float4 yv = is_joint ? reinterpret_cast<const float4*>(ybuf)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -109,6 +120,50 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, const float* __restrict
   FkOut out;
   out.lp = sp * inv3e;
   out.lr = sr * lrot9e;
+  out.le = 0.0f;
+  // extension losses: value, and seeds of the adjoint (pe -> pbar of this lane, re02 / re22 -> Rbar[0][2], Rbar[2][2])
+  float pe[3] = {0.f, 0.f, 0.f}, re02 = 0.f, re22 = 0.f;
+  if (X.mask) {  // warp-uniform
+    float le = 0.0f;
+    const float p0x = __shfl_sync(0xffffffffu, p[0], 0), p0z = __shfl_sync(0xffffffffu, p[2], 0);
+    if ((X.mask & 1) && (lane == 4 || lane == 8)) {  // mean over the two toes of (global y + p_y - floor)^2  (:133-135)
+      const float e = X.gpos_y + (p[1] - X.floor_level);
+      le = fmaf(0.5f * e, e, le);
+      pe[1] = e;
+    }
+    float sx = 0.f, sz = 0.f;  // ground-plane seeds that the hips receive with the opposite sign
+    if ((X.mask & 4) && lane == 13) {  // |head - hips|^2 on the ground plane (:159-164)
+      const float dx = p[0] - p0x, dz = p[2] - p0z;
+      le += dx * dx + dz * dz;
+      sx = 2.0f * dx; sz = 2.0f * dz;
+    }
+    if ((X.mask & 8) && (lane == 3 || lane == 7)) {  // max(|hips - ankle|^2 - 0.2^2, 0) on the ground plane (:166-176)
+      const float dx = p[0] - p0x, dz = p[2] - p0z;
+      const float d2 = dx * dx + dz * dz - 0.2f * 0.2f;
+      if (d2 > 0.0f) { le += d2; sx = 2.0f * dx; sz = 2.0f * dz; }
+    }
+    pe[0] = sx; pe[2] = sz;
+    {
+      const float tx = __shfl_sync(0xffffffffu, sx, 13) + __shfl_sync(0xffffffffu, sx, 3) + __shfl_sync(0xffffffffu, sx, 7);
+      const float tz = __shfl_sync(0xffffffffu, sz, 13) + __shfl_sync(0xffffffffu, sz, 3) + __shfl_sync(0xffffffffu, sz, 7);
+      if (is_root) { pe[0] -= tx; pe[2] -= tz; }
+    }
+    if (X.mask & 2) {  // (1 - min(1, fwd_head . fwd_hips + 0.2))^2 with the forward axes (third columns) flattened to the ground (:137-157)
+      const float hx = __shfl_sync(0xffffffffu, R[2], 13), hz = __shfl_sync(0xffffffffu, R[8], 13);
+      const float gx = R0[2], gz = R0[8];
+      const float nh = sqrtf(hx * hx + hz * hz), ng = sqrtf(gx * gx + gz * gz);
+      if (nh > 0.5f) {
+        const float ihx = hx / nh, ihz = hz / nh, igx = gx / ng, igz = gz / ng;
+        const float s = ihx * igx + ihz * igz, c = s + 0.2f;
+        if (c < 1.0f) {
+          const float dl = -2.0f * (1.0f - c);  // dL/ds
+          if (lane == 13) { re02 = dl * (igx - s * ihx) / nh; re22 = dl * (igz - s * ihz) / nh; }
+          if (is_root) { re02 = dl * (ihx - s * igx) / ng; re22 = dl * (ihz - s * igz) / ng; le += (1.0f - c) * (1.0f - c); }
+        }
+      }
+    }
+    out.le = warp_sum(le);
+  }
   if (EPILOGUE) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { q_out[i] = q[i]; r_out[i] = r[i]; }
@@ -118,10 +173,12 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, const float* __restrict
   if (ADJOINT) {
     // seeds
     const float kp = 2.0f * wp * inv3e, kr = 2.0f * wr * lrot9e;
-    float pb[3] = {ep[0] * kp, ep[1] * kp, ep[2] * kp};
+    float pb[3] = {fmaf(ep[0], kp, pe[0]), fmaf(ep[1], kp, pe[1]), fmaf(ep[2], kp, pe[2])};
     float Rb[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) Rb[i] = eR[i] * kr;
+    Rb[2] += re02;
+    Rb[8] += re22;
     // subtree sums of pbar over the pre-order numbering: inclusive scan, then a range difference
     float P[3] = {pb[0], pb[1], pb[2]};
 #pragma unroll
@@ -205,5 +262,11 @@ __device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybu
                                          const float g[4], float inv3e, float lrot9e, int lane, float q_out[4], float r_out[4],
                                          float p_out[3], float d_out[3]) {
   return fk_loss<ADJOINT, EPILOGUE>(M, ybuf, trk, g, inv3e, lrot9e, lane, q_out, r_out, p_out, d_out, FkEmitInPlace{ybuf, lane});
+}
+template <bool ADJOINT, bool EPILOGUE, class MODEL>
+__device__ __forceinline__ FkOut fk_loss(const MODEL& M, float* __restrict__ ybuf, const ClipTrackers* __restrict__ trk,
+                                         const float g[4], float inv3e, float lrot9e, int lane, float q_out[4], float r_out[4],
+                                         float p_out[3], float d_out[3], const FkExtra X) {
+  return fk_loss<ADJOINT, EPILOGUE>(M, ybuf, trk, g, inv3e, lrot9e, lane, q_out, r_out, p_out, d_out, FkEmitInPlace{ybuf, lane}, X);
 }
 

@@ -269,26 +269,26 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
       S.loss[n0 + c][0] = S.loss[n0 + c][1] = S.loss[n0 + c][2] = __int_as_float(0x7f800000);
       S.iters[n0 + c] = 0;
     }
-    ClipTrackers row;
-    row.pw = row.r0 = row.r1 = row.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float origin[3] = {0.f, 0.f, 0.f};  // world-absolute targets are taken relative to the clip's current global position
-    if (A.targets_world) { origin[0] = A.gpos[cc * 3]; origin[1] = A.gpos[cc * 3 + 1]; origin[2] = A.gpos[cc * 3 + 2]; }
-    const int32_t* jn = A.joints + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride);
-    const float* wt = A.weights + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride * 2);
-    for (int e = 0; e < ne; ++e) {
-      if (jn[e] == lane) {
-        const float* tp = A.tgt_pos + ((size_t)cc * A.ee_stride + e) * 3;
-        const float* tr = A.tgt_rot + ((size_t)cc * A.ee_stride + e) * 9;
-        row.pw = make_float4(tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt[2 * e]);
-        row.r0 = make_float4(tr[0], tr[1], tr[2], wt[2 * e + 1]);
-        row.r1 = make_float4(tr[3], tr[4], tr[5], 0.f);
-        row.r2 = make_float4(tr[6], tr[7], tr[8], 0.f);
+    // tracker stream of the clip: lane e loads slot e (all slots in flight at once, neighbouring lanes read neighbouring
+    // addresses) and scatters its row to the lane of the joint it tracks; untracked joints keep zero weights
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) S.trk[n0 + c][i][lane] = zero4;
+    __syncwarp();
+    if (lane < ne) {
+      float origin[3] = {0.f, 0.f, 0.f};  // world-absolute targets are taken relative to the clip's current global position
+      if (A.targets_world) { origin[0] = A.gpos[cc * 3]; origin[1] = A.gpos[cc * 3 + 1]; origin[2] = A.gpos[cc * 3 + 2]; }
+      const int j = A.joints[(A.shared_trackers ? 0 : (size_t)cc * A.ee_stride) + lane];
+      const float2 wt = reinterpret_cast<const float2*>(A.weights + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride * 2))[lane];
+      const float* tp = A.tgt_pos + ((size_t)cc * A.ee_stride + lane) * 3;
+      const float* tr = A.tgt_rot + ((size_t)cc * A.ee_stride + lane) * 9;
+      if (j >= 0 && j < DP_J) {
+        S.trk[n0 + c][0][j] = make_float4(tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt.x);
+        S.trk[n0 + c][1][j] = make_float4(tr[0], tr[1], tr[2], wt.y);
+        S.trk[n0 + c][2][j] = make_float4(tr[3], tr[4], tr[5], 0.f);
+        S.trk[n0 + c][3][j] = make_float4(tr[6], tr[7], tr[8], 0.f);
       }
     }
-    S.trk[n0 + c][0][lane] = row.pw;
-    S.trk[n0 + c][1][lane] = row.r0;
-    S.trk[n0 + c][2][lane] = row.r1;
-    S.trk[n0 + c][3][lane] = row.r2;
     if (lane < DP_L / 2) {  // latent -> B operand of the first layer
       store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z.x);
       store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z.y);

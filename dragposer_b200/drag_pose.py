@@ -147,7 +147,9 @@ class DragPose:
     def run(self, target_ee_pos, target_ee_rot, mask_joints, weights_joints, offsets, stop_eps_pos=1e-2, stop_eps_rot=1e-2,
             max_iter=100, min_loss_incr=0.00001, learning_rate=1e-3, lambda_rot=1, lambda_temporal=1,
             temporal_future_window=60, height_indices=(0, 4, 8, 13, 17, 21), joint_adjustment_indices=None,
-            joint_adjustment_weight=0.01, verbose=False):
+            joint_adjustment_weight=0.01, verbose=False, extension_losses=0, floor_level=0.0):
+        """extension_losses / floor_level (not in the reference signature): bit mask re-enabling the reference's commented-out
+        "Additional Losses" (drag_pose.py:129-183), see engine.EXT_*; 0 = the shipped behaviour."""
         if list(height_indices) != [0, 4, 8, 13, 17, 21]:
             raise ValueError("height_indices other than train_temporal.param['height_indices'] are not supported")
         assert temporal_future_window % dpm.SAMPLE_STEP == 0  # drag_pose.py:236
@@ -158,7 +160,8 @@ class DragPose:
                              _as_np(weights_joints).reshape(E, 2), stop_eps_pos=stop_eps_pos, stop_eps_rot=stop_eps_rot,
                              max_iter=max_iter, min_loss_incr=min_loss_incr, learning_rate=learning_rate, lambda_rot=lambda_rot,
                              lambda_temporal=lambda_temporal, temporal_future_window=temporal_future_window,
-                             joint_adjustment_indices=joint_adjustment_indices, joint_adjustment_weight=joint_adjustment_weight)
+                             joint_adjustment_indices=joint_adjustment_indices, joint_adjustment_weight=joint_adjustment_weight,
+                             extension_losses=extension_losses, floor_level=floor_level)
         iters, losses = eng.frame_stats()
         self.last_iterations, self.last_losses = int(iters[0]), losses[0]
         if verbose:

@@ -67,18 +67,23 @@ def pack_temporal(tm: TemporalModel) -> np.ndarray:
     return np.concatenate(parts)
 
 
+# bits of `extension_losses`: the reference's "Additional Losses" (python/src/drag_pose.py:129-183, commented out as shipped)
+EXT_FEET_FLOOR, EXT_FORWARD, EXT_HEAD_HIPS, EXT_HIPS_FEET = 1, 2, 4, 8
+
+
 class RunOptions:
-    """Keyword surface of DragPose.run (python/src/drag_pose.py:196-215), same defaults."""
+    """Keyword surface of DragPose.run (python/src/drag_pose.py:196-215), same defaults, plus the engine's own switches
+    (decoder_path, targets_world, extension_losses / floor_level -- see include/dp_engine.h:dp_run_params)."""
 
     def __init__(self, stop_eps_pos=1e-2, stop_eps_rot=1e-2, max_iter=100, min_loss_incr=0.00001, learning_rate=1e-3,
                  lambda_rot=1, lambda_temporal=1, temporal_future_window=60, joint_adjustment_indices=None,
-                 joint_adjustment_weight=0.01, decoder_path=0, targets_world=False):
+                 joint_adjustment_weight=0.01, decoder_path=0, targets_world=False, extension_losses=0, floor_level=0.0):
         self.c = _lib.RunParams(
             float(stop_eps_pos), float(stop_eps_rot), float(min_loss_incr), int(max_iter), float(learning_rate),
             float(lambda_rot), float(lambda_temporal), int(temporal_future_window),
             -1 if joint_adjustment_indices is None else int(joint_adjustment_indices[0]),
             0 if joint_adjustment_indices is None else int(joint_adjustment_indices[1]),
-            float(joint_adjustment_weight), int(decoder_path), int(bool(targets_world)))
+            float(joint_adjustment_weight), int(decoder_path), int(bool(targets_world)), int(extension_losses), float(floor_level))
 
 
 class BatchedDragPose:
@@ -265,7 +270,7 @@ class BatchedDragPose:
         return dict(latent=rows[..., :24], grad=rows[..., 24:48], loss=rows[..., 48:51], active=rows[..., 51] > 0)
 
     def eval_gradient(self, latents, global_rot, tgt_latent, tgt_pos, tgt_rot, joints, weights, n_ee=None, lambda_rot=1.0,
-                      lambda_temporal=1.0, decoder_path=0):
+                      lambda_temporal=1.0, decoder_path=0, extension_losses=0, floor_level=0.0, global_pos=None):
         """Teacher-forced loss + d(loss)/d(latent) at given latents; no state change."""
         z = _f32(latents).reshape(-1, 24)
         n = z.shape[0]
@@ -275,9 +280,11 @@ class BatchedDragPose:
         tr = _f32(tgt_rot).reshape(n, E, 9)
         joints, weights, shared, ne = self._trackers(joints, weights, n_ee, n, E)
         grad, losses, pos = np.empty((n, 24), F32), np.empty((n, 3), F32), np.empty((n, 22, 3), F32)
+        gp = None if global_pos is None else _f32(global_pos).reshape(n, 3)
         _lib.check(self.lib.dp_engine_eval_gradient(self.h, n, _ptr(z), _ptr(g), _ptr(t), _ptr(ne), _ptr(joints), _ptr(weights),
                                                     shared, _ptr(tp), _ptr(tr), E, float(lambda_rot), float(lambda_temporal),
-                                                    int(decoder_path), _ptr(grad), _ptr(losses), _ptr(pos)))
+                                                    int(decoder_path), _ptr(grad), _ptr(losses), _ptr(pos), int(extension_losses),
+                                                    float(floor_level), _ptr(gp)))
         return dict(grad=grad, lp=losses[:, 0], lr=losses[:, 1], lt=losses[:, 2], pos=pos)
 
     def last_decoder_path(self):

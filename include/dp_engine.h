@@ -68,7 +68,16 @@ typedef struct {
   int32_t targets_world;            /* 0: tgt_pos is relative to the clip's current global position (what DragPose.run takes);
                                        1: tgt_pos is world-absolute and the kernel subtracts the current global position itself
                                        (eval_drag.py:164-202 -- lets whole BVH clips stream without a per-frame host step) */
+  int32_t extension_losses;         /* bit mask of the reference's "Additional Losses" (drag_pose.py:129-183, commented out as shipped;
+                                       added to the total loss with weight 1, y axis = 1): DP_EXT_FEET_FLOOR | DP_EXT_FORWARD |
+                                       DP_EXT_HEAD_HIPS | DP_EXT_HIPS_FEET; 0 = none (the shipped behaviour).  Runs on the fp32
+                                       CUDA-core frame kernel (decoder_path 3 is refused with a non-zero mask). */
+  float floor_level;                /* floor height of DP_EXT_FEET_FLOOR (drag_pose.py:134) */
 } dp_run_params;
+#define DP_EXT_FEET_FLOOR 1   /* mean over the toes (joints 4, 8) of (global y + p_y - floor)^2          drag_pose.py:133-135 */
+#define DP_EXT_FORWARD 2      /* (1 - min(1, fwd_head . fwd_hips + 0.2))^2, axes flattened to the ground  drag_pose.py:137-157 */
+#define DP_EXT_HEAD_HIPS 4    /* |head - hips|^2 on the ground plane                                      drag_pose.py:159-164 */
+#define DP_EXT_HIPS_FEET 8    /* sum over the ankles (3, 7) of max(|hips - ankle|^2 - 0.2^2, 0)           drag_pose.py:166-176 */
 
 /* Pose-VAE decoder folded to three dense layers + statistics + skeleton.
  * All pointers are HOST memory, row-major, float32 unless stated. */
@@ -151,12 +160,14 @@ int dp_engine_get_trace(dp_engine* e, float* rows, int max_iter);
 
 /* Teacher-forced single evaluation (no state change): latents (n,24), global_rot (n,4),
  * tgt_latent (n,24) + trackers as above; grad (n,24), losses (n,3), positions (n,22,3)
- * (any output may be NULL).  HOST pointers. */
+ * (any output may be NULL).  extension_losses / floor_level as in dp_run_params, global_pos (n,3) = the clips' current global
+ * positions (only the feet-floor term reads it; NULL = zeros).  HOST pointers. */
 int dp_engine_eval_gradient(dp_engine* e, int n, const float* latents, const float* global_rot,
                             const float* tgt_latent, const int32_t* n_ee, const int32_t* joints,
                             const float* weights, int shared_trackers, const float* tgt_pos,
                             const float* tgt_rot, int ee_stride, float lambda_rot, float lambda_temporal,
-                            int decoder_path, float* grad, float* losses, float* positions);
+                            int decoder_path, float* grad, float* losses, float* positions,
+                            int extension_losses, float floor_level, const float* global_pos);
 
 /* Copies of the carried state in chronological ring order (HOST pointers, any may be
  * NULL): latent (B,24), global_pos (B,3), global_rot (B,4), latent_buf (B,60,24),

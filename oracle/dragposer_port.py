@@ -158,6 +158,33 @@ def from_root_quat(q, parents):
     return out
 
 
+EXT_FEET_FLOOR, EXT_FORWARD, EXT_HEAD_HIPS, EXT_HIPS_FEET = 1, 2, 4, 8
+
+
+def extension_losses(pos, rot, global_pos, mask, floor_level=0.0):
+    """The four "Additional Losses" of drag_pose.py:129-183 (commented out in the shipped reference; y axis = 1), per clip (B,).
+    pos (B,J,3) relative to the previous root, rot (B,J,3,3), global_pos (B,3) = current_global_pos."""
+    B = pos.shape[0]
+    total = pos.new_zeros(B)
+    if mask & EXT_FEET_FLOOR:  # :133-135
+        total = total + ((global_pos[:, 1:2] + (pos[:, [4, 8], 1] - floor_level)) ** 2).mean(1)
+    if mask & EXT_FORWARD:  # :137-157; quat.mul_vec(quat.from_matrix(R), (0,0,1)) is the third column of R
+        fh = rot[:, 13, :, 2] * pos.new_tensor([1.0, 0.0, 1.0])
+        nh = fh.norm(dim=-1)
+        fg = rot[:, 0, :, 2] * pos.new_tensor([1.0, 0.0, 1.0])
+        fg = fg / fg.norm(dim=-1, keepdim=True)
+        s = ((fh / nh[:, None].clamp(min=1e-30)) * fg).sum(-1) + 0.2
+        term = (1 - torch.minimum(torch.ones_like(s), s)) ** 2
+        total = total + torch.where(nh > 0.5, term, torch.zeros_like(term))
+    flat = pos.new_tensor([1.0, 0.0, 1.0])
+    if mask & EXT_HEAD_HIPS:  # :159-164 (global_pos cancels)
+        total = total + (((pos[:, 13] - pos[:, 0]) * flat) ** 2).sum(-1)
+    if mask & EXT_HIPS_FEET:  # :166-176
+        for j in (3, 7):
+            total = total + torch.clamp((((pos[:, 0] - pos[:, j]) * flat) ** 2).sum(-1) - 0.2 * 0.2, min=0.0)
+    return total
+
+
 def tracker_loss(w, latent, motion, disp, g_rot, tgt_pos, tgt_rot, tgt_latent, joints, weights, valid,
                  lambda_rot, lambda_temporal):
     """Per-clip loss terms (B,), plus the by-products the frame epilogue needs.
@@ -179,7 +206,7 @@ def tracker_loss(w, latent, motion, disp, g_rot, tgt_pos, tgt_rot, tgt_latent, j
     lp = (((p_sel - tgt_pos) ** 2) * (weights[..., 0] * valid)[..., None]).sum((1, 2)) / (3.0 * n_e)
     lr = (((r_sel - tgt_rot) ** 2) * (weights[..., 1] * valid)[..., None, None]).sum((1, 2, 3)) / (9.0 * n_e)
     lt = ((latent - tgt_latent) ** 2).mean(1)
-    return lp, lr * lambda_rot, lt * lambda_temporal, world_disp, d, world_rot, pos
+    return lp, lr * lambda_rot, lt * lambda_temporal, world_disp, d, world_rot, pos, rot
 
 
 def adam_step(z, g, m, v, step, lr, active):
@@ -297,7 +324,7 @@ class PortDragPose:
 
     def run(self, tgt_pos, tgt_rot, joints, weights, n_ee=None, stop_eps_pos=1e-2, stop_eps_rot=1e-2,
             max_iter=100, min_loss_incr=1e-5, learning_rate=1e-3, lambda_rot=1.0, lambda_temporal=1.0,
-            temporal_future_window=60, joint_adjustment=None, joint_adjustment_weight=0.01):
+            temporal_future_window=60, joint_adjustment=None, joint_adjustment_weight=0.01, extension_losses_mask=0, floor_level=0.0):
         f = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32)
         B = self.latent.shape[0]
         tgt_pos, tgt_rot, weights = f(tgt_pos), f(tgt_rot), f(weights)
@@ -334,10 +361,12 @@ class PortDragPose:
                 break
             z = self.latent.clone().requires_grad_(True)
             motion, disp = decode(self.w, z)
-            l_p, l_r, l_t, wdisp, d_root, wrot, pos = tracker_loss(
+            l_p, l_r, l_t, wdisp, d_root, wrot, pos, rot_all = tracker_loss(
                 self.w, z, motion, disp, self.grot, tgt_pos, tgt_rot, tgt_latent, joints, weights, valid,
                 lambda_rot, lambda_temporal)
             total = l_p + l_r + l_t
+            if extension_losses_mask:
+                total = total + extension_losses(pos, rot_all, self.gpos, extension_losses_mask, floor_level)
             (total * active.float()).sum().backward()
             g = z.grad
             if self.trace is not None:
@@ -403,7 +432,7 @@ def time_reference_loop(npz_path, temporal_sd, n_clips, n_frames, max_iter, work
 
 
 def loss_and_grad(w: PortWeights, latent, g_rot, tgt_pos, tgt_rot, tgt_latent, joints, weights, n_ee=None,
-                  lambda_rot=1.0, lambda_temporal=1.0, dtype=torch.float32):
+                  lambda_rot=1.0, lambda_temporal=1.0, dtype=torch.float32, extension_losses_mask=0, global_pos=None, floor_level=0.0):
     """Teacher-forced evaluation: loss terms and d(loss)/d(latent) at given latents (B,24).
     dtype=torch.float64 (with PortWeights(..., dtype=torch.float64)) gives the float64 truth."""
     f = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float32).to(dtype)
@@ -420,10 +449,14 @@ def loss_and_grad(w: PortWeights, latent, g_rot, tgt_pos, tgt_rot, tgt_latent, j
     valid = (torch.arange(E)[None] < n_ee[:, None]).to(dtype)
     joints = torch.where(valid > 0, joints, torch.zeros_like(joints))
     motion, disp = decode(w, z)
-    lp, lr, lt, wdisp, d_root, wrot, pos = tracker_loss(w, z, motion, disp, f(g_rot), f(tgt_pos), f(tgt_rot),
+    lp, lr, lt, wdisp, d_root, wrot, pos, rot_all = tracker_loss(w, z, motion, disp, f(g_rot), f(tgt_pos), f(tgt_rot),
                                                         f(tgt_latent), joints, weights, valid, lambda_rot,
                                                         lambda_temporal)
-    (lp + lr + lt).sum().backward()
-    return dict(lp=lp.detach().numpy(), lr=lr.detach().numpy(), lt=lt.detach().numpy(), grad=z.grad.numpy(),
+    le = torch.zeros_like(lp)
+    if extension_losses_mask:
+        gp = torch.zeros(B, 3, dtype=dtype) if global_pos is None else f(global_pos)
+        le = extension_losses(pos, rot_all, gp, extension_losses_mask, floor_level)
+    (lp + lr + lt + le).sum().backward()
+    return dict(lp=lp.detach().numpy(), lr=lr.detach().numpy(), lt=lt.detach().numpy(), le=le.detach().numpy(), grad=z.grad.numpy(),
                 pos=pos.detach().numpy(), motion=motion.detach().numpy(), wrot=wrot.detach().numpy(),
                 wdisp=wdisp.detach().numpy())

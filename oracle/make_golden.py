@@ -65,7 +65,7 @@ class Recorder:
             self._close()
             out = orig_loss(*a, **k)
             self.rows.append(dict(latent=drag.latent.detach().clone().numpy()[0], lp=float(out[0]),
-                                  lr=float(out[1]), lt=float(out[2])))
+                                  lr=float(out[1]), lt=float(out[2]), le=float(out[3])))
             return out
 
         drag.loss = loss
@@ -80,18 +80,18 @@ class Recorder:
         return rows
 
 
-def init_drag(ref, latent0):
-    drag = ref.new_drag()
-    drag.set_initial_pose(torch.zeros(1, 176, 1), torch.zeros(1, 3, 1), torch.tensor([[1.0, 0, 0, 0]]).unsqueeze(-1),
-                          torch.zeros(6))
+def init_drag(ref, latent0, extension_losses=False, gpos0=(0.0, 0.0, 0.0)):
+    drag = ref.new_drag(extension_losses=extension_losses)
+    drag.set_initial_pose(torch.zeros(1, 176, 1), torch.tensor(gpos0, dtype=torch.float32).reshape(1, 3, 1),
+                          torch.tensor([[1.0, 0, 0, 0]]).unsqueeze(-1), torch.zeros(6))
     z = torch.from_numpy(latent0.copy()).reshape(1, 24)
     drag.latent = z.clone().requires_grad_()
     drag.latent_buffer = torch.tile(z, (60, 1))
     return drag
 
 
-def run_frames(ref, wl, clip, n_frames, record_iters=False, n_ee=None, **opt):
-    drag = init_drag(ref, wl["latent0"][clip])
+def run_frames(ref, wl, clip, n_frames, record_iters=False, n_ee=None, extension_losses=False, gpos0=(0.0, 0.0, 0.0), **opt):
+    drag = init_drag(ref, wl["latent0"][clip], extension_losses, gpos0)
     rec = Recorder(drag) if record_iters else None
     poses, gposs, iters, traces, grots, tgt_lats = [], [], [], [], [], []
     offsets = ref.offsets
@@ -386,6 +386,71 @@ def _reference_result_and_metrics(ref, results_pose, results_gpos, gt_dir, gt_na
     return mpjpe, mpeepe, text
 
 
+def golden_extension_losses(ref, pm):
+    """the reference loop with its commented-out "Additional Losses" block (drag_pose.py:129-183) re-enabled by
+    oracle/reference_harness.load_drag_pose_with_extension_losses: 3 clips x 3 frames x 30 fixed iterations, 6 trackers, start root
+    at (0.3, 0.9, -0.2) so that the feet-floor term sees a plausible height; per-iteration latents, gradients and the four loss values."""
+    cfg = synthetic.config_6_trackers()
+    n_clips, n_frames, iters = 3, 3, 30
+    gpos0 = (0.3, 0.9, -0.2)
+    wl = synthetic.make_workload(pm, ref.offsets_np.astype(np.float32), cfg, n_clips, n_frames, first_clip=40)
+    fixed = dict(stop_eps_pos=-1.0, stop_eps_rot=-1.0, max_iter=iters, min_loss_incr=-float("inf"), learning_rate=1e-2)
+    out = dict(latent0=wl["latent0"], tgt_pos=wl["tgt_pos"], tgt_rot=wl["tgt_rot"], joints=wl["joints"], weights=wl["weights"],
+               gpos0=np.asarray(gpos0, np.float32))
+    P, G, L, GR, LS, LE, FR, FT, FG = [], [], [], [], [], [], [], [], []
+    for c in range(n_clips):
+        drag = init_drag(ref, wl["latent0"][c], True, gpos0)
+        rec = Recorder(drag)
+        poses, gposs, lat, grad, loss, le, grots, tls, gps = [], [], [], [], [], [], [], [], []
+        for t in range(n_frames):
+            grots.append(drag.current_global_rot.detach().numpy()[0].copy())
+            gps.append(drag.current_global_pos.detach().numpy()[0, :, 0].copy())
+            pose, gpos = drag.run(torch.from_numpy(wl["tgt_pos"][t, c].copy()), torch.from_numpy(wl["tgt_rot"][t, c].copy()),
+                                  torch.from_numpy(np.asarray(wl["joints"])).long(), torch.from_numpy(wl["weights"].copy()), ref.offsets,
+                                  lambda_rot=1, lambda_temporal=wl["lambda_temporal"], temporal_future_window=wl["window"],
+                                  joint_adjustment_indices=wl["joint_adjustment"], joint_adjustment_weight=wl["joint_adjustment_weight"], **fixed)
+            tls.append(drag.target_latent_buffer[0].detach().numpy().copy())
+            rows = rec.take()
+            assert len(rows) == iters
+            poses.append(pose.detach().numpy().copy()), gposs.append(gpos.detach().numpy().copy())
+            lat.append(np.stack([r["latent"] for r in rows])), grad.append(np.stack([r["grad"] for r in rows]))
+            loss.append(np.array([[r["lp"], r["lr"], r["lt"]] for r in rows])), le.append(np.array([r["le"] for r in rows]))
+        P.append(np.stack(poses)), G.append(np.stack(gposs)), L.append(np.stack(lat)), GR.append(np.stack(grad)), LS.append(np.stack(loss))
+        LE.append(np.stack(le)), FR.append(np.stack(grots)), FT.append(np.stack(tls)), FG.append(np.stack(gps))
+    st = lambda x: np.stack(x, 1)  # (frames, clips, ...)
+    out.update(pose=st(P), gpos=st(G), latent=st(L), grad=st(GR), loss=st(LS), extra=st(LE), grot=st(FR), tgt_latent=st(FT), frame_gpos=st(FG))
+    print("extension losses: extra-loss range %.4g .. %.4g (tracker terms %.4g .. %.4g)" % (out["extra"].min(), out["extra"].max(),
+          out["loss"][..., :2].sum(-1).min(), out["loss"][..., :2].sum(-1).max()))
+    # Single evaluations (decode, loss, backward: drag_pose.py:309-343) at WILD states -- latent 1.5 N(0,I), random previous root
+    # rotation and position -- because the head / hips "forward" term only switches on when the two face more than ~37 degrees
+    # apart, which the optimisation trajectories above never reach.
+    g = torch.Generator().manual_seed(31)
+    n_wild = 32
+    zw = 1.5 * torch.randn(n_wild, 24, generator=g)
+    gq = torch.randn(n_wild, 4, generator=g)
+    gq = gq / gq.norm(dim=1, keepdim=True)
+    gp = torch.randn(n_wild, 3, generator=g) * torch.tensor([0.5, 0.3, 0.5]) + torch.tensor([0.0, 0.9, 0.0])
+    tl = 0.3 * torch.randn(n_wild, 24, generator=g)
+    drag = init_drag(ref, wl["latent0"][0], True, gpos0)
+    mask = torch.from_numpy(np.asarray(wl["joints"])).long()
+    wts = torch.from_numpy(wl["weights"].copy())
+    W_grad, W_loss, W_extra = [], [], []
+    for i in range(n_wild):
+        drag.latent = zw[i : i + 1].clone().requires_grad_()
+        drag.current_global_rot = gq[i : i + 1].clone()
+        drag.current_global_pos = gp[i].reshape(1, 3, 1).clone()
+        pose, disp = drag.decoder(drag.latent, drag.data.mean_dqs, drag.data.std_dqs)
+        res = drag.loss(pose, disp, torch.from_numpy(wl["tgt_pos"][0, i % n_clips].copy()), torch.from_numpy(wl["tgt_rot"][0, i % n_clips].copy()),
+                        tl[i], ref.offsets, mask, wts, 1, 0.02)
+        (res[0] + res[1] + res[2] + res[3]).backward()
+        W_grad.append(drag.latent.grad.numpy()[0].copy())
+        W_loss.append([float(res[0]), float(res[1]), float(res[2])])
+        W_extra.append(float(res[3]))
+    out.update(wild_latent=zw.numpy(), wild_grot=gq.numpy(), wild_gpos=gp.numpy(), wild_tgt_latent=tl.numpy(), wild_clip=np.arange(n_wild) % n_clips,
+               wild_grad=np.stack(W_grad), wild_loss=np.asarray(W_loss), wild_extra=np.asarray(W_extra))
+    np.savez_compressed(os.path.join(OUT, "ref_extension_losses.npz"), **out)
+
+
 def golden_encoder(ref, n=48):
     """Encoder.forward (autoencoder.py:136-143) of the shipped generator on real frames: every 100th frame of example.bvh,
     standardised dual quaternions exactly as eval_drag feeds them (TestMotionData), -> mu, logvar; plus one seeded
@@ -454,7 +519,7 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     ref = build()
     pm = save_model_fixture(ref)
-    which = sys.argv[1:] or ["trace", "frames3", "temporal", "rundrag", "evalbvh", "encoder", "resultpath"]
+    which = sys.argv[1:] or ["trace", "frames3", "temporal", "rundrag", "evalbvh", "encoder", "resultpath", "extlosses"]
     if "trace" in which:
         golden_iter_traces(ref, pm)
     if "frames3" in which:
@@ -467,6 +532,8 @@ if __name__ == "__main__":
         golden_eval_bvh(ref)
     if "encoder" in which:
         golden_encoder(ref)
+    if "extlosses" in which:
+        golden_extension_losses(ref, pm)
     if "resultpath" in which:
         golden_result_path(ref)
     if "evalfull" in which:  # not in the default list: ~6 minutes

@@ -33,6 +33,34 @@ def activate():
             sys.path.insert(0, p)
 
 
+def load_drag_pose_with_extension_losses():
+    """The reference's `DragPose` with the commented-out "Additional Losses" block of drag_pose.py:129-183 (feet-floor, head-hips
+    forward, head-hips colinear, hips-feet colinear -- the documented constraints-as-losses extension point) re-enabled: the source
+    text is read from the reference tree, the comment markers of exactly that block are stripped, `additional_losses = 0` is dropped
+    and the result is exec'd into a fresh module.  Nothing is written to disk and no reference source enters this repository."""
+    activate()
+    import types
+
+    with open(os.path.join(REFERENCE_SRC, "drag_pose.py"), "r") as fh:
+        lines = fh.read().split("\n")
+    a = next(i for i, l in enumerate(lines) if l.strip().startswith("# Additional Losses"))
+    b = next(i for i, l in enumerate(lines) if l.strip() == "additional_losses = 0")
+    out = lines[: a + 1]
+    for l in lines[a + 1 : b]:
+        ind = len(l) - len(l.lstrip())
+        body = l.lstrip()
+        if body.startswith("# "):
+            body = body[2:]
+        elif body == "#":
+            body = ""
+        out.append(" " * ind + body)
+    out += lines[b + 1 :]
+    mod = types.ModuleType("drag_pose_extension_losses")
+    mod.__file__ = os.path.join(REFERENCE_SRC, "drag_pose.py")
+    exec(compile("\n".join(out), mod.__file__ + " [extension losses enabled]", "exec"), mod.__dict__)
+    return mod.DragPose
+
+
 class Reference:
     """Builds the reference objects exactly like eval_drag.main / RunDrag do
     (eval_drag.py:21-59, run_drag.py:16-59) with the two documented deviations
@@ -75,8 +103,11 @@ class Reference:
         self.stds_latent = torch.ones(24)
         self.offsets = torch.tensor(self.offsets_np, dtype=torch.float32)
 
-    def new_drag(self):
-        from drag_pose import DragPose
+    def new_drag(self, extension_losses=False):
+        if extension_losses:
+            DragPose = load_drag_pose_with_extension_losses()
+        else:
+            from drag_pose import DragPose
 
         return DragPose(self.generator, self.temporal, self.means_latent, self.stds_latent, "cpu", "cpu")
 
