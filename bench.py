@@ -6,9 +6,11 @@ A "step" is one frame of the hot path for every clip of the batch: temporal-pred
 target (window 0 => every frame) + 100 x {decode, FK, tracker loss, adjoint, decoder
 backward, latent Adam} + frame epilogue.  `value` has the tracker streams resident in
 HBM; `e2e` goes through the host-buffer API (H2D of the step's targets and D2H of the
-poses inside the timed region).  `--impl reference` times the CPU oracle port of the
-reference loop (the reference is Python and cannot travel to the GPU box) on all host
-cores.  One JSON line on stdout (rank 0).
+poses inside the timed region).  At N = 1 the same line also carries BASELINE config 3
+(`configs["3trk_var_4096"]`: head + hands, variable tracker mask, window 16) and the
+B = 1 latency of the DragPoserDLL C ABI (`latency`).  `--impl reference` times the CPU
+oracle port of the reference loop (the reference is Python and cannot travel to the GPU
+box) on all host cores.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -28,7 +30,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "model_dancedb.npz")
 FLOP_PER_CLIP_ITER = 35520.0      # decoder fwd + bwd-data GEMMs, folded 24->40->60->92
 HBM_BYTES_PER_CLIP_FRAME = 1300.0  # algorithmic state + tracker + result bytes
 MAX_ITER = 100
-
+# Per-core speed of the oracle port relative to the UNMODIFIED reference loop, measured in the build container (the reference
+# tree does not travel to the GPU box): scripts/port_vs_reference.py, 1 clip x 3 frames x 100 fixed iterations, one thread.
+PORT_VS_REFERENCE_PER_CORE = {"ratio": 1.44, "port_frames_per_s": 4.15, "reference_frames_per_s": 2.89,
+                              "how": "scripts/port_vs_reference.py in the build container (8-vCPU Xeon, torch 2.11 CPU), one thread, "
+                                     "same clip and targets; the port is the faster of the two, so GPU / port ratios understate GPU / reference"}
 
 KERNEL_NAMES = {
     1: "dp_frame_simt_kernel (persistent per-frame loop; fp32 CUDA-core decoder)",
@@ -36,7 +42,7 @@ KERNEL_NAMES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture whose
 # summary is committed under profiles/ (keyed by decoder path, clips per GPU, tracker config); null for other configurations
-NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 2955008}
+NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 4230656}
 
 
 def fixed_opts(cfg):
@@ -120,14 +126,71 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def cpu_reference(n_warm, n_timed, tracker_cfg, cores=None):
+    """All host cores, one clip per core; returns (clip-frames/s, cores, sample text)."""
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(i, n_warm, n_timed, tracker_cfg) for i in range(cores)])
+    value = cores * n_timed / max(times)
+    sample = (f"{cores} clips x {n_timed} frames (one single-threaded process per core, B=1 like the reference), "
+              f"{MAX_ITER} fixed iterations, {tracker_cfg} trackers, predictor every frame, after {n_warm} warm-up frames")
+    return value, cores, sample
+
+
 # ----------------------------------------------------------------------------- single-frame latency (second half of the metric)
 LAT_POS = (-2.6648, 0.9977, 3.7518)
 LAT_ROT = (0.6381, 0.0078, -0.7698, 0.0110)
 
 
+def quat_from_matrix(m):
+    """(…,3,3) rotation matrices -> (…,4) wxyz quaternions (largest-component selection)."""
+    m = np.asarray(m, np.float64)
+    out = np.empty(m.shape[:-2] + (4,), np.float64)
+    flat_m, flat_o = m.reshape(-1, 3, 3), out.reshape(-1, 4)
+    for i, r in enumerate(flat_m):
+        tr = r[0, 0] + r[1, 1] + r[2, 2]
+        if tr > 0:
+            s = 2.0 * np.sqrt(1.0 + tr)
+            q = (0.25 * s, (r[2, 1] - r[1, 2]) / s, (r[0, 2] - r[2, 0]) / s, (r[1, 0] - r[0, 1]) / s)
+        elif r[0, 0] > r[1, 1] and r[0, 0] > r[2, 2]:
+            s = 2.0 * np.sqrt(1.0 + r[0, 0] - r[1, 1] - r[2, 2])
+            q = ((r[2, 1] - r[1, 2]) / s, 0.25 * s, (r[0, 1] + r[1, 0]) / s, (r[0, 2] + r[2, 0]) / s)
+        elif r[1, 1] > r[2, 2]:
+            s = 2.0 * np.sqrt(1.0 + r[1, 1] - r[0, 0] - r[2, 2])
+            q = ((r[0, 2] - r[2, 0]) / s, (r[0, 1] + r[1, 0]) / s, 0.25 * s, (r[1, 2] + r[2, 1]) / s)
+        else:
+            s = 2.0 * np.sqrt(1.0 + r[2, 2] - r[0, 0] - r[1, 1])
+            q = ((r[1, 0] - r[0, 1]) / s, (r[0, 2] + r[2, 0]) / s, (r[1, 2] + r[2, 1]) / s, 0.25 * s)
+        flat_o[i] = q
+    return out.astype(np.float32)
+
+
+def latency_stream(n_frames):
+    """The moving target stream both latency arms replay: clip 0 of the synthetic 6-tracker workload (latent random walk, SURVEY
+    8d), tracker positions relative to the root and tracker rotations (matrices for the port, quaternions for the C ABI)."""
+    from dragposer_b200 import model, synthetic
+
+    cfg = synthetic.config_6_trackers()
+    pm = model.load_folded_npz(GOLDEN)
+    npz = np.load(GOLDEN)
+    wl = synthetic.make_workload(pm, npz["offsets"], cfg, 1, n_frames)
+    return wl, quat_from_matrix(wl["tgt_rot"][:, 0])
+
+
+def _stats(ms):
+    t = np.sort(np.asarray(ms))
+    pick = lambda q: float(t[min(len(t) - 1, int(len(t) * q))])
+    return {"p50_ms": pick(0.5), "p90_ms": pick(0.9), "p99_ms": pick(0.99), "max_ms": float(t[-1]), "mean_ms": float(t.mean()), "calls": int(len(t))}
+
+
 def dll_latency(calls=1000):
-    """p50 / p90 wall-clock of drag_pose through the DragPoserDLL C ABI, B = 1, host buffers in and out:
-    Unity parameters (MaxIter 5 / 10, lr 0.01, window 16) and the offline 100 iterations; targets of DragPoserDLL/main.cpp."""
+    """Wall-clock of drag_pose through the DragPoserDLL C ABI, B = 1, host buffers in and out, on the moving synthetic
+    stream: the Unity settings (MaxIter 5 / 10, lr 0.01, window 16, the reference session's stop thresholds), the offline budget
+    (MaxIter 100 with those thresholds) and a FIXED 100 iterations (thresholds and min_loss_incr off).  Frames on which the
+    temporal predictor runs (every 16th) are reported separately from the others; `all` mixes them as a session sees them."""
     import ctypes as C
     import tempfile
 
@@ -155,12 +218,19 @@ def dll_latency(calls=1000):
     lib.drag_pose.argtypes = [V, C.c_int, C.POINTER(F3), C.POINTER(Q4), C.POINTER(Q4), C.POINTER(F3)]
     lib.destroy_drag_poser.argtypes = [V]
     lib.dp_last_status.argtypes = [V]
+    lib.dp_get_last_iterations.argtypes = [V]
+    lib.dp_set_min_loss_increment.argtypes = [V, C.c_double]
     g = np.load(os.path.join(ROOT, "tests", "golden", "ref_rundrag.npz"))
-    out = {"boundary": "DragPoserDLL C ABI drag_pose, B = 1, 6 trackers, host buffers in/out, window 16", "calls": calls,
-           "early_stop": "stopEpsPos 1e-4, stopEpsRot 1e-2 as in the reference session (the loop ends at MaxIter or at the thresholds)"}
+    window = 16
+    n_fixed = max(160, calls // 4)
+    wl, quats = latency_stream(calls + 24)
+    out = {"boundary": "DragPoserDLL C ABI drag_pose, B = 1, 6 trackers, host buffers in/out, window 16",
+           "stream": "clip 0 of the synthetic 6-tracker workload (latent random walk), one new target set per call"}
+    settings = (("max_iter_5", 5, False, calls), ("max_iter_10", 10, False, calls), ("max_iter_100", 100, False, max(200, calls // 2)),
+                ("fixed_100_iterations", 100, True, n_fixed))
     with tempfile.TemporaryDirectory() as d:
         export_model.export(GOLDEN, os.path.join(d, "model.dpm"), allow_random_temporal=True)
-        for max_iter in (5, 10, 100):
+        for name, max_iter, fixed, n in settings:
             h = lib.init_drag_poser()
             lib.set_reference_skeleton(h, os.path.join(ROOT, "tests", "golden", "skeleton22.bvh").encode())
             lib.load_models(h, d.encode())
@@ -169,71 +239,61 @@ def dll_latency(calls=1000):
             lib.init_drag_model(h, F3(*LAT_POS), Q4(*LAT_ROT))
             if lib.dp_last_status(h) != 0:
                 raise SystemExit("bench.py: DragPoserDLL session failed to start")
-            T = g["tgt_pos"].shape[0]
-            pos = [(F3 * 6)(*[F3(*p) for p in g["tgt_pos"][t].tolist()]) for t in range(T)]
-            rot = (Q4 * 6)(*[Q4(*q) for q in g["tgt_quat"].tolist()])
+            if fixed:
+                lib.dp_set_min_loss_increment(h, -float("inf"))
+            pos = [(F3 * 6)(*[F3(*p) for p in wl["tgt_pos"][t, 0].tolist()]) for t in range(n + 20)]
+            rot = [(Q4 * 6)(*[Q4(*q) for q in quats[t].tolist()]) for t in range(n + 20)]
             res, gp = (Q4 * 22)(), (F3 * 1)()
-            n = calls if max_iter < 100 else max(100, calls // 5)
-            times = []
+            times, iters = [], []
             for i in range(n + 20):  # the per-frame call sequence of DragPoser.cs:137-173
                 lib.set_mask_and_weights(h, mask, weights)
-                lib.set_optim_params(h, 0.01 * 0.01, 0.01, max_iter, 0.01)
-                lib.set_lambdas(h, 1, 0.02, 16)
+                if fixed:
+                    lib.set_optim_params(h, -1.0, -1.0, max_iter, 0.01)
+                else:
+                    lib.set_optim_params(h, 0.01 * 0.01, 0.01, max_iter, 0.01)
+                lib.set_lambdas(h, 1, 0.02, window)
                 t0 = time.perf_counter()
-                lib.drag_pose(h, 6, pos[i % T], rot, res, gp)
-                times.append(time.perf_counter() - t0)
+                lib.drag_pose(h, 6, pos[i], rot[i], res, gp)
+                times.append((time.perf_counter() - t0) * 1e3)
+                iters.append(lib.dp_get_last_iterations(h))
                 lib.set_global_pos(h, gp[0])
             lib.destroy_drag_poser(h)
-            t = np.sort(np.array(times[20:])) * 1e3
-            out[f"max_iter_{max_iter}"] = {"p50_ms": float(t[len(t) // 2]), "p90_ms": float(t[int(len(t) * 0.9)])}
-    out["p50_ms"] = out["max_iter_5"]["p50_ms"]
+            times, iters = np.array(times[20:]), np.array(iters[20:])
+            pred = (np.arange(20, n + 20) % window) == 0  # frames on which current_index == 0: the predictor runs (5 decoder passes)
+            out[name] = {"all": _stats(times), "predictor_frames": _stats(times[pred]), "other_frames": _stats(times[~pred]),
+                         "mean_iterations": float(iters.mean())}
+    out["p50_ms"] = out["max_iter_5"]["all"]["p50_ms"]
     return out
 
 
 def port_latency(calls=30):
-    """The reference arm of the latency metric: the oracle port's DragPose.run, B = 1, one core, same parameters."""
-    torch_threads = 1
+    """The reference arm of the latency metric: the oracle port's DragPose.run, B = 1, one core, same stream and parameters."""
     import torch
 
-    torch.set_num_threads(torch_threads)
+    torch.set_num_threads(1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dragposer_port as port
-    from dragposer_b200 import model, synthetic
+    from dragposer_b200 import model
 
-    cfg = synthetic.config_6_trackers()
-    pm = model.load_folded_npz(GOLDEN)
     npz = np.load(GOLDEN)
-    out = {"boundary": "oracle port of DragPose.run, B = 1, 6 trackers, one core, window 16", "calls": calls,
-           "early_stop": "stopEpsPos 1e-4, stopEpsRot 1e-2 (the loop ends at MaxIter or at the thresholds)"}
-    for max_iter in (5, 10):
-        wl = synthetic.make_workload(pm, npz["offsets"], cfg, 1, calls + 3)
+    wl, _ = latency_stream(calls + 3)
+    out = {"boundary": "oracle port of DragPose.run, B = 1, 6 trackers, one core, window 16",
+           "stream": "clip 0 of the synthetic 6-tracker workload (latent random walk), one new target set per call"}
+    for name, max_iter, fixed, n in (("max_iter_5", 5, False, calls), ("max_iter_10", 10, False, calls),
+                                     ("fixed_100_iterations", 100, True, max(6, calls // 5))):
         drag = port.PortDragPose(port.PortWeights(npz), model.random_temporal_state(2222))
         drag.set_initial_state(wl["latent0"], np.zeros((1, 3)), [[1.0, 0, 0, 0]], np.zeros((1, 6)))
         times = []
-        for t in range(calls + 3):
+        for t in range(n + 3):
             t0 = time.perf_counter()
-            drag.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], stop_eps_pos=1e-4, stop_eps_rot=1e-2, max_iter=max_iter,
-                     min_loss_incr=1e-5, learning_rate=1e-2, lambda_rot=1.0, lambda_temporal=0.02, temporal_future_window=16,
-                     joint_adjustment=None, joint_adjustment_weight=0.0)
-            times.append(time.perf_counter() - t0)
-        t = np.sort(np.array(times[3:])) * 1e3
-        out[f"max_iter_{max_iter}"] = {"p50_ms": float(t[len(t) // 2]), "p90_ms": float(t[int(len(t) * 0.9)])}
-    out["p50_ms"] = out["max_iter_5"]["p50_ms"]
+            drag.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], stop_eps_pos=-1.0 if fixed else 1e-4,
+                     stop_eps_rot=-1.0 if fixed else 1e-2, max_iter=max_iter, min_loss_incr=-float("inf") if fixed else 1e-5,
+                     learning_rate=1e-2, lambda_rot=1.0, lambda_temporal=0.02, temporal_future_window=16, joint_adjustment=None,
+                     joint_adjustment_weight=0.0)
+            times.append((time.perf_counter() - t0) * 1e3)
+        out[name] = {"all": _stats(times[3:])}
+    out["p50_ms"] = out["max_iter_5"]["all"]["p50_ms"]
     return out
-
-
-def cpu_reference(n_warm, n_timed, tracker_cfg, cores=None):
-    """All host cores, one clip per core; returns (clip-frames/s, cores, sample text)."""
-    import multiprocessing as mp
-
-    cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(i, n_warm, n_timed, tracker_cfg) for i in range(cores)])
-    value = cores * n_timed / max(times)
-    sample = (f"{cores} clips x {n_timed} frames (one single-threaded process per core, B=1 like the reference), "
-              f"{MAX_ITER} fixed iterations, {tracker_cfg} trackers, predictor every frame, after {n_warm} warm-up frames")
-    return value, cores, sample
 
 
 def run_reference(args):
@@ -243,12 +303,17 @@ def run_reference(args):
     cfg = get_config(args.trackers)
     n_warm, n_timed = max(1, min(args.warmup, 1)), max(1, min(args.steps, 8))
     value, cores, sample = cpu_reference(n_warm, n_timed, args.trackers)
+    config = workload_config(args, cfg, args.clips * args.gpus)
+    # what this arm actually ran: per-clip CPU cost does not depend on how many clips exist, so the bounded sample stands for the
+    # workload above -- but the sample is the sample
+    config["cpu_sample"] = {"clips": cores, "frames_per_clip": n_timed, "warmup_frames": n_warm, "processes": cores, "threads_per_process": 1}
     line = {
         "impl": "reference", "metric": "clip-frames/sec (fixed 100 opt iters)", "value": value, "unit": "clip-frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, args.clips * args.gpus),
-        "cpu_baseline": {"value": value, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "port_vs_unmodified_reference_per_core": PORT_VS_REFERENCE_PER_CORE},
         "e2e": {"value": value, "unit": "clip-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -257,21 +322,174 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, cfg, clips_total):
-    return {"workload": f"{args.trackers}-tracker synthetic streams (SURVEY 8d), model_dancedb weights, seed-2222 random-init predictor, "
-                        f"window {cfg.temporal_future_window}, fixed {MAX_ITER} iterations",
-            "clips_per_gpu": args.clips, "clips_total": clips_total, "trackers": int(args.trackers), "max_iter": MAX_ITER,
+def workload_config(args, cfg, clips_total, trackers=None):
+    trackers = trackers or args.trackers
+    return {"workload": f"{trackers}-tracker synthetic streams (SURVEY 8d){', variable tracker mask' if trackers == '3' else ''}, model_dancedb "
+                        f"weights, seed-2222 random-init predictor, window {cfg.temporal_future_window}, fixed {MAX_ITER} iterations",
+            "clips_per_gpu": args.clips, "clips_total": clips_total, "trackers": int(trackers), "max_iter": MAX_ITER,
             "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"clip-shard x{args.gpus}"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_ours(args):
+def measure(args, trackers, K, W, rank, world, dev, local, clocks=None):
+    """Device-timed and end-to-end throughput of one workload (tracker config) at args.clips clips per GPU; returns a dict."""
     import torch
     import torch.distributed as dist
 
     from dragposer_b200 import dist as dpdist
     from dragposer_b200 import model, synthetic
     from dragposer_b200.engine import BatchedDragPose, RunOptions
+
+    cfg = get_config(trackers)
+    pm = model.load_folded_npz(GOLDEN)
+    offsets = np.load(GOLDEN)["offsets"]
+    tm = model.temporal_from_state(model.random_temporal_state(2222))
+    B = args.clips
+    n_total = B * world
+    T = W + K
+    variable = trackers == "3"
+    wl = synthetic.make_workload(pm, offsets, cfg, B, T, first_clip=rank * B, variable_mask=variable)
+    eng = BatchedDragPose(pm, offsets, tm, B, device=local)
+    eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+    opts = RunOptions(decoder_path=args.decoder_path, **fixed_opts(cfg))
+    E = wl["tgt_pos"].shape[2]
+    d_tp = torch.from_numpy(wl["tgt_pos"]).to(dev)
+    d_tr = torch.from_numpy(wl["tgt_rot"]).to(dev)
+    if variable:
+        d_j, d_w = torch.from_numpy(wl["joints_tb"]).to(dev), torch.from_numpy(wl["weights_tb"]).to(dev)
+        d_ne = torch.from_numpy(wl["n_ee"]).to(dev)
+    else:
+        d_j = torch.from_numpy(wl["joints"].astype(np.int32)).to(dev)
+        d_w = torch.from_numpy(wl["weights"]).to(dev)
+        d_ne = None
+    # result rows of every frame in the wire layout [pose 88 | global_pos 3 | pad], written by the frame kernel itself
+    d_rows = torch.zeros((T, B, dpdist.ROW), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    work_stream = torch.cuda.Stream(device=dev)  # everything timed runs (and is timed) on this stream
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+
+    def step(t):
+        eng.run_frames_device(1, d_tp[t], d_tr[t], d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_rows[t], None,
+                              n_ee=d_ne[t] if variable else None, shared=not variable, ee_stride=E, stream=stream, options=opts)
+
+    # the only collective of the job: the K frames' result rows go to rank 0 in a few chunks, each gather running while the
+    # next chunk's frames are computed; only the last chunk's gather is exposed
+    n_chunks = min(4, K) if world > 1 else 0
+    bounds = [W + (K * i) // n_chunks for i in range(n_chunks + 1)] if n_chunks else []
+    recv = [torch.empty((world, bounds[i + 1] - bounds[i], B, dpdist.ROW), dtype=torch.float32, device=dev) if rank == 0 else None
+            for i in range(n_chunks)]
+    for t in range(W):
+        step(t)
+    if world > 1:  # warm the collective too (NCCL connects its channels on the first call of a shape)
+        for i in range(n_chunks):
+            _, h = dpdist.gather_packed(d_rows[bounds[i]:bounds[i + 1]], n_total, dst=0, out=recv[i], async_op=True)
+            h.wait()
+    if clocks is not None:
+        clocks.start()  # before the barrier: every rank must enter the timed region at the same moment
+    eng.set_profiling(True)
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    evs, handles, chunk = [], [], 0
+    for k in range(K):
+        flush.zero_()  # L2 flush between timed steps (outside the event pair)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(W + k)
+        b.record()
+        evs.append((a, b))
+        if n_chunks and W + k + 1 == bounds[chunk + 1]:
+            _, h = dpdist.gather_packed(d_rows[bounds[chunk]:bounds[chunk + 1]], n_total, dst=0, out=recv[chunk], async_op=True)
+            handles.append(h)
+            chunk += 1
+    if handles:  # what is left of the gathers once the last frame is done
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for h in handles:
+            h.wait()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    gather_tail_ms = evs[-1][0].elapsed_time(evs[-1][1]) if handles else 0.0
+    launches = eng.launch_count() - l0
+    ms_pred, ms_frame, nprof = eng.profile()
+    eng.set_profiling(False)
+    clk = clocks.stop() if clocks is not None else None
+    ms_by_rank, parts_by_rank = [ms / K], None
+    if world > 1:
+        dist.barrier()
+        every = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(every, torch.tensor([ms, ms_frame / max(nprof, 1), ms_pred / max(nprof, 1), gather_tail_ms], dtype=torch.float64, device=dev))
+        ms_by_rank = [float(t[0].item()) / K for t in every]
+        parts_by_rank = [[round(float(t[1].item()), 4), round(float(t[2].item()), 4), round(float(t[3].item()), 4)] for t in every]
+        ms = max(float(t[0].item()) for t in every)  # the job is as fast as its slowest rank
+    value = n_total * K / (ms * 1e-3)
+
+    # ---- e2e: HOST arrays through the public API (BatchedDragPose.run_frames), every frame's staging + H2D + D2H inside the
+    # timed region (the call double-buffers them against the kernels of the neighbouring frames); with several GPUs the SAME K
+    # frames then go to rank 0 through the same gather, from host memory and back to host memory
+    h_tp, h_tr = wl["tgt_pos"], wl["tgt_rot"]
+    host_out = (np.zeros((K, B, 88), np.float32), np.zeros((K, B, 3), np.float32))  # result arrays of the caller, reused
+    pinned = torch.zeros((K, B, dpdist.ROW), dtype=torch.float32).pin_memory() if world > 1 else None
+
+    def run_host(t0, t1):
+        out = host_out if t1 - t0 == K else None
+        if variable:
+            return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints_tb"][t0:t1], wl["weights_tb"][t0:t1], n_ee=wl["n_ee"][t0:t1],
+                                  out=out, options=opts)
+        return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints"], wl["weights"], out=out, options=opts)
+
+    run_host(0, min(W, 2))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    poses, gposes = run_host(W, W + K)
+    if world > 1:
+        pinned[:, :, :88] = torch.from_numpy(poses)
+        pinned[:, :, 88:91] = torch.from_numpy(gposes)
+        got, _ = dpdist.gather_packed(pinned.to(dev, non_blocking=True), n_total, dst=0)
+        if rank == 0:
+            got.buffer.cpu()
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    h2d = B * E * (3 + 9) * 4 + (B * E * (1 + 2) * 4 + B * 4 if variable else E * 12)
+    d2h = B * (88 + 3) * 4
+    path = eng.last_decoder_path()
+    eng.close()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    return dict(cfg=cfg, value=value, ms=ms, K=K, launches=launches, frame_ms=ms_frame / max(nprof, 1), pred_ms=ms_pred / max(nprof, 1), clk=clk,
+                ms_by_rank=ms_by_rank, parts_by_rank=parts_by_rank, e2e_value=n_total * K / e2e_s, h2d=h2d, d2h=d2h, path=path, n_total=n_total,
+                gather={"chunks": n_chunks, "to": "rank 0", "bytes_received_by_rank_0": int(max(world - 1, 0) * K * B * dpdist.ROW * 4)})
+
+
+def roofline(m, B, trackers, peaks):
+    # burst peak: the timed region is a few tens of milliseconds at full clock (each step is bracketed by its own events)
+    tf32_peak = (peaks.get("bf16_tflops") or 1632.8) / 2.0
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+    which = "measured bf16 burst / 2 = TF32 (MEASURED_PEAKS.json)" if peaks else "fallback (no MEASURED_PEAKS.json)"
+    achieved_tf = B * MAX_ITER * FLOP_PER_CLIP_ITER / (m["frame_ms"] * 1e-3) / 1e12
+    achieved_gbs = B * HBM_BYTES_PER_CLIP_FRAME / (m["frame_ms"] * 1e-3) / 1e9
+    return {"bound": "tensor", "kernel": KERNEL_NAMES[m["path"]], "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / tf32_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((m["path"], B, trackers)), "peak_source": which,
+            "kernel_ms_per_launch": m["frame_ms"], "predictor_ms_per_step": m["pred_ms"],
+            "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
+            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 7.76, "tp_ff_tc_kernel": 44.2,
+                                            "source": "profiles/r2_frame_kernel.md: sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32, issued ops"},
+            "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -283,152 +501,46 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = get_config(args.trackers)
-    pm = model.load_folded_npz(GOLDEN)
-    offsets = np.load(GOLDEN)["offsets"]
-    tm = model.temporal_from_state(model.random_temporal_state(2222))
-    B, K, W = args.clips, args.steps, args.warmup
-    n_total = B * world
-    T = W + K
-    wl = synthetic.make_workload(pm, offsets, cfg, B, T, first_clip=rank * B, variable_mask=(args.trackers == "3"))
-    eng = BatchedDragPose(pm, offsets, tm, B, device=local)
-    eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
-    opts = RunOptions(decoder_path=args.decoder_path, **fixed_opts(cfg))
-    E = wl["tgt_pos"].shape[2]
-    variable = "n_ee" in wl
-    d_tp = torch.from_numpy(wl["tgt_pos"]).to(dev)
-    d_tr = torch.from_numpy(wl["tgt_rot"]).to(dev)
-    if variable:
-        d_j, d_w = torch.from_numpy(wl["joints_tb"]).to(dev), torch.from_numpy(wl["weights_tb"]).to(dev)
-        d_ne = torch.from_numpy(wl["n_ee"]).to(dev)
-    else:
-        d_j = torch.from_numpy(wl["joints"].astype(np.int32)).to(dev)
-        d_w = torch.from_numpy(wl["weights"]).to(dev)
-        d_ne = None
-    d_pose = torch.empty((T, B, 88), dtype=torch.float32, device=dev)
-    d_gpos = torch.empty((T, B, 3), dtype=torch.float32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    work_stream = torch.cuda.Stream(device=dev)  # everything timed runs (and is timed) on this stream
-    torch.cuda.set_stream(work_stream)
-    stream = work_stream.cuda_stream
-
-    def step(t):
-        eng.run_frames_device(1, d_tp[t], d_tr[t], d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_pose[t], d_gpos[t],
-                              n_ee=d_ne[t] if variable else None, shared=not variable, ee_stride=E, stream=stream, options=opts)
-
-    for t in range(W):
-        step(t)
-    if world > 1:  # warm the collective too (NCCL connects its channels on the first call of a shape)
-        dpdist.gather_frames(d_pose[W:W + K], d_gpos[W:W + K], n_total)
-    clocks = ClockSampler(local, world)
+    K, W = args.steps, args.warmup
+    clocks = ClockSampler(local, world) if rank == 0 else None
+    m = measure(args, args.trackers, K, W, rank, world, dev, local, clocks)
+    line, peaks = None, {}
     if rank == 0:
-        clocks.start()  # before the barrier: every rank must enter the timed region at the same moment
-    eng.set_profiling(True)
-    l0 = eng.launch_count()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    evs = []
-    for k in range(K):
-        flush.zero_()  # L2 flush between timed steps (outside the event pair)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step(W + k)
-        b.record()
-        evs.append((a, b))
-    if world > 1:  # the only collective of the job: ONE gather of the K frames' result rows, in rank order, inside the timed region
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        dpdist.gather_frames(d_pose[W:W + K], d_gpos[W:W + K], n_total)
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    launches = eng.launch_count() - l0
-    ms_pred, ms_frame, nprof = eng.profile()
-    eng.set_profiling(False)
-    clk = clocks.stop() if rank == 0 else None
-    ms_by_rank, parts_by_rank = [ms / K], None
-    if world > 1:
-        dist.barrier()
-        every = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(every, torch.tensor([ms, ms_frame / max(nprof, 1), ms_pred / max(nprof, 1)], dtype=torch.float64, device=dev))
-        ms_by_rank = [float(t[0].item()) / K for t in every]
-        parts_by_rank = [[round(float(t[1].item()), 4), round(float(t[2].item()), 4)] for t in every]
-        ms = max(float(t[0].item()) for t in every)  # the job is as fast as its slowest rank
-    value = n_total * K / (ms * 1e-3)
-
-    # ---- e2e: HOST arrays through the public API (BatchedDragPose.run_frames), every frame's staging + H2D + D2H inside the
-    # timed region; the call double-buffers them so they overlap the kernels of the neighbouring frames
-    h_tp, h_tr = wl["tgt_pos"], wl["tgt_rot"]
-    run_kw = dict(options=opts)
-
-    host_out = (np.zeros((K, B, 88), np.float32), np.zeros((K, B, 3), np.float32))  # result arrays of the caller, reused
-
-    def run_host(t0, t1):
-        out = host_out if t1 - t0 == K else None
-        if variable:
-            return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints_tb"][t0:t1], wl["weights_tb"][t0:t1], n_ee=wl["n_ee"][t0:t1],
-                                  out=out, **run_kw)
-        return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints"], wl["weights"], out=out, **run_kw)
-
-    run_host(0, min(W, 2))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    poses, gposes = run_host(W, W + K)
-    last = (poses[-1], gposes[-1])
-    if world > 1:  # gather of the last frame's poses across the ranks (NCCL)
-        dpdist.gather_results(torch.from_numpy(last[0]).to(dev), torch.from_numpy(last[1]).to(dev), n_total)
-        torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    e2e_value = n_total * K / e2e_s
-    h2d = B * E * (3 + 9) * 4 + (B * E * (1 + 2) * 4 + B * 4 if variable else E * 12)
-    d2h = B * (88 + 3) * 4
-
-    if rank == 0:
-        peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
                 peaks = json.load(fh)
         except Exception:
             pass
-        tf32_peak = (peaks.get("bf16_tflops_sustained") or 1400.0) / 2.0
-        hbm_peak = peaks.get("hbm_gbs") or 6650.0
-        which = "of measured (bf16 sustained / 2 = TF32)" if peaks else "of fallback"
-        frame_ms = ms_frame / max(nprof, 1)
-        achieved_tf = B * MAX_ITER * FLOP_PER_CLIP_ITER / (frame_ms * 1e-3) / 1e12
-        achieved_gbs = B * HBM_BYTES_PER_CLIP_FRAME / (frame_ms * 1e-3) / 1e9
         line = {
-            "metric": "clip-frames/sec (fixed 100 opt iters)", "value": value, "unit": "clip-frames/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, cfg, n_total),
-            "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[eng.last_decoder_path()],
-                         "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf32_peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((eng.last_decoder_path(), B, args.trackers)), "peak_source": which, "kernel_ms_per_launch": frame_ms,
-                         "predictor_ms_per_step": ms_pred / max(nprof, 1),
-                         "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
-                         "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"},
-            "e2e": {"value": e2e_value, "unit": "clip-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clk,
+            "metric": "clip-frames/sec (fixed 100 opt iters)", "value": m["value"], "unit": "clip-frames/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": m["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, m["cfg"], m["n_total"]),
+            "roofline": roofline(m, args.clips, args.trackers, peaks),
+            "e2e": {"value": m["e2e_value"], "unit": "clip-frames/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches": m["launches"], "clocks": m["clk"],
         }
         if world > 1:
-            line["ms_per_step_by_rank"] = [round(v, 4) for v in ms_by_rank]
-            line["frame_kernel_and_predictor_ms_by_rank"] = parts_by_rank
+            line["ms_per_step_by_rank"] = [round(v, 4) for v in m["ms_by_rank"]]
+            line["frame_kernel_predictor_gather_tail_ms_by_rank"] = m["parts_by_rank"]
+            line["gather"] = m["gather"]
+    if world == 1 and not args.no_config3 and args.trackers == "6":
+        # BASELINE config 3 in the same record: head + hands with the hands dropping out, window 16 (the predictor runs on every 16th
+        # frame with five decoder passes), 4096 clips; at least 32 frames so that two predictor frames fall into the timed region
+        k3 = max(K, 32)
+        m3 = measure(args, "3", k3, W, rank, world, dev, local)
+        line["configs"] = {("3trk_var_4096" if args.clips == 4096 else f"3trk_var_{args.clips}"): {
+            "value": m3["value"], "unit": "clip-frames/s", "steps": k3, "ms_per_step": m3["ms"] / k3,
+            "config": workload_config(args, m3["cfg"], m3["n_total"], "3"), "roofline": roofline(m3, args.clips, "3", peaks),
+            "e2e": {"value": m3["e2e_value"], "unit": "clip-frames/s", "h2d_bytes_per_step": m3["h2d"], "d2h_bytes_per_step": m3["d2h"]},
+            "gpu_launches": m3["launches"]}}
+    if rank == 0:
         if world == 1 and not args.no_latency:
-            eng.close()  # the DLL session opens its own engine
             line["latency"] = dll_latency()
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_reference(1, 6, args.trackers)
-            line["cpu_baseline"] = {"value": v, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": "clip-frames/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "port_vs_unmodified_reference_per_core": PORT_VS_REFERENCE_PER_CORE}
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -443,6 +555,7 @@ def main():
     ap.add_argument("--trackers", default="6", choices=["6", "3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the B = 1 C-ABI latency measurement")
+    ap.add_argument("--no-config3", action="store_true", help="skip the second workload (BASELINE config 3) at N = 1")
     ap.add_argument("--decoder-path", type=int, default=0, choices=[0, 1, 3], help="0 auto, 1 fp32 CUDA-core decoder, 3 tcgen05 fp16x2")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

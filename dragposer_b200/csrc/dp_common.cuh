@@ -118,8 +118,9 @@ struct DpFrameArgs {
   float adj_w;
   const float* adam_tab;  // [2][max_iter]: lr/(1-b1^k), sqrt(1-b2^k), k = 1..max_iter
   // outputs
-  float* out_pose;    // (B,88)
+  float* out_pose;    // (B,88), or the packed rows (B,92) = [pose 88 | global_pos 3 | pad] with out_gpos = out_pose + 88
   float* out_gpos;    // (B,3)
+  int out_pose_stride, out_gpos_stride;  // floats per clip: 88 / 3, or 92 / 92 for packed rows
   int32_t* out_iters; // (B)
   float* out_losses;  // (B,3)
   float* trace;       // (B,trace_iters,52) or null

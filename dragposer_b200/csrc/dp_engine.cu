@@ -467,7 +467,9 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.lambda_rot = p->lambda_rot; a.lambda_t = p->lambda_temporal;
   a.adj_joint = p->joint_adjust_joint; a.adj_slot = p->joint_adjust_slot; a.adj_w = p->joint_adjust_weight;
   a.adam_tab = e->d_adam;
-  a.out_pose = out_pose; a.out_gpos = out_gpos; a.out_iters = e->d_iters; a.out_losses = e->d_losses;
+  a.out_pose = out_pose; a.out_iters = e->d_iters; a.out_losses = e->d_losses;
+  if (out_gpos) { a.out_gpos = out_gpos; a.out_pose_stride = DP_POSE; a.out_gpos_stride = 3; }
+  else { a.out_gpos = out_pose + DP_POSE; a.out_pose_stride = a.out_gpos_stride = DP_ROW; }  // packed wire rows
   a.trace = e->trace_enabled ? e->d_trace : nullptr;
   a.trace_iters = e->trace_iters;
   a.phase_cycles = e->profiling >= 2 ? e->d_phase : nullptr;
@@ -493,7 +495,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
 extern "C" int dp_engine_run_frames_device(dp_engine* e, const dp_run_params* p, int n_frames, const int32_t* n_ee,
                                            const int32_t* joints, const float* weights, int shared, const float* tgt_pos,
                                            const float* tgt_rot, int ee_stride, float* out_pose, float* out_gpos, void* stream) {
-  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || !out_gpos || n_frames < 1)
+  if (!e || !p || !joints || !weights || !tgt_pos || !tgt_rot || !out_pose || n_frames < 1)
     return fail(DP_ERR_ARG, "dp_engine_run_frames_device: null argument");
   int rc = check_params(e, p, ee_stride);
   if (rc) return rc;
@@ -505,7 +507,7 @@ extern "C" int dp_engine_run_frames_device(dp_engine* e, const dp_run_params* p,
   for (int f = 0; f < n_frames; ++f) {
     rc = run_one(e, p, n_ee ? n_ee + f * B : nullptr, shared ? joints : joints + f * B * S,
                  shared ? weights : weights + f * B * S * 2, shared, tgt_pos + f * B * S * 3, tgt_rot + f * B * S * 9,
-                 ee_stride, out_pose + f * B * DP_POSE, out_gpos + f * B * 3, st);
+                 ee_stride, out_pose + f * B * (out_gpos ? DP_POSE : DP_ROW), out_gpos ? out_gpos + f * B * 3 : nullptr, st);
     if (rc) return rc;
   }
   return DP_OK;

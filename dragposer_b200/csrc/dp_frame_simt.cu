@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(512, 1) dp_frame_simt_kernel(const __grid_cons
       for (int i = 0; i < 3; ++i) {
         A.disp_buf[((size_t)clip * DP_PAST + A.ring_head) * 3 + i] = d[i] + adj[i];
         A.gpos[clip * 3 + i] = gp[i];
-        A.out_gpos[clip * 3 + i] = gp[i];
+        A.out_gpos[(size_t)clip * A.out_gpos_stride + i] = gp[i];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) A.grot[clip * 4 + i] = r[i];
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) dp_frame_simt_kernel(const __grid_cons
       const float4 mq = reinterpret_cast<const float4*>(M.mean_q)[lane];
       const float4 sq = reinterpret_cast<const float4*>(M.std_q)[lane];
       const float* s = (lane == 0) ? r : q;
-      reinterpret_cast<float4*>(A.out_pose + (size_t)clip * 88)[lane] =
+      reinterpret_cast<float4*>(A.out_pose + (size_t)clip * A.out_pose_stride)[lane] =
           make_float4((s[0] - mq.x) / sq.x, (s[1] - mq.y) / sq.y, (s[2] - mq.z) / sq.z, (s[3] - mq.w) / sq.w);
     }
   }

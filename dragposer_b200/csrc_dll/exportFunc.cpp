@@ -397,6 +397,14 @@ DP_EXPORT void destroy_drag_poser(DragPoser* d) {
 DP_EXPORT int dp_last_status(const DragPoser* d) { return d ? d->status : -1; }
 DP_EXPORT const char* dp_last_message(const DragPoser* d) { return d ? d->message.c_str() : "null session"; }
 DP_EXPORT int dp_get_num_joints(const DragPoser* d) { return d ? d->num_joints : 0; }
+DP_EXPORT int dp_get_last_iterations(DragPoser* d) {
+  int32_t it = -1;
+  if (!d || !d->have_session || dp_engine_get_frame_stats(d->engine, &it, nullptr) != DP_OK) return -1;
+  return it;
+}
+DP_EXPORT void dp_set_min_loss_increment(DragPoser* d, double v) {
+  if (d) d->params.min_loss_incr = v;
+}
 DP_EXPORT int dp_get_num_endeffectors(const DragPoser* d) { return d ? d->num_ee : 0; }
 DP_EXPORT void dp_set_initial_latent(DragPoser* d, const float* latent24) {
   if (!d || !latent24) return;

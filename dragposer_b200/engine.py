@@ -248,7 +248,8 @@ class BatchedDragPose:
     def run_frames_device(self, n_frames, tgt_pos, tgt_rot, joints, weights, out_pose, out_gpos, n_ee=None, shared=True,
                           ee_stride=None, stream=None, options: RunOptions = None):
         """DEVICE-resident torch tensors (float32 / int32, contiguous); enqueues
-        n_frames frames on `stream` (an int cudaStream_t or None) without synchronising."""
+        n_frames frames on `stream` (an int cudaStream_t or None) without synchronising.  out_gpos=None: out_pose is a packed
+        (n_frames, B, 92) tensor of result rows [pose 88 | global_pos 3 | pad] (the wire layout of dist.gather_frames)."""
         dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         E = int(ee_stride if ee_stride is not None else tgt_pos.shape[-2])
         _lib.check(self.lib.dp_engine_run_frames_device(

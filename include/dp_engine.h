@@ -36,6 +36,7 @@ extern "C" {
 #define DP_JOINTS 22
 #define DP_LATENT 24
 #define DP_POSE 88          /* 22 quaternions, standardised root-space */
+#define DP_ROW 92           /* packed result row: pose (88) | global_pos (3) | pad -- the wire format of the multi-GPU gather */
 #define DP_PAST_ROWS 60     /* train_temporal.param["future_frames"][0] */
 #define DP_HEIGHTS 6
 #define DP_MAX_WINDOW 116
@@ -144,7 +145,9 @@ int dp_engine_run_frames_host(dp_engine* e, const dp_run_params* p, int n_frames
 
 /* n_frames consecutive frames with device-resident inputs laid out frame-major
  * (frame stride = B*ee_stride*{1,2,3,9} elements; n_ee stride = B; joints/weights
- * follow the frame stride unless shared_trackers).  Outputs (n_frames,B,88)/(n_frames,B,3). */
+ * follow the frame stride unless shared_trackers).  Outputs (n_frames,B,88)/(n_frames,B,3); with out_global_pos == NULL the
+ * kernels write packed rows instead: out_pose is (n_frames,B,DP_ROW) = [pose | global_pos | pad], the layout
+ * dragposer_b200/dist.py gathers across GPUs without a repacking copy. */
 int dp_engine_run_frames_device(dp_engine* e, const dp_run_params* p, int n_frames, const int32_t* n_ee,
                                 const int32_t* joints, const float* weights, int shared_trackers,
                                 const float* tgt_pos, const float* tgt_rot, int ee_stride,

@@ -51,6 +51,9 @@ DP_EXPORT int dp_get_num_joints(const DragPoser* dragPoser);
 DP_EXPORT int dp_get_num_endeffectors(const DragPoser* dragPoser);
 DP_EXPORT void dp_set_initial_latent(DragPoser* dragPoser, const float* latent24);   /* overrides the encoder draw of init_drag_model */
 DP_EXPORT void dp_get_initial_latent(const DragPoser* dragPoser, float* latent24);
+DP_EXPORT int dp_get_last_iterations(DragPoser* dragPoser);          /* optimisation iterations the last drag_pose ran (-1 on error) */
+DP_EXPORT void dp_set_min_loss_increment(DragPoser* dragPoser, double minLossIncr);  /* DragPose.run's min_loss_incr (run_drag.py keeps the
+                                                                         default 1e-5 and the reference ABI has no setter); -inf disables */
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # prints the frame-kernel / predictor split of bench.py for a few settings passed as "ENV=VAL ..." strings
 for cfg in "$@"; do
-  out=$(env $cfg python bench.py --steps 20 --warmup 3 --no-latency --no-cpu-baseline ${BENCH_ARGS} 2>/dev/null)
+  out=$(env $cfg python bench.py --steps 20 --warmup 3 --no-latency --no-cpu-baseline --no-config3 ${BENCH_ARGS} 2>/dev/null)
   python - "$cfg" <<PY
 import json,sys
 d=json.loads('''$out''')

@@ -107,3 +107,30 @@ def test_streaming_latency_and_error_paths(dll):
     assert lib.dp_last_status(h) != 0
     assert np.array_equal(before, np.array([[r.w, r.x, r.y, r.z] for r in res]))
     lib.destroy_drag_poser(h)
+
+
+def test_two_engines_on_two_devices_in_one_process(pose_model, temporal_model, model_npz):
+    """the opt-in to > 48 KB of dynamic shared memory is per device; a second engine on another GPU of the same
+    process must run the large-shared-memory kernels too (tensor-core frame kernel, predictor) and give the same results."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dragposer_b200 import synthetic
+    from dragposer_b200.engine import BatchedDragPose
+
+    cfg = synthetic.config_6_trackers()
+    B = 600  # >= 512: tcgen05 frame kernel
+    wl = synthetic.make_workload(pose_model, model_npz["offsets"], cfg, B, 2)
+    outs = []
+    engines = [BatchedDragPose(pose_model, model_npz["offsets"], temporal_model, B, device=d) for d in (0, 1)]
+    for eng in engines:
+        eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+    for t in range(2):
+        outs = [eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], lambda_rot=1, lambda_temporal=cfg.lambda_temporal,
+                        temporal_future_window=0, max_iter=10, joint_adjustment_indices=cfg.joint_adjustment,
+                        joint_adjustment_weight=cfg.joint_adjustment_weight) for eng in engines]
+    assert engines[0].last_decoder_path() == 3 and engines[1].last_decoder_path() == 3
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for eng in engines:
+        eng.close()

@@ -142,14 +142,30 @@ gpos = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3) - 0.25
 P, G = dpdist.gather_results(pose, gpos, n)
 assert P.shape == (n, 88) and G.shape == (n, 3)
 assert torch.equal(P[:, 0], torch.arange(n, dtype=torch.float32) + 0.5) and torch.equal(G[:, 2], torch.arange(n, dtype=torch.float32) - 0.25)
-# a batch of frames in one collective: frame t, clip c carries 100 t + c
+# a batch of frames in one collective, to the rank that consumes them: frame t, clip c carries 100 t + c
 T = 3
 pf = pose[None] + 100.0 * torch.arange(T, dtype=torch.float32)[:, None, None]
 gf = gpos[None] + 100.0 * torch.arange(T, dtype=torch.float32)[:, None, None]
-PF, GF = dpdist.gather_frames(pf, gf, n)
-assert PF.shape == (T, n, 88) and GF.shape == (T, n, 3)
+got = dpdist.gather_frames(pf, gf, n, dst=0)
 want = 100.0 * torch.arange(T, dtype=torch.float32)[:, None] + torch.arange(n, dtype=torch.float32)[None]
-assert torch.equal(PF[:, :, 5], want + 0.5) and torch.equal(GF[:, :, 1], want - 0.25)
+if rank == 0:
+    for t in range(T):
+        assert got.pose(t).shape == (n, 88) and got.global_pos(t).shape == (n, 3)
+        assert torch.equal(got.pose(t)[:, 5], want[t] + 0.5) and torch.equal(got.global_pos(t)[:, 1], want[t] - 0.25)
+    assert torch.equal(got.clip(5)[:, 0], want[:, 5] + 0.5)  # one clip over the frames: a view into the receive buffer
+else:
+    assert got is None
+# the engine's own wire layout (packed rows as the frame kernels write them), asynchronously, into a preallocated buffer
+rows = torch.zeros((T, per, dpdist.ROW))
+rows[:, : hi - lo, :88] = pf
+rows[:, : hi - lo, 88:91] = gf
+out = torch.empty((world, T, per, dpdist.ROW)) if rank == 1 else None
+got, work = dpdist.gather_packed(rows, n, dst=1, out=out, async_op=True)
+work.wait()
+if rank == 1:
+    assert got.buffer is out and torch.equal(got.pose(2)[:, 7], want[2] + 0.5)
+else:
+    assert got is None
 dist.destroy_process_group()
 print('rank', rank, 'ok')
 """)
