@@ -429,12 +429,13 @@ def measure(args, trackers, K, W, rank, world, dev, local, clocks=None):
         ms = max(float(t[0].item()) for t in every)  # the job is as fast as its slowest rank
     value = n_total * K / (ms * 1e-3)
 
-    # ---- e2e: HOST arrays through the public API (BatchedDragPose.run_frames), every frame's staging + H2D + D2H inside the
-    # timed region (the call double-buffers them against the kernels of the neighbouring frames); with several GPUs the SAME K
-    # frames then go to rank 0 through the same gather, from host memory and back to host memory
+    # ---- e2e.  One GPU: HOST arrays through the public API (BatchedDragPose.run_frames), every frame's staging + H2D + D2H inside
+    # the timed region (the call double-buffers them against the kernels of the neighbouring frames).  Several GPUs: the consumer
+    # of the poses is rank 0's host memory, so every rank copies each step's targets from PINNED host memory to its GPU, runs the
+    # frame, and the SAME K frames go to rank 0 through the same chunked gather as above, each received chunk being copied to
+    # rank 0's pinned host memory while the next chunk is computed; the clock stops when the last row is in host memory.
     h_tp, h_tr = wl["tgt_pos"], wl["tgt_rot"]
     host_out = (np.zeros((K, B, 88), np.float32), np.zeros((K, B, 3), np.float32))  # result arrays of the caller, reused
-    pinned = torch.zeros((K, B, dpdist.ROW), dtype=torch.float32).pin_memory() if world > 1 else None
 
     def run_host(t0, t1):
         out = host_out if t1 - t0 == K else None
@@ -443,21 +444,43 @@ def measure(args, trackers, K, W, rank, world, dev, local, clocks=None):
                                   out=out, options=opts)
         return eng.run_frames(h_tp[t0:t1], h_tr[t0:t1], wl["joints"], wl["weights"], out=out, options=opts)
 
-    run_host(0, min(W, 2))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    poses, gposes = run_host(W, W + K)
-    if world > 1:
-        pinned[:, :, :88] = torch.from_numpy(poses)
-        pinned[:, :, 88:91] = torch.from_numpy(gposes)
-        got, _ = dpdist.gather_packed(pinned.to(dev, non_blocking=True), n_total, dst=0)
-        if rank == 0:
-            got.buffer.cpu()
+    if world == 1:
+        run_host(0, min(W, 2))
         torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
+        t0 = time.perf_counter()
+        run_host(W, W + K)
+        e2e_s = time.perf_counter() - t0
+    else:
+        p_tp, p_tr = torch.from_numpy(h_tp).pin_memory(), torch.from_numpy(h_tr).pin_memory()
+        s_tp, s_tr = torch.empty_like(d_tp[0]), torch.empty_like(d_tr[0])  # the step's inputs on the device
+        host_recv = [torch.empty(r.shape, dtype=torch.float32).pin_memory() if r is not None else None for r in recv]
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def step_from_host(t):
+            s_tp.copy_(p_tp[t], non_blocking=True)
+            s_tr.copy_(p_tr[t], non_blocking=True)
+            eng.run_frames_device(1, s_tp, s_tr, d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_rows[t], None,
+                                  n_ee=d_ne[t] if variable else None, shared=not variable, ee_stride=E, stream=stream, options=opts)
+
+        step_from_host(0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        chunk, handles = 0, []
+        for k in range(K):
+            step_from_host(W + k)
+            if W + k + 1 == bounds[chunk + 1]:
+                _, h = dpdist.gather_packed(d_rows[bounds[chunk]:bounds[chunk + 1]], n_total, dst=0, out=recv[chunk], async_op=True)
+                handles.append(h)
+                if rank == 0:
+                    with torch.cuda.stream(copy_stream):
+                        h.wait()  # only the copy stream waits for the collective
+                        host_recv[chunk].copy_(recv[chunk], non_blocking=True)
+                chunk += 1
+        for h in handles:
+            h.wait()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
