@@ -107,25 +107,24 @@ __global__ void __launch_bounds__(512, 1) dp_frame_simt_kernel(const __grid_cons
     }
     am[c] = av[c] = make_float2(0.f, 0.f);
     zlast[c] = z[c];
-    // tracker stream of the clip: lane e loads slot e (all slots in flight at once, neighbouring lanes read neighbouring
-    // addresses) and scatters its row to the lane of the joint it tracks; untracked joints keep zero weights
+    // tracker rows: lane j picks the slot that tracks joint j (joints are unique per clip)
     ClipTrackers row;
     row.pw = row.r0 = row.r1 = row.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    trk[c * 32 + lane] = row;
-    __syncwarp();
-    if (lane < ne) {
-      float origin[3] = {0.f, 0.f, 0.f};  // world-absolute targets are taken relative to the clip's current global position
-      if (A.targets_world) { origin[0] = A.gpos[cc * 3]; origin[1] = A.gpos[cc * 3 + 1]; origin[2] = A.gpos[cc * 3 + 2]; }
-      const int j = A.joints[(A.shared_trackers ? 0 : (size_t)cc * A.ee_stride) + lane];
-      const float2 wt = reinterpret_cast<const float2*>(A.weights + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride * 2))[lane];
-      const float* tp = A.tgt_pos + ((size_t)cc * A.ee_stride + lane) * 3;
-      const float* tr = A.tgt_rot + ((size_t)cc * A.ee_stride + lane) * 9;
-      row.pw = make_float4(tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt.x);
-      row.r0 = make_float4(tr[0], tr[1], tr[2], wt.y);
-      row.r1 = make_float4(tr[3], tr[4], tr[5], 0.f);
-      row.r2 = make_float4(tr[6], tr[7], tr[8], 0.f);
-      if (j >= 0 && j < DP_J) trk[c * 32 + j] = row;
+    float origin[3] = {0.f, 0.f, 0.f};  // world-absolute targets are taken relative to the clip's current global position
+    if (A.targets_world) { origin[0] = A.gpos[cc * 3]; origin[1] = A.gpos[cc * 3 + 1]; origin[2] = A.gpos[cc * 3 + 2]; }
+    const int32_t* jn = A.joints + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride);
+    const float* wt = A.weights + (A.shared_trackers ? 0 : (size_t)cc * A.ee_stride * 2);
+    for (int e = 0; e < ne; ++e) {
+      if (jn[e] == lane) {
+        const float* tp = A.tgt_pos + ((size_t)cc * A.ee_stride + e) * 3;
+        const float* tr = A.tgt_rot + ((size_t)cc * A.ee_stride + e) * 9;
+        row.pw = make_float4(tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt[2 * e]);
+        row.r0 = make_float4(tr[0], tr[1], tr[2], wt[2 * e + 1]);
+        row.r1 = make_float4(tr[3], tr[4], tr[5], 0.f);
+        row.r2 = make_float4(tr[6], tr[7], tr[8], 0.f);
+      }
     }
+    trk[c * 32 + lane] = row;
   }
   mbar_wait(bar, 0);  // model image has landed
   __syncwarp();
