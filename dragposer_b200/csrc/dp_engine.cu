@@ -50,6 +50,13 @@ struct dp_engine {
   int target_rows = 0;            // window + 1 of the current buffer, 0 = none yet
   int ring_head = 0;
   int current_index = 0;
+  // Look-ahead at temporal_future_window == 0 (the predictor runs every frame): its inputs end three frames in the past
+  // (train_temporal.param["past_frames"] stops at ring row 56 of 60), so the targets of this frame AND the next three are computed
+  // in ONE batched predictor call (4 x n_clips virtual clips: fuller tiles, a quarter of the launches) -- the same numbers the
+  // reference computes frame by frame.
+  int lookahead = DP_LOOKAHEAD;   // 1 disables (environment DP_LOOKAHEAD=1)
+  float* d_target_pre = nullptr;  // (B, DP_LOOKAHEAD, 24)
+  int look_left = 0, look_next = 0, look_last_row = -1;
   // outputs / diagnostics
   int32_t* d_iters = nullptr;
   float* d_losses = nullptr;
@@ -113,11 +120,15 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaMalloc(&e->d_losses, B * 3 * 4));
   CK(cudaMalloc(&e->d_mu, DP_L * 4));
   CK(cudaMalloc(&e->d_sigma, DP_L * 4));
-  CK(cudaMalloc(&e->tw.enc, B * TP_S * TP_D * 4));
-  CK(cudaMalloc(&e->tw.enc2, B * TP_S * TP_D * 4));
-  CK(cudaMalloc(&e->tw.dec, B * TP_MAXT * TP_D * 4));
-  CK(cudaMalloc(&e->tw.dec2, B * TP_MAXT * TP_D * 4));
-  CK(cudaMalloc(&e->tw.dec_lat, B * TP_MAXT * TP_LAT * 4));
+  if (const char* s = getenv("DP_LOOKAHEAD")) e->lookahead = atoi(s) <= 1 ? 1 : DP_LOOKAHEAD;
+  const size_t V = B * DP_LOOKAHEAD;  // virtual clips of a look-ahead predictor call
+  CK(cudaMalloc(&e->d_target_pre, V * DP_L * 4));
+  CK(cudaMemset(e->d_target_pre, 0, V * DP_L * 4));
+  CK(cudaMalloc(&e->tw.enc, V * TP_S * TP_D * 4));
+  CK(cudaMalloc(&e->tw.enc2, V * TP_S * TP_D * 4));
+  CK(cudaMalloc(&e->tw.dec, V * TP_MAXT * TP_D * 4));
+  CK(cudaMalloc(&e->tw.dec2, V * TP_MAXT * TP_D * 4));
+  CK(cudaMalloc(&e->tw.dec_lat, V * TP_MAXT * TP_LAT * 4));
   CK(cudaMalloc(&e->tw.ffpart, DP_FF_PART_FLOATS * 4));
   e->tw.num_sms = e->num_sms;
   CK(cudaEventCreateWithFlags(&e->tw.ev_fork, cudaEventDisableTiming));
@@ -148,7 +159,7 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   free_pipe(e);
   cudaFree(e->d_model); cudaFree(e->d_model_tc); cudaFree(e->d_model_tmem); cudaFree(e->d_encoder); cudaFree(e->d_tblob); cudaFree(e->d_fftiles); cudaFree(e->d_mu); cudaFree(e->d_sigma);
   cudaFree(e->d_latent); cudaFree(e->d_gpos); cudaFree(e->d_grot); cudaFree(e->d_latent_buf);
-  cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_iters);
+  cudaFree(e->d_disp_buf); cudaFree(e->d_height_buf); cudaFree(e->d_target_buf); cudaFree(e->d_target_pre); cudaFree(e->d_iters);
   cudaFree(e->d_losses); cudaFree(e->d_trace); cudaFree(e->d_adam); cudaFree(e->d_phase);
   cudaFree(e->tw.enc); cudaFree(e->tw.enc2); cudaFree(e->tw.dec); cudaFree(e->tw.dec2); cudaFree(e->tw.dec_lat); cudaFree(e->tw.ffpart);
   for (int i = 0; i < DP_PRED_MAX_PARTS - 1; ++i)
@@ -333,6 +344,7 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
     if (!e->d_fftiles) CK(cudaMalloc(&e->d_fftiles, tiles.size()));
     CK(cudaMemcpy(e->d_fftiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
   }
+  e->look_left = 0;
   e->has_temporal = true;
   return DP_OK;
 }
@@ -359,6 +371,8 @@ extern "C" int dp_engine_init_clips(dp_engine* e, int n, const float* latent0, c
   e->ring_head = 0;
   e->current_index = 0;
   e->target_rows = 0;
+  e->look_left = 0;
+  e->look_last_row = -1;
   return DP_OK;
 }
 
@@ -437,11 +451,27 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
     for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&ev[i]));
     CK(cudaEventRecord(ev[0], st));
   }
-  if (e->current_index == 0) {
-    if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
-    CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
-                       e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
-                       &e->launches));
+  const bool look = W == 0 && e->lookahead > 1;
+  if (!look) {
+    e->look_left = 0;
+    e->look_last_row = -1;
+    if (e->current_index == 0) {
+      if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
+      CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
+                         e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
+                         &e->launches));
+    }
+  } else {
+    if (e->look_left == 0) {  // targets of this frame and of the next lookahead - 1 frames in one call
+      if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
+      CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
+                         e->ring_head, e->n_clips, 0, e->d_target_pre, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
+                         &e->launches, e->lookahead));
+      e->look_left = e->lookahead;
+      e->look_next = 0;
+    }
+    e->look_last_row = e->look_next++;
+    --e->look_left;
   }
   if (e->trace_enabled && (!e->d_trace || e->trace_iters < p->max_iter)) {
     cudaFree(e->d_trace);
@@ -459,6 +489,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
   a.latent_buf = e->d_latent_buf; a.disp_buf = e->d_disp_buf; a.height_buf = e->d_height_buf;
   a.ring_head = e->ring_head;
   a.target_buf = e->d_target_buf; a.target_rows = W + 1; a.target_index = e->current_index;
+  if (look) { a.target_buf = e->d_target_pre; a.target_rows = e->lookahead; a.target_index = e->look_last_row; }
   a.n_ee = n_ee; a.joints = joints; a.weights = weights; a.shared_trackers = shared;
   a.tgt_pos = tgt_pos; a.tgt_rot = tgt_rot; a.ee_stride = ee_stride;
   a.targets_world = p->targets_world ? 1 : 0;
@@ -841,7 +872,11 @@ extern "C" int dp_engine_get_state(dp_engine* e, float* latent, float* gpos, flo
   if (height_buf && (rc = copy_ring(e, e->d_height_buf, height_buf, DP_NH))) return rc;
   if (target_buf) {
     if (e->target_rows <= 0) return fail(DP_ERR_STATE, "no target buffer yet");
-    CK(cudaMemcpy(target_buf, e->d_target_buf, B * e->target_rows * DP_L * 4, cudaMemcpyDeviceToHost));
+    if (e->look_last_row >= 0)  // window 0 with look-ahead: the row the last frame used, as (B,1,24)
+      CK(cudaMemcpy2D(target_buf, DP_L * 4, e->d_target_pre + (size_t)e->look_last_row * DP_L, (size_t)e->lookahead * DP_L * 4, DP_L * 4, B,
+                      cudaMemcpyDeviceToHost));
+    else
+      CK(cudaMemcpy(target_buf, e->d_target_buf, B * e->target_rows * DP_L * 4, cudaMemcpyDeviceToHost));
   }
   if (current_index) *current_index = e->current_index;
   return DP_OK;
@@ -857,6 +892,7 @@ extern "C" int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf,
   CK(cudaMemcpy(e->d_disp_buf, disp_buf, B * DP_PAST * 3 * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->d_height_buf, height_buf, B * DP_PAST * DP_NH * 4, cudaMemcpyHostToDevice));
   e->ring_head = 0;  // rows were given in chronological order
+  e->look_left = 0;  // targets computed ahead from the old rows are void
   return DP_OK;
 }
 
@@ -871,6 +907,7 @@ extern "C" int dp_engine_predict_targets(dp_engine* e, int window, void* stream)
     CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (window + 1) * DP_L * 4, st));
     e->target_rows = window + 1;
   }
+  e->look_last_row = -1;  // dp_engine_get_state reports what this call writes
   CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf, e->ring_head,
                      e->n_clips, window, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
                      &e->launches));
@@ -918,8 +955,9 @@ extern "C" int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double*
 }
 
 extern "C" int dp_engine_set_predictor_path(dp_engine* e, int path) {
-  if (!e || path < 0 || path > 1) return fail(DP_ERR_ARG, "predictor path must be 0 (tcgen05 3xTF32 FF) or 1 (fp32 CUDA-core FF)");
+  if (!e || path < 0 || path > 1) return fail(DP_ERR_ARG, "predictor path must be 0 (tcgen05 fp16x2 attention + FF) or 1 (fp32 CUDA-core kernels)");
   e->predictor_path = path;
+  e->look_left = 0;
   return DP_OK;
 }
 

@@ -44,7 +44,12 @@ cudaError_t dp_frame_tc16_launch(const DpFrameArgs& args, int num_sms, cudaStrea
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
                             const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
                             int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
-                            long long* launches);
+                            long long* launches, int lookahead = 1);
+// lookahead J > 1 (window 0 only): J virtual clips per real clip, virtual clip c * J + j = clip c as the predictor will see it j
+// frames from now; target_buf is then (B, J, 24).  Exact, because the predictor never reads the three newest ring rows:
+// train_temporal.param["past_frames"] ends at row 56 of 60 (drag_pose.py:249-266), so what it reads j <= 3 frames from now is
+// already in the ring today.
+#define DP_LOOKAHEAD 4
 void dp_attn_tc_pack(const float* w_in_t, const float* b_in, const float* w_out_t, const float* b_out, unsigned char* dst);
 cudaError_t dp_attn_tc_launch(const unsigned char* wimg, const float* blob, const TpNorm& N1, const float* xq, int T, int q_stride,
                               const float* xkv, int S, int kv_stride, int n_clips, float* out, cudaStream_t st);

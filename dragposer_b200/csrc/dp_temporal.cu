@@ -38,29 +38,34 @@ __device__ __forceinline__ void layer_norm_row(float v0, float v1, bool has1, co
 __global__ void __launch_bounds__(EMB_THREADS) tp_embed_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ mu,
                                                                const float* __restrict__ sigma, const float* __restrict__ latent_buf,
                                                                const float* __restrict__ disp_buf, const float* __restrict__ height_buf, int head,
-                                                               int n_clips, float* __restrict__ enc, float* __restrict__ dec_lat) {
+                                                               int n_clips, int v0, int J, float* __restrict__ enc, float* __restrict__ dec_lat) {
+  // n_clips VIRTUAL clips starting at virtual index v0: virtual clip v is real clip v / J seen j = v % J frames ahead (its ring
+  // buffers read j rows later) -- the look-ahead batching of dp_engine.cu; J = 1 is the plain case.  enc / dec_lat are indexed by
+  // the local virtual clip, the ring buffers by the real clip.
   __shared__ float xs[EMB_CLIPS * TP_S * EMB_XS];
   const int tid = threadIdx.x, clip0 = blockIdx.x * EMB_CLIPS;
   const int g_here = min(EMB_CLIPS, n_clips - clip0), rows = g_here * TP_S;
   for (int idx = tid; idx < rows * TP_ENC_IN; idx += EMB_THREADS) {
     const int r = idx / TP_ENC_IN, i = idx % TP_ENC_IN, k = r % TP_S;
-    const size_t b = (size_t)(clip0 + r / TP_S);
-    const int slot = (head + 4 * k) % DP_PAST;
-    float v;
+    const int v = v0 + clip0 + r / TP_S, ahead = v % J;
+    const size_t b = (size_t)(v / J);
+    const int slot = (head + 4 * k + ahead) % DP_PAST;
+    float x;
     if (i < TP_LAT) {
-      v = (latent_buf[(b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
+      x = (latent_buf[(b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
     } else if (i < TP_LAT + 3) {
-      v = 0.0f;
-      for (int q = 0; q < 4; ++q) v += disp_buf[(b * DP_PAST + (head + 4 * k + q) % DP_PAST) * 3 + (i - TP_LAT)];
+      x = 0.0f;
+      for (int q = 0; q < 4; ++q) x += disp_buf[(b * DP_PAST + (head + 4 * k + q + ahead) % DP_PAST) * 3 + (i - TP_LAT)];
     } else {
-      v = height_buf[(b * DP_PAST + slot) * DP_NH + (i - TP_LAT - 3)];
+      x = height_buf[(b * DP_PAST + slot) * DP_NH + (i - TP_LAT - 3)];
     }
-    xs[r * EMB_XS + i] = v;
+    xs[r * EMB_XS + i] = x;
   }
   for (int idx = tid; idx < g_here * TP_LAT; idx += EMB_THREADS) {
-    const size_t b = (size_t)(clip0 + idx / TP_LAT);
-    const int i = idx % TP_LAT, slot = (head + 56) % DP_PAST;
-    dec_lat[b * TP_MAXT * TP_LAT + i] = (latent_buf[(b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
+    const int lv = clip0 + idx / TP_LAT, v = v0 + lv;
+    const size_t b = (size_t)(v / J);
+    const int i = idx % TP_LAT, slot = (head + 56 + v % J) % DP_PAST;
+    dec_lat[(size_t)lv * TP_MAXT * TP_LAT + i] = (latent_buf[(b * DP_PAST + slot) * DP_L + i] - mu[i]) / sigma[i];
   }
   __syncthreads();
   const int f = tid % TP_D, rg = tid / TP_D;  // 6 row groups
@@ -393,15 +398,17 @@ __global__ void tp_out_kernel(const float* __restrict__ blob, TpLayout L, const 
 
 static const size_t kFfSmem = sizeof(float) * (2 * TP_D * FF_HC + FF_TM * (TP_D + 1) + FF_TM * (FF_HC + 1));
 
+// B virtual clips starting at virtual clip v0 (J virtual clips per real clip, see tp_embed_kernel); latent_buf / disp_buf /
+// height_buf are the UNSHIFTED ring buffers, target_buf and the work buffers of `w` start at the part's first virtual clip.
 static cudaError_t run_part(const float* blob, const TpLayout& L, const float* mu, const float* sigma, const float* latent_buf,
-                            const float* disp_buf, const float* height_buf, int head, int B, int window, float* target_buf, const TpWork& w,
-                            size_t part_floats, const unsigned char* fftiles, cudaStream_t st, long long* launches) {
+                            const float* disp_buf, const float* height_buf, int head, int B, int v0, int J, int window, float* target_buf,
+                            const TpWork& w, size_t part_floats, const unsigned char* fftiles, cudaStream_t st, long long* launches) {
   cudaError_t err = cudaSuccess;
 
   float* e = w.enc;
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
-  tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, w.enc, w.dec_lat);
+  tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, v0, J, w.enc, w.dec_lat);
   ++*launches;
   for (int l = 0; l < TP_NENC; ++l) {
     if (fftiles)
@@ -423,7 +430,7 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
   int T = 1;
   static const int fused_dec = getenv("DP_PRED_FUSED_DEC") ? atoi(getenv("DP_PRED_FUSED_DEC")) : 1;
   for (int i = 0; i <= window; i += 4, ++T) {
-    if (fftiles && fused_dec && T == 1) {
+    if (fftiles && fused_dec && T == 1 && (size_t)4 * B * TP_D <= part_floats) {
       // single-token pass: embedding + self-attention of layer 0 in one small kernel, then per layer { cross-attention, feed-forward
       // with the next layer's self-attention (or the prediction head) fused into its finishing kernel }: 10 launches instead of 17
       const unsigned char* att = fftiles + DP_TC_ATT_OFFSET;
@@ -491,16 +498,17 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
 // CTA slots, so the block scheduler interleaves the parts and fills the tail of one kernel with the head of another
 // (448 tiles on 296 slots otherwise leave a third, half-empty round in every encoder kernel).
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
-                            const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
+                            const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int n_real,
                             int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,
-                            long long* launches) {
+                            long long* launches, int J) {
+  const int B = n_real * J;  // virtual clips
   cudaError_t err = cudaFuncSetAttribute(tp_ff_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFfSmem);
   if (err != cudaSuccess) return err;
   static const int split_min = getenv("DP_PRED_SPLIT_MIN") ? atoi(getenv("DP_PRED_SPLIT_MIN")) : 2048;
   static const int n_parts_env = getenv("DP_PRED_PARTS") ? atoi(getenv("DP_PRED_PARTS")) : DP_PRED_PARTS_DEFAULT;
   const int n_parts = n_parts_env < 1 ? 1 : (n_parts_env > DP_PRED_MAX_PARTS ? DP_PRED_MAX_PARTS : n_parts_env);
   if (!fftiles || n_parts == 1 || B < split_min)
-    return run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, window, target_buf, w, DP_FF_PART_FLOATS, fftiles, st, launches);
+    return run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, 0, J, window, target_buf, w, DP_FF_PART_FLOATS, fftiles, st, launches);
   if ((err = cudaEventRecord(w.ev_fork, st)) != cudaSuccess) return err;
   const int per = (B + n_parts - 1) / n_parts;
   for (int p = 0; p < n_parts; ++p) {
@@ -513,8 +521,7 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     wp.dec += (size_t)b0 * TP_MAXT * TP_D; wp.dec2 += (size_t)b0 * TP_MAXT * TP_D;
     wp.dec_lat += (size_t)b0 * TP_MAXT * TP_LAT;
     wp.ffpart += (DP_FF_PART_FLOATS / DP_PRED_MAX_PARTS) * p;
-    err = run_part(blob, L, mu, sigma, latent_buf + (size_t)b0 * DP_PAST * DP_L, disp_buf + (size_t)b0 * DP_PAST * 3,
-                   height_buf + (size_t)b0 * DP_PAST * DP_NH, head, nb, window, target_buf + (size_t)b0 * (window + 1) * TP_LAT, wp,
+    err = run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, nb, b0, J, window, target_buf + (size_t)b0 * (window + 1) * TP_LAT, wp,
                    DP_FF_PART_FLOATS / DP_PRED_MAX_PARTS, fftiles, sp, launches);
     if (err != cudaSuccess) return err;
     if (p > 0) {
