@@ -128,6 +128,7 @@ def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights
     B = g["latent0"].shape[0]
     eng.set_initial_state(g["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
     eng.enable_trace(True)
+    worst_late = 0.0
     for t in range(n_frames):
         pose, gpos = eng.run(g["tgt_pos"][t], g["tgt_rot"][t], g["joints"], g["weights"], lambda_rot=1,
                              lambda_temporal=cfg.lambda_temporal, temporal_future_window=cfg.temporal_future_window,
@@ -144,14 +145,23 @@ def test_frames_6_trackers_vs_reference(golden_dir, engine_factory, port_weights
         dg = np.abs(gpos - g[f"{tag}_gpos"][t]).max()
         print(f"{tag} frame {t}: iters {iters} ref {ref_iters} max joint diff {dpos*1e3:.4f} mm root diff {dg*1e3:.4f} mm")
         assert dpos <= POS_TOL and dg <= POS_TOL
-        # per-iteration trajectory: latents stay close to the reference's
+        # per-iteration trajectory: latents stay close to the reference's.  This is a LOOSE guard by nature -- the first Adam step
+        # is lr * sign(g), so a latent dimension whose gradient sits in the fp32 noise takes a +-lr = 1e-2 kick whose sign two
+        # faithful implementations need not agree on; the kick decays as Adam's moments fill.  The real per-iteration guard is the
+        # teacher-forced gradient test above (1e-4 relative at the reference's own latents).  Measured here: first frame of a clip
+        # (common start) <= 3e-6 from iteration 10 on; later frames inherit the carried state's difference.
         tr = eng.trace(opt["max_iter"])
         for c in range(B):
             n = int(min(iters[c], ref_iters[c]))
             assert tr["active"][c, :n].all()
-            dz = np.abs(tr["latent"][c, :n] - g[f"{tag}_latent"][t, c, :n]).max()
-            assert dz <= 2e-3, (t, c, dz)
+            dz = np.abs(tr["latent"][c, :n] - g[f"{tag}_latent"][t, c, :n])
+            assert dz.max() <= 2e-3, (t, c, dz.max())
+            if n > 10:
+                late = float(dz[10:].max())
+                worst_late = max(worst_late, late)
+                assert late <= (2e-4 if t == 0 else 1e-3), (t, c, late)
     eng.enable_trace(False)
+    print(f"{tag}: worst per-iteration latent difference from iteration 10 on: {worst_late:.2e}")
     st = eng.state()
     for c in range(B):
         np.testing.assert_allclose(st["height_buf"][c], g[f"{tag}_state_height_buf_{c}"], atol=1e-3)
