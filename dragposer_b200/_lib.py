@@ -79,6 +79,7 @@ SIGNATURES = {
     "dp_engine_set_encoder_model": (C.c_int, [_VP, C.POINTER(EncoderModelC)]),
     "dp_engine_encode_host": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP]),
     "dp_engine_get_phase_cycles": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),
+    "dp_engine_get_timeline": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),
     "dp_engine_get_profile": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 

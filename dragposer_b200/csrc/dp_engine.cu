@@ -79,7 +79,7 @@ struct dp_engine {
   long long launches = 0;
   // optional device-side timing of the two kernel groups (bench roofline)
   int profiling = 0;
-  unsigned long long* d_phase = nullptr;  // 8 phase-cycle counters of the tcgen05 frame kernel (profiling level 2 only)
+  unsigned long long* d_phase = nullptr;  // 8 phase-cycle counters + 48 timeline stamps of the tcgen05 frame kernel (profiling level 2 only)
   std::vector<cudaEvent_t> prof_events;  // triples: before predictor, before frame kernel, after frame kernel
 };
 
@@ -297,24 +297,29 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
     std::vector<uint32_t> tm((size_t)DP_TC_TMEM_WORDS * 128, 0u);
     const int kpad[3] = {32, 48, 64}, opad[3] = {48, 64, 96};
     uint32_t col = 0;
-    auto put = [&](int l, bool fwd) {
+    // `replicate` = 32: the rows repeat in every 32-lane quarter (the last backward layer: each warp reads dL/dz in its own quarter);
+    // 64: they repeat in the upper 64 lanes (layers of <= 64 rows: all eight epilogue warps of a group share the clips); 0: plain
+    auto put = [&](int l, bool fwd, int replicate) {
       const int K = dims[l], N = dims[l + 1];          // W_l is [N][K]
       const int kk = fwd ? kpad[l] : opad[l];          // padded reduction length of this operand
       for (int p = 0; p < 2; ++p) {
-        for (int m = 0; m < 128; ++m)
+        for (int lane = 0; lane < 128; ++lane)
           for (int k = 0; k < kk; ++k) {
+            const int m = replicate ? (lane % replicate) : lane;
             const bool in = fwd ? (m < N && k < K) : (m < K && k < N);
             float r = in ? 16.0f * (fwd ? A[l][m * K + k] : A[l][k * K + m]) : 0.0f;
             __half h = __float2half_rn(r);
             if (p == 1) { r -= __half2float(h); h = __float2half_rn(r); }
             uint16_t bits;
             memcpy(&bits, &h, 2);
-            tm[(size_t)(col + k / 2) * 128 + m] |= (uint32_t)bits << (16 * (k & 1));
+            tm[(size_t)(col + k / 2) * 128 + lane] |= (uint32_t)bits << (16 * (k & 1));
           }
         col += kk / 2;
       }
     };
-    put(0, true); put(1, true); put(2, true); put(2, false); put(1, false); put(0, false);
+    static_assert(DP_L <= 32, "the replicated rows of the last backward layer must fit a lane quarter");
+    static_assert(DP_H0 <= 64 && DP_H1 <= 64, "the replicated rows of the two hidden layers must fit 64 lanes");
+    put(0, true, 64); put(1, true, 64); put(2, true, 0); put(2, false, 64); put(1, false, 64); put(0, false, 32);
     if (col != DP_TC_TMEM_WORDS) return fail(DP_ERR_STATE, "tensor-memory weight image layout");
     CK(cudaMemcpy(e->d_model_tmem, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
   }
@@ -922,8 +927,8 @@ extern "C" int dp_engine_set_profiling(dp_engine* e, int enable) {
   e->prof_events.clear();
   e->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   if (enable >= 2) {
-    if (!e->d_phase) CK(cudaMalloc(&e->d_phase, 8 * sizeof(unsigned long long)));
-    CK(cudaMemset(e->d_phase, 0, 8 * sizeof(unsigned long long)));
+    if (!e->d_phase) CK(cudaMalloc(&e->d_phase, 64 * sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_phase, 0, 64 * sizeof(unsigned long long)));
   }
   return DP_OK;
 }
@@ -933,6 +938,14 @@ extern "C" int dp_engine_get_phase_cycles(dp_engine* e, unsigned long long* cycl
   if (!e->d_phase) return fail(DP_ERR_STATE, "profiling was never enabled");
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(cycles8, e->d_phase, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return DP_OK;
+}
+
+extern "C" int dp_engine_get_timeline(dp_engine* e, unsigned long long* stamps48) {
+  if (!e || !stamps48) return fail(DP_ERR_ARG, "null argument");
+  if (!e->d_phase) return fail(DP_ERR_STATE, "profiling was never enabled");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(stamps48, e->d_phase + 16, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return DP_OK;
 }
 

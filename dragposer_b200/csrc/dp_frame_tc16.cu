@@ -22,36 +22,38 @@ namespace {
 constexpr int NC = 32;            // clip columns per CTA: two groups of 16 (UMMA N = 16)
 constexpr int kWarps = 16;     // two groups of 8 warps
 constexpr int EC = 8;             // clips per epilogue thread: a group's 8 warps = 4 TMEM lane quarters x 2 clip halves
-// activation image (B operand, MN-major, no swizzle): element (feature k, clip column n) of a piece at
-//   (k / 8) * kB_LBO + (k % 8) * 16 + (n / 8) * kB_SBO + (n % 8) * 2 bytes.
-// The K 8-groups are padded from 512 to 528 bytes: at 512 every 8-group starts in the same bank and the 32 lanes of an epilogue
-// warp (consecutive features, one 16-byte store each) collide four ways; 528 moves each group on by four banks.
-constexpr uint32_t kB_LBO = 128 * (NC / 8) + 16;
-constexpr uint32_t kB_SBO = 128;
-constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // per fp16 piece
-// dL/dy image (B operand of the first backward layer only), K-MAJOR: element (clip column n, feature k) of a piece at
-//   (n / 8) * kD_SBO + (k / 8) * kD_LBO + (n % 8) * 16 + (k % 8) * 2 bytes,
+// activation image (B operand, MN-major, no swizzle).  The two fp16 pieces of a group's 16 clips lie SIDE BY SIDE along N, so that
+// one N = 32 instruction multiplies a weight piece with both of them: element (feature k, group g, piece p, clip n < 16) at
+//   (k / 8) * kB_LBO + (k % 8) * 16 + (4 g + 2 p + n / 8) * kB_SBO + (n % 8) * 2 bytes.
+// The K 8-groups are padded from 1024 to 1040 bytes: unpadded, every 8-group starts in the same bank and the 32 lanes of an
+// epilogue warp (consecutive features, one 16-byte store each) collide four ways; the pad moves each group on by four banks.
+constexpr uint32_t kB_SBO = 128, kB_PIECE = 2 * kB_SBO;
+constexpr uint32_t kB_LBO = kB_SBO * 2 * (NC / 8) + 16;
+constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // both pieces
+// dL/dy image (B operand of the first backward layer only), K-MAJOR: element (group g, piece p, clip n < 16, feature k) at
+//   (4 g + 2 p + n / 8) * kD_SBO + (k / 8) * kD_LBO + (n % 8) * 16 + (k % 8) * 2 bytes,
 // so that the kinematics lane of joint j stores its four values dL/dy[4j .. 4j+3] of a clip as ONE 8-byte word per piece -- the
 // adjoint writes the tensor-core operand itself and the backward layers start after a single group barrier (round 1 wrote fp32
 // rows, and the epilogue warps re-read them transposed, split them and stored them behind a second barrier).  kD_LBO is padded
 // from 128 to 144 bytes for the same bank reason as kB_LBO.
-constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kDyBytes = (NC / 8) * kD_SBO;
+constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kD_PIECE = 2 * kD_SBO, kDyBytes = 2 * (NC / 8) * kD_SBO;
 constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scaled per clip into [16, 32) (see dp_frame_tc.cu)
 enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
-// tensor-memory columns: accumulators of group g at 16 g; then the weight pieces (two K elements per 32-bit word)
-constexpr uint32_t kT_D = 0, kT_W = 32, kT_COLS = 512;
+// tensor-memory columns: accumulators of group g at 32 g (16 columns per B piece); then the weight pieces (two K elements per word)
+constexpr uint32_t kT_D = 0, kT_W = 64, kT_COLS = 512;
 static_assert(kT_W + DP_TC_TMEM_WORDS <= kT_COLS, "weights must fit in tensor memory");
 
 struct SmemT {
   __align__(16) unsigned char model[DP_TC_IMAGE_BYTES(0)];   // biases, statistics, skeleton tables (no weight pieces)
-  __align__(16) unsigned char ping[2][kPingBytes];  // [piece]  z (24) / a1 (60) / dL/dh1 (60)
-  __align__(16) unsigned char pong[2][kPongBytes];  // [piece]  a0 (40) / dL/dy (92) / dL/dh0 (40)
-  __align__(16) unsigned char dyimg[2][kDyBytes];   // [piece]  dL/dy (92), K-major
+  __align__(16) unsigned char ping[kPingBytes];     // z (24) / a1 (60) / dL/dh1 (60)
+  __align__(16) unsigned char pong[kPongBytes];     // a0 (40) / dL/dh0 (40)
+  __align__(16) unsigned char dyimg[kDyBytes];      // dL/dy (92), K-major
   __align__(16) float ybuf[NC][96];                 // y (fp32, one row per clip)
-  float zgrad[NC][25];                              // dL/dz from the decoder (fp32)
   float bscale[NC];                                 // 1 / (per-clip power-of-two scale of dL/dy)
   __align__(16) float4 trk[NC][4][32];              // tracker tables, structure of arrays (dp_fk2.cuh)
-  __align__(16) float2 st[NC][5][DP_L / 2];         // [ST_Z latent | ST_TL target latent | ST_M, ST_V Adam moments | ST_ZLAST]
+  // optimiser state of a warp's clip pair, one float2 (.x first clip, .y second) per latent feature:
+  // [ST_Z latent | ST_TL target latent | ST_M, ST_V Adam moments | ST_ZLAST last evaluated latent]
+  __align__(16) float2 st[NC / 2][5][DP_L];
   __align__(16) float groot[NC][4];                 // previous world root rotation g (wxyz)
   __align__(16) float2 fkscr[NC / 2][16];           // per clip pair: R_0, r, d parked between the two halves of the kinematics pass
   double prev[NC];                                  // previous total loss (early stopping compares in double)
@@ -82,9 +84,9 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {  
 __device__ __forceinline__ void unpack_f16x2(uint32_t p, float& lo_elem, float& hi_elem) {
   asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo_elem), "=f"(hi_elem) : "r"(p));
 }
-// 8 fp32 values (feature k, clip 8-group cg of the tile) -> the two fp16 pieces of an MN-major activation image
-__device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_stride, int k, int cg, const float (&v)[EC]) {
-  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + cg * kB_SBO;
+// 8 fp32 values (feature k; slot = 4 group + clip half: the 8-group of the first piece) -> the two fp16 pieces of an MN-major image
+__device__ __forceinline__ void store_pieces(unsigned char* img, int k, int slot, const float (&v)[EC]) {
+  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + slot * kB_SBO;
   uint32_t p1[4], p2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -95,17 +97,26 @@ __device__ __forceinline__ void store_pieces(unsigned char* img, uint32_t piece_
     p2[i] = pack_f16x2(x0 - h0, x1 - h1);
   }
   *reinterpret_cast<uint4*>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-  *reinterpret_cast<uint4*>(dst + piece_stride) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  *reinterpret_cast<uint4*>(dst + kB_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
 }
-// a single fp32 value (feature k, clip column n) -> its pieces (used by the Adam lanes for the latent)
-__device__ __forceinline__ void store_piece_scalar(unsigned char* img, uint32_t piece_stride, int k, int n, float x) {
-  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (n >> 3) * kB_SBO + (n & 7) * 2;
-  const uint32_t p = pack_f16x2(x, 0.0f);
+// 4 fp32 values (feature k; 8-group `slot`, clips 4 sub .. 4 sub + 3 of it) -> the two fp16 pieces, one 8-byte store each
+__device__ __forceinline__ void store_pieces4(unsigned char* img, int k, int slot, int sub, const float (&v)[4]) {
+  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + slot * kB_SBO + sub * 8;
+  const uint32_t a = pack_f16x2(v[0], v[1]), b = pack_f16x2(v[2], v[3]);
+  float h0, h1, h2, h3;
+  unpack_f16x2(a, h0, h1);
+  unpack_f16x2(b, h2, h3);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(a, b);
+  *reinterpret_cast<uint2*>(dst + kB_PIECE) = make_uint2(pack_f16x2(v[0] - h0, v[1] - h1), pack_f16x2(v[2] - h2, v[3] - h3));
+}
+// one feature of a clip PAIR (columns cl, cl + 1 of group g, cl even) -> its pieces, one 32-bit store each (latent rows of ping)
+__device__ __forceinline__ void store_piece_pair(unsigned char* img, int k, int g, int cl, float x0, float x1) {
+  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (4 * g + (cl >> 3)) * kB_SBO + (cl & 7) * 2;
+  const uint32_t p = pack_f16x2(x0, x1);
   float h0, h1;
   unpack_f16x2(p, h0, h1);
-  const uint32_t q = pack_f16x2(x - h0, 0.0f);
-  *reinterpret_cast<unsigned short*>(dst) = (unsigned short)(p & 0xffffu);
-  *reinterpret_cast<unsigned short*>(dst + piece_stride) = (unsigned short)(q & 0xffffu);
+  *reinterpret_cast<uint32_t*>(dst) = p;
+  *reinterpret_cast<uint32_t*>(dst + kB_PIECE) = pack_f16x2(x0 - h0, x1 - h1);
 }
 
 // weight pieces in tensor memory (word offsets inside kT_W): layer l forward = W_l (rows = outputs), backward = W_l^T
@@ -121,18 +132,18 @@ static_assert(WT<0, false>::p2 + 24 == DP_TC_TMEM_WORDS, "tensor-memory weight m
 // sink of the kinematics adjoint: the (scaled) dL/dy of the warp's two clips as fp16 pieces of the K-major operand image
 struct EmitDyPieces {
   unsigned char* img;
-  int n0, lane;
+  int g, cl, lane;  // group, (even) column of the warp's first clip inside the group
   static __device__ __forceinline__ void put(unsigned char* dst, float x0, float x1, float x2, float x3) {
     const uint32_t a = pack_f16x2(x0, x1), b = pack_f16x2(x2, x3);
     float h0, h1, h2, h3;
     unpack_f16x2(a, h0, h1);
     unpack_f16x2(b, h2, h3);
     *reinterpret_cast<uint2*>(dst) = make_uint2(a, b);
-    *reinterpret_cast<uint2*>(dst + kDyBytes) = make_uint2(pack_f16x2(x0 - h0, x1 - h1), pack_f16x2(x2 - h2, x3 - h3));
+    *reinterpret_cast<uint2*>(dst + kD_PIECE) = make_uint2(pack_f16x2(x0 - h0, x1 - h1), pack_f16x2(x2 - h2, x3 - h3));
   }
   __device__ __forceinline__ void operator()(const P2 (&o)[4], const P2 (&db)[3]) const {
-    // clips n0 and n0 + 1 share an 8-group (n0 is even): rows (n0 % 8) and (n0 % 8) + 1 of the same core matrices
-    unsigned char* base = img + (n0 >> 3) * kD_SBO + (n0 & 7) * 16;
+    // the two clips share an 8-group (cl is even): rows (cl % 8) and (cl % 8) + 1 of the same core matrices
+    unsigned char* base = img + (4 * g + (cl >> 3)) * kD_SBO + (cl & 7) * 16;
     if (lane < DP_J) {
       unsigned char* dst = base + (lane >> 1) * kD_LBO + (lane & 1) * 8;  // k = 4 lane: 8-group lane / 2, first or second half
       put(dst, o[0].v.x, o[1].v.x, o[2].v.x, o[3].v.x);
@@ -153,42 +164,80 @@ struct Ctx {
   uint32_t phase;  // parity of the group's next MMA completion
 };
 
-// one dense layer of one group on the tensor pipe + its epilogue; every thread of the group calls this (ends with the
-// group barrier).  A = weight pieces in tensor memory, B = the group's 16 clip columns of the activation image.
-// B_KMAJOR: the B operand is the K-major dL/dy image instead of an MN-major activation image.
-template <int L, bool FWD, bool B_KMAJOR = false, class Epi>
-__device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint32_t src_stride, int out_rows, Epi epi) {
-  SmemT& S = *c.S;
+// MMAs of one dense layer of one group; every thread of the group calls this, one elected lane of the group's first warp issues.
+// A = weight pieces in tensor memory, B = the group's clip columns of the activation image: per K step of 16
+//   D[:, 0..31] (+)= A1 . [B1 | B2]   (N = 32: the (1,1) product lands in columns 0..15, the (1,2) product in columns 16..31)
+//   D[:, 0..15]  += A2 . B1           (N = 16: the (2,1) product)
+// and the epilogue adds the two column blocks -- two instructions per K step instead of three (an instruction costs ~20 issue
+// cycles whatever its N).  B_KMAJOR: the B operand is the K-major dL/dy image instead of an MN-major activation image.
+template <int L, bool FWD, bool B_KMAJOR = false>
+__device__ __forceinline__ void tc_issue(Ctx& c, const unsigned char* src) {
   if (c.wg == 0) {
     tc_fence_after();
     if (elect_one()) {
-      // fp16 x fp16 -> fp32, N 16, M 128; bit 16: B is MN-major
-      constexpr uint32_t idesc = (1u << 4) | (B_KMAJOR ? 0u : (1u << 16)) | ((uint32_t)(16 >> 3) << 17) | (8u << 24);
+      // fp16 x fp16 -> fp32, M 128; bit 16: B is MN-major
+      constexpr uint32_t idesc = (1u << 4) | (B_KMAJOR ? 0u : (1u << 16)) | (8u << 24);
+      constexpr uint32_t idesc16 = idesc | ((uint32_t)(16 >> 3) << 17), idesc32 = idesc | ((uint32_t)(32 >> 3) << 17);
       constexpr uint32_t lbo = B_KMAJOR ? kD_LBO : kB_LBO, sbo = B_KMAJOR ? kD_SBO : kB_SBO;
-      const uint32_t b_base = smem_u32(src) + (uint32_t)c.gid * 2 * sbo;  // the group's 16 clip columns = two 8-groups
-      const UmmaDescBase b1 = umma_desc_base(b_base, lbo, sbo), b2 = umma_desc_base(b_base + src_stride, lbo, sbo);
-      const uint32_t d = c.tmem + kT_D + 16 * c.gid, a1 = c.tmem + kT_W + WT<L, FWD>::p1, a2 = c.tmem + kT_W + WT<L, FWD>::p2;
+      const UmmaDescBase b = umma_desc_base(smem_u32(src) + (uint32_t)c.gid * 4 * sbo, lbo, sbo);  // the group's four 8-groups
+      const uint32_t d = c.tmem + kT_D + 32 * c.gid, a1 = c.tmem + kT_W + WT<L, FWD>::p1, a2 = c.tmem + kT_W + WT<L, FWD>::p2;
 #pragma unroll
-      for (int k = 0; k < (int)WT<L, FWD>::ksteps; ++k) {  // (2,1) | (1,2) | (1,1), smallest first
+      for (int k = 0; k < (int)WT<L, FWD>::ksteps; ++k) {
         const uint32_t bo = k * 2 * lbo;  // K = 16 per instruction: two 8-groups of K
-        if (k == 0) umma_f16_ts_c<false>(d, a2 + 8 * k, umma_desc_at(b1, bo), idesc);
-        else umma_f16_ts_c<true>(d, a2 + 8 * k, umma_desc_at(b1, bo), idesc);
-        umma_f16_ts_c<true>(d, a1 + 8 * k, umma_desc_at(b2, bo), idesc);
-        umma_f16_ts_c<true>(d, a1 + 8 * k, umma_desc_at(b1, bo), idesc);
+        if (k == 0) umma_f16_ts_c<false>(d, a1 + 8 * k, umma_desc_at(b, bo), idesc32);
+        else umma_f16_ts_c<true>(d, a1 + 8 * k, umma_desc_at(b, bo), idesc32);
+        umma_f16_ts_c<true>(d, a2 + 8 * k, umma_desc_at(b, bo), idesc16);
       }
-      umma_commit(&S.bar_mma[c.gid]);
+      umma_commit(&c.S->bar_mma[c.gid]);
     }
     __syncwarp();
   }
+}
+// one dense layer + its epilogue (lane == output feature, 8 clips per thread); ends with the group barrier
+template <int L, bool FWD, bool B_KMAJOR = false, class Epi>
+__device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, int out_rows, Epi epi) {
+  SmemT& S = *c.S;
+  tc_issue<L, FWD, B_KMAJOR>(c, src);
   const int quarter = c.wg & 3, half = c.wg >> 2;
   if (quarter * 32 < out_rows) {
     mbar_wait(&S.bar_mma[c.gid], c.phase);
-    tc_fence_after();
-    float v[EC];
-    tmem_ld8(c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(16 * c.gid + EC * half), v);
+      tc_fence_after();
+    float v[EC], w[EC];
+    const uint32_t t = c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(32 * c.gid + EC * half);
+    tmem_ld8(t, v);
+    tmem_ld8(t + 16, w);
     tmem_ld_wait();
+  #pragma unroll
+    for (int i = 0; i < EC; ++i) v[i] += w[i];
     const int k = quarter * 32 + c.lane;
     if (k < out_rows) epi(k, half, v);
+    tc_fence_before();
+    }
+  fence_proxy_async();
+  c.phase ^= 1u;
+  group_sync(c.gid);
+}
+
+// the same for a layer with at most 64 output rows whose weight rows are REPLICATED in the upper 64 lanes of the tensor-memory operand:
+// all eight warps of the group take part, lane quarters 0 / 1 on clips 0..3 of their 8-clip half, quarters 2 / 3 (the replicas) on
+// clips 4..7 -- four clips per thread instead of eight halves the dependent chain of the epilogue (the longest part of a layer)
+template <int L, bool FWD, bool B_KMAJOR = false, class Epi>
+__device__ __forceinline__ void tc_layer4(Ctx& c, const unsigned char* src, int out_rows, Epi epi) {
+  SmemT& S = *c.S;
+  tc_issue<L, FWD, B_KMAJOR>(c, src);
+  const int quarter = c.wg & 3, half = c.wg >> 2, sub = quarter >> 1;
+  if ((quarter & 1) * 32 < out_rows) {
+    mbar_wait(&S.bar_mma[c.gid], c.phase);
+    tc_fence_after();
+    float v[4], w[4];
+    const uint32_t t = c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(32 * c.gid + EC * half + 4 * sub);
+    tmem_ld4(t, v);
+    tmem_ld4(t + 16, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += w[i];
+    const int k = (quarter & 1) * 32 + c.lane;
+    if (k < out_rows) epi(k, half, sub, v);
     tc_fence_before();
   }
   fence_proxy_async();
@@ -196,6 +245,8 @@ __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, uint3
   group_sync(c.gid);
 }
 
+// CLOCK: the phase clock / timeline of CTA 0 (profiling level 2) is compiled into a second instantiation only
+template <bool CLOCK>
 __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __grid_constant__ DpFrameArgs A) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemT& S = *reinterpret_cast<SmemT*>(smem_raw);
@@ -211,7 +262,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   if (warp == 0) tmem_alloc(&S.tmem_base, kT_COLS);
   static_assert(offsetof(SmemT, dyimg) == offsetof(SmemT, ping) + sizeof(S.ping) + sizeof(S.pong), "operand images are contiguous");
   for (int i = threadIdx.x; i < (int)(sizeof(S.ping) + sizeof(S.pong) + sizeof(S.dyimg)) / 16; i += kWarps * 32)
-    reinterpret_cast<uint4*>(&S.ping[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);  // pad rows / columns must stay finite
+    reinterpret_cast<uint4*>(&S.ping[0])[i] = make_uint4(0u, 0u, 0u, 0u);  // pad rows / columns must stay finite
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -252,18 +303,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     inv3e[c] = 1.0f / (3.0f * (float)ne);
     lrot9e[c] = A.lambda_rot / (9.0f * (float)ne);
     if (lane < 4) S.groot[n0 + c][lane] = A.grot[cc * 4 + lane];
-    float2 z = make_float2(0.f, 0.f), tl = z;
-    if (lane < DP_L / 2 && valid[c]) {
-      z = reinterpret_cast<const float2*>(A.latent + (size_t)cc * DP_L)[lane];
-      tl = reinterpret_cast<const float2*>(A.target_buf + ((size_t)cc * A.target_rows + A.target_index) * DP_L)[lane];
-    }
-    if (lane < DP_L / 2) {
-      S.st[n0 + c][ST_Z][lane] = z;
-      S.st[n0 + c][ST_TL][lane] = tl;
-      S.st[n0 + c][ST_M][lane] = make_float2(0.f, 0.f);
-      S.st[n0 + c][ST_V][lane] = make_float2(0.f, 0.f);
-      S.st[n0 + c][ST_ZLAST][lane] = z;
-    }
     if (lane == 0) {
       S.prev[n0 + c] = 10000000.0;
       S.loss[n0 + c][0] = S.loss[n0 + c][1] = S.loss[n0 + c][2] = __int_as_float(0x7f800000);
@@ -289,10 +328,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
         S.trk[n0 + c][3][j] = make_float4(tr[6], tr[7], tr[8], 0.f);
       }
     }
-    if (lane < DP_L / 2) {  // latent -> B operand of the first layer
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, z.x);
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, z.y);
+  }
+  if (lane < DP_L) {  // optimiser state of the pair; latent -> B operand of the first layer
+    float2 z = make_float2(0.f, 0.f), tl = z;
+    if (valid[0]) {
+      z.x = A.latent[(size_t)clip0 * DP_L + lane];
+      tl.x = A.target_buf[((size_t)clip0 * A.target_rows + A.target_index) * DP_L + lane];
     }
+    if (valid[1]) {
+      z.y = A.latent[(size_t)(clip0 + 1) * DP_L + lane];
+      tl.y = A.target_buf[((size_t)(clip0 + 1) * A.target_rows + A.target_index) * DP_L + lane];
+    }
+    S.st[warp][ST_Z][lane] = z;
+    S.st[warp][ST_TL][lane] = tl;
+    S.st[warp][ST_M][lane] = make_float2(0.f, 0.f);
+    S.st[warp][ST_V][lane] = make_float2(0.f, 0.f);
+    S.st[warp][ST_ZLAST][lane] = z;
+    store_piece_pair(S.ping, lane, gid, 2 * wg, z.x, z.y);
   }
   const P2 inv3e2 = mk2(inv3e[0], inv3e[1]), lrot9e2 = mk2(lrot9e[0], lrot9e[1]);
   __syncwarp();
@@ -304,43 +356,27 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
 
   const FkLaneIdx lane_idx = fk_lane_idx(M, lane);  // skeleton indices of this lane, in registers for the whole launch
   constexpr float wsc = 1.0f / kWScale;  // undoes the weight-image scaling
-  const int cg0 = 2 * gid;               // first clip 8-group of this group in the activation images
-  unsigned neg0 = 0, neg1 = 0;           // LeakyReLU slope bits of (feature k, this thread's 8 clips) for the backward pass
+  const int slot0 = 4 * gid;             // first 8-group (piece 1) of this group in the activation images
+  unsigned neg0 = 0, neg1 = 0;           // LeakyReLU slope bits of (feature k, this thread's 4 clips) for the backward pass
   auto forward = [&]() {
-    tc_layer<0, true>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
+    tc_layer4<0, true>(ctx, S.ping, DP_H0, [&](int k, int half, int sub, float (&v)[4]) {
       const float b = M.b0[k];
       neg0 = 0;
 #pragma unroll
-      for (int i = 0; i < EC; ++i) { v[i] = fmaf(v[i], wsc, b); neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces(&S.pong[0][0], kPongBytes, k, cg0 + half, v);
+      for (int i = 0; i < 4; ++i) { v[i] = fmaf(v[i], wsc, b); neg0 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces4(S.pong, k, slot0 + half, sub, v);
     });
-    tc_layer<1, true>(ctx, &S.pong[0][0], kPongBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
+    tc_layer4<1, true>(ctx, S.pong, DP_H1, [&](int k, int half, int sub, float (&v)[4]) {
       const float b = M.b1[k];
       neg1 = 0;
 #pragma unroll
-      for (int i = 0; i < EC; ++i) { v[i] = fmaf(v[i], wsc, b); neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
-      store_pieces(&S.ping[0][0], kPingBytes, k, cg0 + half, v);
+      for (int i = 0; i < 4; ++i) { v[i] = fmaf(v[i], wsc, b); neg1 |= (v[i] > 0.f ? 0u : 1u) << i; v[i] = lrelu(v[i]); }
+      store_pieces4(S.ping, k, slot0 + half, sub, v);
     });
-    tc_layer<2, true>(ctx, &S.ping[0][0], kPingBytes, DP_Y, [&](int k, int half, float (&v)[EC]) {
+    tc_layer<2, true>(ctx, S.ping, DP_Y, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b2[k];
 #pragma unroll
-      for (int i = 0; i < EC; ++i) S.ybuf[8 * (cg0 + half) + i][k] = fmaf(v[i], wsc, b);
-    });
-  };
-  auto backward = [&]() {  // dL/dy pieces were written by the kinematics warps (EmitDyPieces)
-    tc_layer<2, false, true>(ctx, &S.dyimg[0][0], kDyBytes, DP_H1, [&](int k, int half, float (&v)[EC]) {
-#pragma unroll
-      for (int i = 0; i < EC; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
-      store_pieces(&S.ping[0][0], kPingBytes, k, cg0 + half, v);
-    });
-    tc_layer<1, false>(ctx, &S.ping[0][0], kPingBytes, DP_H0, [&](int k, int half, float (&v)[EC]) {
-#pragma unroll
-      for (int i = 0; i < EC; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f * wsc : wsc;
-      store_pieces(&S.pong[0][0], kPongBytes, k, cg0 + half, v);
-    });
-    tc_layer<0, false>(ctx, &S.pong[0][0], kPongBytes, DP_L, [&](int k, int half, float (&v)[EC]) {
-#pragma unroll
-      for (int i = 0; i < EC; ++i) S.zgrad[8 * (cg0 + half) + i][k] = v[i] * (wsc * S.bscale[8 * (cg0 + half) + i]);
+      for (int i = 0; i < EC; ++i) S.ybuf[16 * gid + 8 * half + i][k] = fmaf(v[i], wsc, b);
     });
   };
 
@@ -348,112 +384,154 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   // early-stop test of the NEXT iteration, evaluated right after each Adam step (initial losses are +inf, initial increment 1)
   bool active[CPW] = {valid[0] && 1.0 > A.min_incr, valid[1] && 1.0 > A.min_incr};
   const float lt_scale = A.lambda_t * (1.0f / (float)DP_L);
-  const bool clocked = A.phase_cycles != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool clocked = CLOCK && A.phase_cycles != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   long long tick = clocked ? clock64() : 0;
   auto phase_done = [&](int i) {
-    if (clocked) {
+    if (CLOCK && clocked) {
       const long long now = clock64();
       A.phase_cycles[i] += (unsigned long long)(now - tick);
       tick = now;
     }
   };
+  // optional timeline of both groups over iterations 40..43 (scripts/timeline.py): six stamps per group and iteration
+  const bool tl_on = CLOCK && A.phase_cycles != nullptr && blockIdx.x == 0 && wg == 0 && lane == 0;
+  auto stamp = [&](int it, int k) {
+    if (CLOCK && tl_on && it >= 40 && it < 44) A.phase_cycles[16 + gid * 24 + (it - 40) * 6 + k] = (unsigned long long)clock64();
+  };
   for (int it = 0; it < A.max_iter; ++it) {
-    if (!group_or(gid, active[0] || active[1])) break;  // also publishes the latent pieces written by the Adam lanes
-    if (lane == 0) {  // the Adam phase reads two table entries: pull their lines into L1 now instead of stalling there
+    if (!group_or(gid, active[0] || active[1])) break;  // also publishes the latent pieces written by the Adam epilogue
+    if (lane == 0) {  // the Adam epilogue reads two table entries: pull their lines into L1 now instead of stalling there
       asm volatile("prefetch.global.L1 [%0];" ::"l"(A.adam_tab + it));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(A.adam_tab + A.max_iter + it));
     }
     phase_done(3);
+    stamp(it, 0);
     forward();
     phase_done(0);
+    stamp(it, 1);
     float nlp[CPW] = {0.f, 0.f}, nlr[CPW] = {0.f, 0.f};
     if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
-      // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is written)
+      // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is read)
       const FkOut2 o = fk_loss2<true, false, true>(M, lane_idx, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0][0], &S.trk[n0 + 1][0][0], &S.groot[n0][0],
                                                    &S.fkscr[warp][0], inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0],
-                                                   EmitDyPieces{&S.dyimg[0][0], n0, lane});
+                                                   EmitDyPieces{S.dyimg, gid, 2 * wg, lane});
       phase_done(4);
       if (active[0]) { nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x; }
       if (active[1]) { nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y; }
     }
+    stamp(it, 2);
     fence_proxy_async();  // the dL/dy pieces are read by the tensor core (async proxy)
     group_sync(gid);
     phase_done(1);
-    backward();
-    phase_done(2);
-    const float step_size = A.adam_tab[it], inv_bc2s = A.adam_tab[A.max_iter + it];  // lr/(1-b1^k), 1/sqrt(1-b2^k)
-    {  // latent loss, Adam and early-stop bookkeeping of BOTH clips in one pass: clip 0 on lanes 0..11, clip 1 on lanes 16..27
-      const int c = lane >> 4, j = lane & 15, n = n0 + c;
-      const bool lat = j < DP_L / 2;
-      const bool act = c ? active[1] : active[0];
-      const float my_lp = c ? nlp[1] : nlp[0], my_lr = c ? nlr[1] : nlr[0];
-      float2 z = make_float2(0.f, 0.f), tl = z;
-      if (lat) { z = S.st[n][ST_Z][j]; tl = S.st[n][ST_TL][j]; }
-      const float dx = z.x - tl.x, dy = z.y - tl.y;
-      float ssq = fmaf(dx, dx, dy * dy);
+    stamp(it, 3);
+    // backward layers; dL/dy pieces were written by the kinematics warps (EmitDyPieces)
+    tc_layer4<2, false, true>(ctx, S.dyimg, DP_H1, [&](int k, int half, int sub, float (&v)[4]) {
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);  // sums stay inside each 16-lane half
-      const float nlt = ssq * lt_scale;
-      float gx = 0.f, gy = 0.f;
-      if (lat) {
-        gx = fmaf(2.0f * lt_scale, dx, S.zgrad[n][2 * j]);
-        gy = fmaf(2.0f * lt_scale, dy, S.zgrad[n][2 * j + 1]);
+      for (int i = 0; i < 4; ++i) v[i] *= ((neg1 >> i) & 1u) ? 0.2f * wsc : wsc;
+      store_pieces4(S.ping, k, slot0 + half, sub, v);
+    });
+    tc_layer4<1, false>(ctx, S.ping, DP_H0, [&](int k, int half, int sub, float (&v)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] *= ((neg0 >> i) & 1u) ? 0.2f * wsc : wsc;
+      store_pieces4(S.pong, k, slot0 + half, sub, v);
+    });
+    phase_done(2);
+    stamp(it, 4);
+    // last backward layer (dL/dz = W_0^T dL/dh0) with the optimiser step as its epilogue.  The 24 rows of W_0^T are replicated in all
+    // four lane quarters of the tensor-memory operand, so EVERY warp of the group reads dL/dz of its own clip pair (lane == latent
+    // feature, two accumulator columns) and does the pair's Adam step, latent loss and early-stop bookkeeping -- no fp32 staging
+    // of dL/dz, no separate optimiser phase behind another group barrier.  Everything that does not depend on dL/dz (state loads,
+    // the latent loss and its warp sum) is done while the MMAs are in flight.
+    tc_issue<0, false>(ctx, S.pong);
+    {
+      const bool lat = lane < DP_L;
+      float2 z = make_float2(0.f, 0.f), tl = z, am = z, av = z;
+      if (lat) { z = S.st[warp][ST_Z][lane]; tl = S.st[warp][ST_TL][lane]; am = S.st[warp][ST_M][lane]; av = S.st[warp][ST_V][lane]; }
+      const float step_size = A.adam_tab[it], inv_bc2s = A.adam_tab[A.max_iter + it];  // lr/(1-b1^k), 1/sqrt(1-b2^k)
+      const float us0 = wsc * S.bscale[n0], us1 = wsc * S.bscale[n0 + 1];               // undo the weight and dL/dy scalings
+      const double prev0 = S.prev[n0], prev1 = S.prev[n0 + 1];
+      const float dx = z.x - tl.x, dy = z.y - tl.y;
+      float s0 = dx * dx, s1 = dy * dy;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {  // lanes >= 24 hold zeros; every lane ends with the same two sums
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       }
-      if (A.trace && act) {
-        float* row = A.trace + ((size_t)(clip0 + c) * A.trace_iters + it) * 52;
-        if (lat) {
-          reinterpret_cast<float2*>(row)[j] = z;
-          reinterpret_cast<float2*>(row + DP_L)[j] = make_float2(gx, gy);
+      const float nlt0 = s0 * lt_scale, nlt1 = s1 * lt_scale;
+      mbar_wait(&S.bar_mma[gid], ctx.phase);
+      tc_fence_after();
+      float d1[2], d2[2];
+      const uint32_t t = tmem + ((uint32_t)((wg & 3) * 32) << 16) + kT_D + (uint32_t)(32 * gid + 2 * wg);
+      tmem_ld2(t, d1);
+      tmem_ld2(t + 16, d2);
+      tmem_ld_wait();
+      tc_fence_before();
+      ctx.phase ^= 1u;
+      const float gx = fmaf(2.0f * lt_scale, dx, (d1[0] + d2[0]) * us0), gy = fmaf(2.0f * lt_scale, dy, (d1[1] + d2[1]) * us1);
+      if (A.trace && lat) {
+        if (active[0]) {
+          float* row = A.trace + ((size_t)clip0 * A.trace_iters + it) * 52;
+          row[lane] = z.x; row[DP_L + lane] = gx;
+          if (lane == 0) { row[48] = nlp[0]; row[49] = nlr[0]; row[50] = nlt0; row[51] = 1.0f; }
         }
-        if (j == 0) { row[48] = my_lp; row[49] = my_lr; row[50] = nlt; row[51] = 1.0f; }
+        if (active[1]) {
+          float* row = A.trace + ((size_t)(clip0 + 1) * A.trace_iters + it) * 52;
+          row[lane] = z.y; row[DP_L + lane] = gy;
+          if (lane == 0) { row[48] = nlp[1]; row[49] = nlr[1]; row[50] = nlt1; row[51] = 1.0f; }
+        }
       }
       if (A.eval_only) {
-        if (act && lat) reinterpret_cast<float2*>(A.eval_grad + (size_t)(clip0 + c) * DP_L)[j] = make_float2(gx, gy);
-      } else if (act && lat) {
-        float2 am = S.st[n][ST_M][j], av = S.st[n][ST_V][j];
-        am.x = fmaf(0.1f, gx - am.x, am.x);
-        am.y = fmaf(0.1f, gy - am.y, am.y);
-        av.x = av.x * 0.999f + (0.001f * gx) * gx;
-        av.y = av.y * 0.999f + (0.001f * gy) * gy;
-        S.st[n][ST_M][j] = am;
-        S.st[n][ST_V][j] = av;
-        S.st[n][ST_ZLAST][j] = z;  // the frame's output is decoded from the last EVALUATED latent
-        z.x += __fdividef(-step_size * am.x, fmaf(fast_sqrt(av.x), inv_bc2s, 1e-8f));
-        z.y += __fdividef(-step_size * am.y, fmaf(fast_sqrt(av.y), inv_bc2s, 1e-8f));
-        S.st[n][ST_Z][j] = z;
+        if (lat && active[0]) A.eval_grad[(size_t)clip0 * DP_L + lane] = gx;
+        if (lat && active[1]) A.eval_grad[(size_t)(clip0 + 1) * DP_L + lane] = gy;
+      } else if (lat) {
+        // branch-free: both clips are stepped, a stopped (or padding) clip keeps its state through the selects
+        const float2 zl = S.st[warp][ST_ZLAST][lane];
+        const float mx = fmaf(0.1f, gx - am.x, am.x), my = fmaf(0.1f, gy - am.y, am.y);
+        const float vx = av.x * 0.999f + (0.001f * gx) * gx, vy = av.y * 0.999f + (0.001f * gy) * gy;
+        // MUFU square root / reciprocal without the denormal range extension: a denormal second moment is far below eps = 1e-8
+        const float ux = (-step_size * mx) * rcp_ftz(fmaf(sqrt_ftz(vx), inv_bc2s, 1e-8f));
+        const float uy = (-step_size * my) * rcp_ftz(fmaf(sqrt_ftz(vy), inv_bc2s, 1e-8f));
+        const bool a0 = active[0], a1 = active[1];
+        S.st[warp][ST_M][lane] = make_float2(a0 ? mx : am.x, a1 ? my : am.y);
+        S.st[warp][ST_V][lane] = make_float2(a0 ? vx : av.x, a1 ? vy : av.y);
+        S.st[warp][ST_ZLAST][lane] = make_float2(a0 ? z.x : zl.x, a1 ? z.y : zl.y);  // the output is decoded from the last EVALUATED latent
+        z.x = a0 ? z.x + ux : z.x;
+        z.y = a1 ? z.y + uy : z.y;
+        S.st[warp][ST_Z][lane] = z;
       }
       // the latent rows of the ping image were overwritten by the a1 / dL/dh1 pieces of this iteration: restore them for
       // EVERY clip (stopped and padding clips included) so that no column ever feeds back on its own garbage -- a
       // non-finite value in a K-padding row would poison the column through 0 x NaN
-      if (lat) {
-        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * j, n, z.x);
-        store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * j + 1, n, z.y);
+      if (lat) store_piece_pair(S.ping, lane, gid, 2 * wg, z.x, z.y);
+      fence_proxy_async();
+      // early-stop bookkeeping: every lane holds the same (warp-uniform) numbers
+      const float total0 = (nlp[0] + nlr[0]) + nlt0, total1 = (nlp[1] + nlr[1]) + nlt1;
+      const double incr0 = prev0 - (double)total0, incr1 = prev1 - (double)total1;
+      if (lane == 0) {
+        if (active[0]) {
+          S.prev[n0] = (double)total0;
+          S.loss[n0][0] = nlp[0]; S.loss[n0][1] = nlr[0]; S.loss[n0][2] = nlt0;
+          S.iters[n0] += 1;
+        }
+        if (active[1]) {
+          S.prev[n0 + 1] = (double)total1;
+          S.loss[n0 + 1][0] = nlp[1]; S.loss[n0 + 1][1] = nlr[1]; S.loss[n0 + 1][2] = nlt1;
+          S.iters[n0 + 1] += 1;
+        }
       }
-      const float total = (my_lp + my_lr) + nlt;
-      const double incr = S.prev[n] - (double)total;
+      active[0] = active[0] && ((double)nlp[0] > A.eps_pos || (double)nlr[0] > A.eps_rot) && (incr0 > A.min_incr);
+      active[1] = active[1] && ((double)nlp[1] > A.eps_pos || (double)nlr[1] > A.eps_rot) && (incr1 > A.min_incr);
       __syncwarp();
-      if (act && j == 0) {
-        S.prev[n] = (double)total;
-        S.loss[n][0] = my_lp; S.loss[n][1] = my_lr; S.loss[n][2] = nlt;
-        S.iters[n] += 1;
-      }
-      const bool next = act && ((double)my_lp > A.eps_pos || (double)my_lr > A.eps_rot) && (incr > A.min_incr);
-      const unsigned votes = __ballot_sync(0xffffffffu, next);
-      active[0] = votes & 1u;
-      active[1] = (votes >> 16) & 1u;
     }
-    fence_proxy_async();
+    stamp(it, 5);
   }
 
   // ---- frame epilogue (drag_pose.py:369-414) from the LAST EVALUATED latent (pre-step)
   __syncwarp();
-#pragma unroll
-  for (int c = 0; c < CPW; ++c)
-    if (lane < DP_L / 2) {
-      const float2 zl = S.st[n0 + c][ST_ZLAST][lane];
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane, n0 + c, zl.x);
-      store_piece_scalar(&S.ping[0][0], kPingBytes, 2 * lane + 1, n0 + c, zl.y);
-    }
+  if (lane < DP_L) {
+    const float2 zl = S.st[warp][ST_ZLAST][lane];
+    store_piece_pair(S.ping, lane, gid, 2 * wg, zl.x, zl.y);
+  }
   fence_proxy_async();
   group_sync(gid);
   forward();
@@ -495,9 +573,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     __syncwarp();
     const int hs = M.height_slot[lane];
     if (hs >= 0) A.height_buf[((size_t)clip * DP_PAST + A.ring_head) * DP_NH + hs] = p[1] + gp[1];
-    if (lane < DP_L / 2) {
-      reinterpret_cast<float2*>(A.latent_buf + ((size_t)clip * DP_PAST + A.ring_head) * DP_L)[lane] = S.st[n0 + c][ST_ZLAST][lane];
-      reinterpret_cast<float2*>(A.latent + (size_t)clip * DP_L)[lane] = S.st[n0 + c][ST_Z][lane];
+    if (lane < DP_L) {
+      const float2 zl = S.st[warp][ST_ZLAST][lane], zn = S.st[warp][ST_Z][lane];
+      A.latent_buf[((size_t)clip * DP_PAST + A.ring_head) * DP_L + lane] = c ? zl.y : zl.x;
+      A.latent[(size_t)clip * DP_L + lane] = c ? zn.y : zn.x;
     }
     if (lane == 0) {
 #pragma unroll
@@ -529,15 +608,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
 }  // namespace
 
 cudaError_t dp_frame_tc16_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream) {
-  static std::atomic<unsigned long long> configured{0};
+  static std::atomic<unsigned long long> configured{0}, configured_clk{0};
   const size_t smem = sizeof(SmemT) + 1024;
-  if (cudaError_t e = dp_ensure_smem(dp_frame_tc16_kernel, smem, configured); e != cudaSuccess) return e;
+  const bool clk = args.phase_cycles != nullptr;
+  if (cudaError_t e = clk ? dp_ensure_smem(dp_frame_tc16_kernel<true>, smem, configured_clk) : dp_ensure_smem(dp_frame_tc16_kernel<false>, smem, configured);
+      e != cudaSuccess)
+    return e;
   // spread the clips over every SM: 4096 clips -> 28 per CTA (two groups of 14) on 147 SMs
   DpFrameArgs a = args;
   int cpc = (args.n_clips + num_sms - 1) / num_sms;
   cpc = cpc < 1 ? 1 : (cpc > NC ? NC : cpc);
   if (args.n_clips > num_sms * NC) cpc = NC;  // several waves anyway: use full tiles
   a.clips_per_cta = cpc;
-  dp_frame_tc16_kernel<<<(args.n_clips + cpc - 1) / cpc, kWarps * 32, smem, stream>>>(a);
+  const int grid = (args.n_clips + cpc - 1) / cpc;
+  if (clk) dp_frame_tc16_kernel<true><<<grid, kWarps * 32, smem, stream>>>(a);
+  else dp_frame_tc16_kernel<false><<<grid, kWarps * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

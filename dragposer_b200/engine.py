@@ -306,6 +306,13 @@ class BatchedDragPose:
         _lib.check(self.lib.dp_engine_get_phase_cycles(self.h, out))
         return [int(v) for v in out]
 
+    def timeline(self):
+        """Stamps (device clock) of the two clip groups of CTA 0 over iterations 40..43 of the last frame run under set_profiling(2):
+        array [group][iteration][loop top, forward, kinematics, barrier, two backward layers, last layer + Adam] (include/dp_engine.h)."""
+        out = (C.c_ulonglong * 48)()
+        _lib.check(self.lib.dp_engine_get_timeline(self.h, out))
+        return np.array(list(out), dtype=np.int64).reshape(2, 4, 6)
+
     def profile(self):
         """(ms in the temporal predictor, ms in the frame kernel, frames) since set_profiling(True)."""
         a, b, n = C.c_double(0), C.c_double(0), C.c_longlong(0)

@@ -203,6 +203,10 @@ int dp_engine_get_profile(dp_engine* e, double* ms_predictor, double* ms_frame_k
  * 8 counters: [0] decoder forward, [1] dL/dy scaling + block barrier after the kinematics, [2] decoder backward,
  * [3] Adam + bookkeeping + loop barrier, [4] kinematics + loss + adjoint pass, [5..7] reserved (0). */
 int dp_engine_get_phase_cycles(dp_engine* e, unsigned long long* cycles8);
+/* Timeline of the two clip groups of CTA 0 over iterations 40..43 of the last frame run at profiling level 2 (device clock64):
+ * stamps48[(group * 4 + iteration - 40) * 6 + k], k = loop top, forward done, kinematics done, barrier after the kinematics,
+ * first two backward layers done, last backward layer + Adam done.  scripts/timeline.py prints it. */
+int dp_engine_get_timeline(dp_engine* e, unsigned long long* stamps48);
 
 /* Clip start-up on the device.  Folded pose-VAE encoder: three dense layers + the mu / logvar heads
  * (autoencoder.py:136-143 folded; python: model.PoseModel.enc_*), HOST pointers, row-major (out,in) like the decoder. */

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from dragposer_b200 import model, synthetic
 from dragposer_b200.engine import BatchedDragPose, RunOptions
 
-B, T, ITERS = 4096, 6, 100
+B, T, ITERS = (int(sys.argv[1]) if len(sys.argv) > 1 else 4096), 6, 100
 npz = os.path.join(ROOT, "tests/golden/model_dancedb.npz")
 pm = model.load_folded_npz(npz); off = np.load(npz)["offsets"]
 tm = model.temporal_from_state(model.random_temporal_state(2222))
