@@ -125,12 +125,15 @@ DP_DI FkLaneIdx fk_lane_idx(const MODEL& M, int lane) {
 }
 DP_DI int fk_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
 
-// ybuf* / trk*: the two clips' 96-float y rows (dL/dy is written in place) and tracker tables -- structure of arrays, float4
-// [4][32] = {tp.xyz w_pos | TR row 0, w_rot | TR row 1 | TR row 2} x lane, so that a warp's 16-byte loads are bank-conflict free
-// (the array-of-structures rows of dp_fk.cuh are 64 bytes apart: four-way conflicts, 96 of the 214 shared-memory wavefronts of a
-// pass in the round-1 profile); groot: their previous world
-// root rotations, 2 x 4 floats in shared memory (re-read where needed instead of held in registers); scr: 16 float2 of
-// per-pair scratch for the warp-uniform R_0, r and d, parked in shared memory between the forward and the adjoint half.
+// All per-clip inputs of a warp's clip PAIR are stored interleaved, so that a 16-byte shared-memory load delivers two packed operands
+// (.x first clip, .y second clip) straight into aligned register pairs -- no MOVs to assemble them (48 of the ~1080 instructions of a
+// pass in the round-2 profile):
+//   y2    float4 [2][24]: [0][j] = (y[4j] a, y[4j] b, y[4j+1] a, y[4j+1] b), [1][j] = the same for y[4j+2], y[4j+3]; slot j = 22 holds
+//         the root displacement y[88..90].  Lane j reads its two float4 at a 16-byte lane stride: conflict free.
+//   trk2  float4 [8][32]: tracker tables, structure of arrays: rows 2r / 2r + 1 are the packed halves of
+//         {tp.xyz w_pos | TR row 0, w_rot | TR row 1 | TR row 2}[r] x lane, i.e. [2r][j] = (x a, x b, y a, y b), [2r+1][j] = (z a, z b, w a, w b).
+//   groot2 float2 [4]: the pair's previous world root rotations (wxyz); scr: 16 float2 of per-pair scratch for the warp-uniform R_0, r
+//         and d, parked in shared memory between the forward and the adjoint half.
 // SCALE (fp16 tensor-core path): dL/dy of each clip is multiplied by the exact power of two that brings its largest
 // component into [16, 32) before it is written; inv_scale[0..1] receive the two inverse factors.
 // The adjoint hands dL/dy to `emit(o, db)`, called convergently by all 32 lanes: o[i] = dL/dy[4 lane + i] of the two clips (zeros on
@@ -139,20 +142,19 @@ struct FkEmitNone {
   DP_DI void operator()(const P2 (&)[4], const P2 (&)[3]) const {}
 };
 template <bool ADJOINT, bool EPILOGUE, bool SCALE = false, class MODEL, class EMIT = FkEmitNone>
-DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float* __restrict__ ybuf_a, const float* __restrict__ ybuf_b, const float4* __restrict__ trk_a,
-                      const float4* __restrict__ trk_b, const float* __restrict__ groot, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
+DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float4* __restrict__ y2, const float4* __restrict__ trk2,
+                      const float2* __restrict__ groot2, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
                       P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr, EMIT emit = EMIT()) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 ya = is_joint ? reinterpret_cast<const float4*>(ybuf_a)[lane] : zero4;
-  const float4 yb = is_joint ? reinterpret_cast<const float4*>(ybuf_b)[lane] : zero4;
-  const float4 da = reinterpret_cast<const float4*>(ybuf_a)[DP_J], db = reinterpret_cast<const float4*>(ybuf_b)[DP_J];
+  const float4 y01 = is_joint ? y2[lane] : zero4, y23 = is_joint ? y2[24 + lane] : zero4;
+  const float4 d01 = y2[DP_J], d23 = y2[24 + DP_J];
   const float4 mq = is_joint ? reinterpret_cast<const float4*>(M.mean_q)[lane] : make_float4(1.f, 0.f, 0.f, 0.f);
   const float4 sq = is_joint ? reinterpret_cast<const float4*>(M.std_q)[lane] : zero4;
   __syncwarp();
-  const P2 u[4] = {mad(sq.x, mk2(ya.x, yb.x), splat(mq.x)), mad(sq.y, mk2(ya.y, yb.y), splat(mq.y)),
-                   mad(sq.z, mk2(ya.z, yb.z), splat(mq.z)), mad(sq.w, mk2(ya.w, yb.w), splat(mq.w))};
+  const P2 u[4] = {mad(sq.x, mk2(y01.x, y01.y), splat(mq.x)), mad(sq.y, mk2(y01.z, y01.w), splat(mq.y)),
+                   mad(sq.z, mk2(y23.x, y23.y), splat(mq.z)), mad(sq.w, mk2(y23.z, y23.w), splat(mq.w))};
   const P2 n = sqrt2(mad(u[3], u[3], mad(u[2], u[2], mad(u[1], u[1], u[0] * u[0]))));
   const P2 inv = rcp2(n + splat(1e-8f));
   const P2 q[4] = {u[0] * inv, u[1] * inv, u[2] * inv, u[3] * inv};
@@ -161,8 +163,8 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float* __restric
   for (int i = 0; i < 4; ++i) q0[i] = shfl(q[i], 0);
   P2 r[4];
   {
-    const float4 ga = reinterpret_cast<const float4*>(groot)[0], gb = reinterpret_cast<const float4*>(groot)[1];
-    const P2 g[4] = {mk2(ga.x, gb.x), mk2(ga.y, gb.y), mk2(ga.z, gb.z), mk2(ga.w, gb.w)};
+    const float4 g01 = reinterpret_cast<const float4*>(groot2)[0], g23 = reinterpret_cast<const float4*>(groot2)[1];
+    const P2 g[4] = {mk2(g01.x, g01.y), mk2(g01.z, g01.w), mk2(g23.x, g23.y), mk2(g23.z, g23.w)};
     quat_mul(g, q0, r);  // world root rotation (drag_pose.py:88-92)
   }
   P2 R0[9], Mj[9], R[9];
@@ -173,8 +175,8 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float* __restric
     quat_to_mat(qj, Mj);
   }
   mat_mul(R0, Mj, R);  // closed form of utils.py:80-149: R_j = R_0 M(q_j)
-  const P2 d[3] = {mad(M.std_d[0], mk2(da.x, db.x), splat(M.mean_d[0])), mad(M.std_d[1], mk2(da.y, db.y), splat(M.mean_d[1])),
-                   mad(M.std_d[2], mk2(da.z, db.z), splat(M.mean_d[2]))};
+  const P2 d[3] = {mad(M.std_d[0], mk2(d01.x, d01.y), splat(M.mean_d[0])), mad(M.std_d[1], mk2(d01.z, d01.w), splat(M.mean_d[1])),
+                   mad(M.std_d[2], mk2(d23.x, d23.y), splat(M.mean_d[2]))};
   // c_j = R_parent o_j ; p_j = sum of c over the ancestor chain (log-step pointer jumping); p_0 = R_0 d (drag_pose.py:102)
   const int par = fk_byte(ix.a, 0);
   const float4 off = *reinterpret_cast<const float4*>(M.off[lane]);
@@ -206,22 +208,22 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float* __restric
   // masked tracker loss (drag_pose.py:116-124); untracked lanes carry zero weights
   P2 ep[3], eR[9], wp, wr;
   {
-    const float4 a = trk_a[lane], b = trk_b[lane];
-    ep[0] = p[0] - mk2(a.x, b.x); ep[1] = p[1] - mk2(a.y, b.y); ep[2] = p[2] - mk2(a.z, b.z);
-    wp = mk2(a.w, b.w);
+    const float4 a = trk2[lane], b = trk2[32 + lane];
+    ep[0] = p[0] - mk2(a.x, a.y); ep[1] = p[1] - mk2(a.z, a.w); ep[2] = p[2] - mk2(b.x, b.y);
+    wp = mk2(b.z, b.w);
   }
   {
-    const float4 a = trk_a[32 + lane], b = trk_b[32 + lane];
-    eR[0] = R[0] - mk2(a.x, b.x); eR[1] = R[1] - mk2(a.y, b.y); eR[2] = R[2] - mk2(a.z, b.z);
-    wr = mk2(a.w, b.w);
+    const float4 a = trk2[64 + lane], b = trk2[96 + lane];
+    eR[0] = R[0] - mk2(a.x, a.y); eR[1] = R[1] - mk2(a.z, a.w); eR[2] = R[2] - mk2(b.x, b.y);
+    wr = mk2(b.z, b.w);
   }
   {
-    const float4 a = trk_a[64 + lane], b = trk_b[64 + lane];
-    eR[3] = R[3] - mk2(a.x, b.x); eR[4] = R[4] - mk2(a.y, b.y); eR[5] = R[5] - mk2(a.z, b.z);
+    const float4 a = trk2[128 + lane], b = trk2[160 + lane];
+    eR[3] = R[3] - mk2(a.x, a.y); eR[4] = R[4] - mk2(a.z, a.w); eR[5] = R[5] - mk2(b.x, b.y);
   }
   {
-    const float4 a = trk_a[96 + lane], b = trk_b[96 + lane];
-    eR[6] = R[6] - mk2(a.x, b.x); eR[7] = R[7] - mk2(a.y, b.y); eR[8] = R[8] - mk2(a.z, b.z);
+    const float4 a = trk2[192 + lane], b = trk2[224 + lane];
+    eR[6] = R[6] - mk2(a.x, a.y); eR[7] = R[7] - mk2(a.z, a.w); eR[8] = R[8] - mk2(b.x, b.y);
   }
   P2 sp = mad(ep[2], ep[2], mad(ep[1], ep[1], ep[0] * ep[0]));
   P2 sr = eR[0] * eR[0];
@@ -303,8 +305,8 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float* __restric
     }
     P2 qb[4];
     if (is_root) {
-      const float4 ga = reinterpret_cast<const float4*>(groot)[0], gb = reinterpret_cast<const float4*>(groot)[1];
-      const P2 gc[4] = {mk2(ga.x, gb.x), mk2(-ga.y, -gb.y), mk2(-ga.z, -gb.z), mk2(-ga.w, -gb.w)};
+      const float4 g01 = reinterpret_cast<const float4*>(groot2)[0], g23 = reinterpret_cast<const float4*>(groot2)[1];
+      const P2 gc[4] = {mk2(g01.x, g01.y), -mk2(g01.z, g01.w), -mk2(g23.x, g23.y), -mk2(g23.z, g23.w)};
       quat_mul(gc, rbp, qb);  // r = g (x) q_0  ->  q0bar = conj(g) (x) rbar
     } else {
       P2 G[9], R0s[9];

@@ -48,13 +48,13 @@ struct SmemT {
   __align__(16) unsigned char ping[kPingBytes];     // z (24) / a1 (60) / dL/dh1 (60)
   __align__(16) unsigned char pong[kPongBytes];     // a0 (40) / dL/dh0 (40)
   __align__(16) unsigned char dyimg[kDyBytes];      // dL/dy (92), K-major
-  __align__(16) float ybuf[NC][96];                 // y (fp32, one row per clip)
+  __align__(16) float4 y2[NC / 2][2][24];           // y (fp32) of a warp's clip pair, interleaved (dp_fk2.cuh)
   float bscale[NC];                                 // 1 / (per-clip power-of-two scale of dL/dy)
-  __align__(16) float4 trk[NC][4][32];              // tracker tables, structure of arrays (dp_fk2.cuh)
+  __align__(16) float4 trk2[NC / 2][8][32];         // tracker tables of a clip pair, interleaved structure of arrays (dp_fk2.cuh)
   // optimiser state of a warp's clip pair, one float2 (.x first clip, .y second) per latent feature:
   // [ST_Z latent | ST_TL target latent | ST_M, ST_V Adam moments | ST_ZLAST last evaluated latent]
   __align__(16) float2 st[NC / 2][5][DP_L];
-  __align__(16) float groot[NC][4];                 // previous world root rotation g (wxyz)
+  __align__(16) float2 groot2[NC / 2][4];           // previous world root rotations g (wxyz) of a clip pair
   __align__(16) float2 fkscr[NC / 2][16];           // per clip pair: R_0, r, d parked between the two halves of the kinematics pass
   double prev[NC];                                  // previous total loss (early stopping compares in double)
   float loss[NC][3];                                // last evaluated lp, lr, lt
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     ne = max(1, min(ne, A.ee_stride));
     inv3e[c] = 1.0f / (3.0f * (float)ne);
     lrot9e[c] = A.lambda_rot / (9.0f * (float)ne);
-    if (lane < 4) S.groot[n0 + c][lane] = A.grot[cc * 4 + lane];
+    if (lane < 4) reinterpret_cast<float*>(&S.groot2[warp][lane])[c] = A.grot[cc * 4 + lane];
     if (lane == 0) {
       S.prev[n0 + c] = 10000000.0;
       S.loss[n0 + c][0] = S.loss[n0 + c][1] = S.loss[n0 + c][2] = __int_as_float(0x7f800000);
@@ -310,9 +310,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     }
     // tracker stream of the clip: lane e loads slot e (all slots in flight at once, neighbouring lanes read neighbouring
     // addresses) and scatters its row to the lane of the joint it tracks; untracked joints keep zero weights
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c == 0) {
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) S.trk[n0 + c][i][lane] = zero4;
+      for (int i = 0; i < 8; ++i) S.trk2[warp][i][lane] = zero4;
+    }
     __syncwarp();
     if (lane < ne) {
       float origin[3] = {0.f, 0.f, 0.f};  // world-absolute targets are taken relative to the clip's current global position
@@ -322,10 +324,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
       const float* tp = A.tgt_pos + ((size_t)cc * A.ee_stride + lane) * 3;
       const float* tr = A.tgt_rot + ((size_t)cc * A.ee_stride + lane) * 9;
       if (j >= 0 && j < DP_J) {
-        S.trk[n0 + c][0][j] = make_float4(tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt.x);
-        S.trk[n0 + c][1][j] = make_float4(tr[0], tr[1], tr[2], wt.y);
-        S.trk[n0 + c][2][j] = make_float4(tr[3], tr[4], tr[5], 0.f);
-        S.trk[n0 + c][3][j] = make_float4(tr[6], tr[7], tr[8], 0.f);
+        // row r of the table = (x, y, z, w): packed halves [2r][j] = (x a, x b, y a, y b), [2r+1][j] = (z a, z b, w a, w b); clip c is the .x / .y half
+        auto put = [&](int r, float x, float y, float z, float w) {
+          float* lo = reinterpret_cast<float*>(&S.trk2[warp][2 * r][j]) + c;
+          float* hi = reinterpret_cast<float*>(&S.trk2[warp][2 * r + 1][j]) + c;
+          lo[0] = x; lo[2] = y; hi[0] = z; hi[2] = w;
+        };
+        put(0, tp[0] - origin[0], tp[1] - origin[1], tp[2] - origin[2], wt.x);
+        put(1, tr[0], tr[1], tr[2], wt.y);
+        put(2, tr[3], tr[4], tr[5], 0.f);
+        put(3, tr[6], tr[7], tr[8], 0.f);
       }
     }
   }
@@ -376,7 +384,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     tc_layer<2, true>(ctx, S.ping, DP_Y, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b2[k];
 #pragma unroll
-      for (int i = 0; i < EC; ++i) S.ybuf[16 * gid + 8 * half + i][k] = fmaf(v[i], wsc, b);
+      for (int i = 0; i < EC; i += 2)  // clips 2p, 2p + 1 of this 8-clip half = pair 8 gid + 4 half + p; feature k = 4 j + c
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(&S.y2[8 * gid + 4 * half + i / 2][(k >> 1) & 1][k >> 2]) + 2 * (k & 1)) =
+            make_float2(fmaf(v[i], wsc, b), fmaf(v[i + 1], wsc, b));
     });
   };
 
@@ -412,8 +422,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     float nlp[CPW] = {0.f, 0.f}, nlr[CPW] = {0.f, 0.f};
     if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
       // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is read)
-      const FkOut2 o = fk_loss2<true, false, true>(M, lane_idx, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0][0], &S.trk[n0 + 1][0][0], &S.groot[n0][0],
-                                                   &S.fkscr[warp][0], inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0],
+      const FkOut2 o = fk_loss2<true, false, true>(M, lane_idx, &S.y2[warp][0][0], &S.trk2[warp][0][0], &S.groot2[warp][0], &S.fkscr[warp][0],
+                                                   inv3e2, lrot9e2, lane, nullptr, nullptr, nullptr, nullptr, &S.bscale[n0],
                                                    EmitDyPieces{S.dyimg, gid, 2 * wg, lane});
       phase_done(4);
       if (active[0]) { nlp[0] = o.lp.v.x; nlr[0] = o.lr.v.x; }
@@ -537,7 +547,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   forward();
   P2 q2[4], r2[4], p2[3], d2[3];
   if (valid[0] || valid[1])
-    fk_loss2<false, true>(M, lane_idx, &S.ybuf[n0][0], &S.ybuf[n0 + 1][0], &S.trk[n0][0][0], &S.trk[n0 + 1][0][0], &S.groot[n0][0], &S.fkscr[warp][0], inv3e2, lrot9e2, lane, q2, r2, p2, d2);
+    fk_loss2<false, true>(M, lane_idx, &S.y2[warp][0][0], &S.trk2[warp][0][0], &S.groot2[warp][0], &S.fkscr[warp][0], inv3e2, lrot9e2, lane, q2, r2, p2, d2);
 #pragma unroll
   for (int c = 0; c < CPW; ++c) {
     if (!valid[c]) continue;
