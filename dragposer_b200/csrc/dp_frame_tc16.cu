@@ -38,6 +38,16 @@ constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LB
 // from 128 to 144 bytes for the same bank reason as kB_LBO.
 constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kD_PIECE = 2 * kD_SBO, kDyBytes = 2 * (NC / 8) * kD_SBO;
 constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scaled per clip into [16, 32) (see dp_frame_tc.cu)
+// Generic-proxy writes of an operand image (st.shared by the epilogue / kinematics / Adam threads) must be ordered before the
+// tensor core's async-proxy reads.  true: the ONE issuing thread executes fence.proxy.async after the group barrier that made the
+// writes visible to it (writer -> barrier -> fence -> tcgen05.mma is a causality chain through the fence; the barrier has drained
+// the stores, so the fence is cheap); false: every writer fences before the barrier (MEMBAR.ALL.CTA with its stores in flight) --
+// the pattern CUTLASS uses, and the default: the issuer-only variant measured 0.664 vs 0.666 ms per frame (scripts/ab_frame.sh),
+// nothing worth leaving the documented pattern for.
+#ifndef DP_ISSUER_FENCE
+#define DP_ISSUER_FENCE 0
+#endif
+constexpr bool kIssuerFence = DP_ISSUER_FENCE != 0;
 enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
 // tensor-memory columns: accumulators of group g at 32 g (16 columns per B piece); then the weight pieces (two K elements per word)
 constexpr uint32_t kT_D = 0, kT_W = 64, kT_COLS = 512;
@@ -175,6 +185,7 @@ __device__ __forceinline__ void tc_issue(Ctx& c, const unsigned char* src) {
   if (c.wg == 0) {
     tc_fence_after();
     if (elect_one()) {
+      if (kIssuerFence) fence_proxy_async();  // see kIssuerFence
       // fp16 x fp16 -> fp32, M 128; bit 16: B is MN-major
       constexpr uint32_t idesc = (1u << 4) | (B_KMAJOR ? 0u : (1u << 16)) | (8u << 24);
       constexpr uint32_t idesc16 = idesc | ((uint32_t)(16 >> 3) << 17), idesc32 = idesc | ((uint32_t)(32 >> 3) << 17);
@@ -213,7 +224,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, int o
     if (k < out_rows) epi(k, half, v);
     tc_fence_before();
     }
-  fence_proxy_async();
+  if (!kIssuerFence) fence_proxy_async();
   c.phase ^= 1u;
   group_sync(c.gid);
 }
@@ -240,7 +251,7 @@ __device__ __forceinline__ void tc_layer4(Ctx& c, const unsigned char* src, int 
     if (k < out_rows) epi(k, half, sub, v);
     tc_fence_before();
   }
-  fence_proxy_async();
+  if (!kIssuerFence) fence_proxy_async();
   c.phase ^= 1u;
   group_sync(c.gid);
 }
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
       if (active[1]) { nlp[1] = o.lp.v.y; nlr[1] = o.lr.v.y; }
     }
     stamp(it, 2);
-    fence_proxy_async();  // the dL/dy pieces are read by the tensor core (async proxy)
+    if (!kIssuerFence) fence_proxy_async();  // the dL/dy pieces are read by the tensor core (async proxy)
     group_sync(gid);
     phase_done(1);
     stamp(it, 3);
@@ -513,7 +524,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
       // EVERY clip (stopped and padding clips included) so that no column ever feeds back on its own garbage -- a
       // non-finite value in a K-padding row would poison the column through 0 x NaN
       if (lat) store_piece_pair(S.ping, lane, gid, 2 * wg, z.x, z.y);
-      fence_proxy_async();
+      if (!kIssuerFence) fence_proxy_async();
       // early-stop bookkeeping: every lane holds the same (warp-uniform) numbers
       const float total0 = (nlp[0] + nlr[0]) + nlt0, total1 = (nlp[1] + nlr[1]) + nlt1;
       const double incr0 = prev0 - (double)total0, incr1 = prev1 - (double)total1;
@@ -542,7 +553,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     const float2 zl = S.st[warp][ST_ZLAST][lane];
     store_piece_pair(S.ping, lane, gid, 2 * wg, zl.x, zl.y);
   }
-  fence_proxy_async();
+  if (!kIssuerFence) fence_proxy_async();
   group_sync(gid);
   forward();
   P2 q2[4], r2[4], p2[3], d2[3];
