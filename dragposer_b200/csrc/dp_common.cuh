@@ -52,15 +52,8 @@ struct __align__(16) DpModelImage {
 };
 static_assert(sizeof(DpModelImage) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
 
-// Model image of the tcgen05 frame kernel: the three folded matrices as bf16 split pieces (x = x1 + x2 [+ x3]) in the
-// canonical no-swizzle UMMA layout -- element (o, i) of layer l at (o/8)*128*(kin/8) + (i/8)*128 + (o%8)*16 + (i%8)*2 --
-// read K-major by the forward GEMMs and MN-major by the backward GEMMs; zero padded to kin x kout (multiples of 16).
-#define DP_TC_CLIPS 32
-#define DP_TC_W0_OFF 0u
-#define DP_TC_W1_OFF 3072u    // W0: 48 rows x 32 cols x 2 B
-#define DP_TC_W2_OFF 9216u    // W1: 64 x 48 x 2 B = 6144
-#define DP_TC_W_BYTES 21504u  // W2: 96 x 64 x 2 B = 12288
-#define DP_TC_PIECES 3
+// Table image of the tcgen05 frame kernel (biases, statistics, skeleton tables; one bulk-TMA copy per CTA).  Its weights do not
+// live here: they are fp16x2 pieces in TENSOR memory, loaded from the [word][lane] image described below.
 struct __align__(16) DpModelImageTC {
   float b0[DP_H0];
   float b1[DP_H1];
@@ -77,17 +70,14 @@ struct __align__(16) DpModelImageTC {
   int32_t last[32];
   int32_t height_slot[32];
   int32_t pad[32];
-  // LAST member: a kernel that uses only the first n pieces copies (and reserves shared memory for) a prefix of the image
-  __align__(16) unsigned char w[DP_TC_PIECES][DP_TC_W_BYTES];
 };
 // fp16x2 weights for the tensor-memory-resident kernel (dp_frame_tc16.cu): 352 32-bit words per TMEM lane, image [word][128 lanes]
 #define DP_TC_TMEM_WORDS 352
-#define DP_TC_IMAGE_BYTES(n_pieces) (sizeof(DpModelImageTC) - (DP_TC_PIECES - (n_pieces)) * DP_TC_W_BYTES)
 static_assert(sizeof(DpModelImageTC) % 16 == 0, "bulk copy needs a multiple of 16 bytes");
 
 struct DpFrameArgs {
   const DpModelImage* model;
-  const DpModelImageTC* model_tc;    // tables + bf16x3 weight pieces (the tensor-memory kernel copies only the table prefix)
+  const DpModelImageTC* model_tc;    // tables of the tcgen05 kernel
   const uint32_t* model_tmem;        // fp16x2 pieces of 16 W and 16 W^T as tensor-memory words [DP_TC_TMEM_WORDS][128]
   int n_clips;
   // carried state (HBM)

@@ -253,36 +253,9 @@ extern "C" int dp_engine_set_pose_model(dp_engine* e, const dp_pose_model* m) {
   while ((1 << I.pad[0]) <= max_depth) ++I.pad[0];  // pointer-jumping rounds: smallest r with 2^r > max depth
   I.pad[1] = max_children;
   CK(cudaMemcpy(e->d_model, raw.data(), raw.size(), cudaMemcpyHostToDevice));
-  {  // tcgen05 image: bf16 split pieces of the same matrices + the same statistics / skeleton tables
+  {  // tcgen05 kernel: the same biases / statistics / skeleton tables, and the weights as a tensor-memory image
     std::vector<unsigned char> raw_tc(sizeof(DpModelImageTC), 0);
     DpModelImageTC& T = *reinterpret_cast<DpModelImageTC*>(raw_tc.data());
-    auto bf16_rn = [](float x) -> uint16_t {  // round-to-nearest-even, what cvt.rn.bf16.f32 does
-      uint32_t u;
-      memcpy(&u, &x, 4);
-      u += 0x7FFFu + ((u >> 16) & 1u);
-      return (uint16_t)(u >> 16);
-    };
-    auto bf16_val = [](uint16_t h) -> float {
-      const uint32_t u = (uint32_t)h << 16;
-      float f;
-      memcpy(&f, &u, 4);
-      return f;
-    };
-    const uint32_t woff[3] = {DP_TC_W0_OFF, DP_TC_W1_OFF, DP_TC_W2_OFF};
-    const int kin[3] = {32, 48, 64};
-    for (int l = 0; l < 3; ++l) {
-      const int K = dims[l], N = dims[l + 1];
-      for (int o = 0; o < N; ++o)
-        for (int i = 0; i < K; ++i) {
-          float r = A[l][o * K + i];
-          const uint32_t at = woff[l] + (o / 8) * 128 * (kin[l] / 8) + (i / 8) * 128 + (o % 8) * 16 + (i % 8) * 2;
-          for (int p = 0; p < DP_TC_PIECES; ++p) {
-            const uint16_t h = bf16_rn(r);
-            memcpy(&T.w[p][at], &h, 2);
-            r -= bf16_val(h);
-          }
-        }
-    }
     memcpy(T.b0, I.b0, sizeof(I.b0)); memcpy(T.b1, I.b1, sizeof(I.b1)); memcpy(T.b2, I.b2, sizeof(I.b2));
     memcpy(T.mean_q, I.mean_q, sizeof(I.mean_q)); memcpy(T.std_q, I.std_q, sizeof(I.std_q));
     memcpy(T.mean_d, I.mean_d, sizeof(I.mean_d)); memcpy(T.std_d, I.std_d, sizeof(I.std_d));

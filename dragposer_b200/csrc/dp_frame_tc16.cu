@@ -54,7 +54,7 @@ constexpr uint32_t kT_D = 0, kT_W = 64, kT_COLS = 512;
 static_assert(kT_W + DP_TC_TMEM_WORDS <= kT_COLS, "weights must fit in tensor memory");
 
 struct SmemT {
-  __align__(16) unsigned char model[DP_TC_IMAGE_BYTES(0)];   // biases, statistics, skeleton tables (no weight pieces)
+  __align__(16) unsigned char model[sizeof(DpModelImageTC)];  // biases, statistics, skeleton tables
   __align__(16) unsigned char ping[kPingBytes];     // z (24) / a1 (60) / dL/dh1 (60)
   __align__(16) unsigned char pong[kPongBytes];     // a0 (40) / dL/dh0 (40)
   __align__(16) unsigned char dyimg[kDyBytes];      // dL/dy (92), K-major
@@ -93,21 +93,6 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {  
 }
 __device__ __forceinline__ void unpack_f16x2(uint32_t p, float& lo_elem, float& hi_elem) {
   asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo_elem), "=f"(hi_elem) : "r"(p));
-}
-// 8 fp32 values (feature k; slot = 4 group + clip half: the 8-group of the first piece) -> the two fp16 pieces of an MN-major image
-__device__ __forceinline__ void store_pieces(unsigned char* img, int k, int slot, const float (&v)[EC]) {
-  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + slot * kB_SBO;
-  uint32_t p1[4], p2[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float x0 = v[2 * i], x1 = v[2 * i + 1];
-    p1[i] = pack_f16x2(x0, x1);
-    float h0, h1;
-    unpack_f16x2(p1[i], h0, h1);
-    p2[i] = pack_f16x2(x0 - h0, x1 - h1);
-  }
-  *reinterpret_cast<uint4*>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-  *reinterpret_cast<uint4*>(dst + kB_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
 }
 // 4 fp32 values (feature k; 8-group `slot`, clips 4 sub .. 4 sub + 3 of it) -> the two fp16 pieces, one 8-byte store each
 __device__ __forceinline__ void store_pieces4(unsigned char* img, int k, int slot, int sub, const float (&v)[4]) {
