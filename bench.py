@@ -42,7 +42,7 @@ KERNEL_NAMES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture whose
 # summary is committed under profiles/ (keyed by decoder path, clips per GPU, tracker config); null for other configurations
-NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 4230656}
+NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 2471424}  # profiles/r2_frame_kernel.md (final capture): 2 470 912 read + 512 written
 
 
 def fixed_opts(cfg):
@@ -452,15 +452,27 @@ def measure(args, trackers, K, W, rank, world, dev, local, clocks=None):
         e2e_s = time.perf_counter() - t0
     else:
         p_tp, p_tr = torch.from_numpy(h_tp).pin_memory(), torch.from_numpy(h_tr).pin_memory()
-        s_tp, s_tr = torch.empty_like(d_tp[0]), torch.empty_like(d_tr[0])  # the step's inputs on the device
+        # the step's inputs on the device, double-buffered: the copy of step t+1 (own stream) runs under the kernels of step t
+        s_tp, s_tr = [torch.empty_like(d_tp[0]) for _ in range(2)], [torch.empty_like(d_tr[0]) for _ in range(2)]
         host_recv = [torch.empty(r.shape, dtype=torch.float32).pin_memory() if r is not None else None for r in recv]
         copy_stream = torch.cuda.Stream(device=dev)
+        in_stream = torch.cuda.Stream(device=dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        n_host_steps = [0]
 
         def step_from_host(t):
-            s_tp.copy_(p_tp[t], non_blocking=True)
-            s_tr.copy_(p_tr[t], non_blocking=True)
-            eng.run_frames_device(1, s_tp, s_tr, d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_rows[t], None,
+            slot = n_host_steps[0] & 1
+            n_host_steps[0] += 1
+            with torch.cuda.stream(in_stream):
+                in_stream.wait_event(ev_done[slot])  # the frame that last read this slot has finished (no-op the first time round)
+                s_tp[slot].copy_(p_tp[t], non_blocking=True)
+                s_tr[slot].copy_(p_tr[t], non_blocking=True)
+                ev_in[slot].record(in_stream)
+            work_stream.wait_event(ev_in[slot])
+            eng.run_frames_device(1, s_tp[slot], s_tr[slot], d_j[t] if variable else d_j, d_w[t] if variable else d_w, d_rows[t], None,
                                   n_ee=d_ne[t] if variable else None, shared=not variable, ee_stride=E, stream=stream, options=opts)
+            ev_done[slot].record(work_stream)
 
         step_from_host(0)
         torch.cuda.synchronize()
@@ -505,8 +517,8 @@ def roofline(m, B, trackers, peaks):
             "frac": achieved_tf / tf32_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((m["path"], B, trackers)), "peak_source": which,
             "kernel_ms_per_launch": m["frame_ms"], "predictor_ms_per_step": m["pred_ms"],
             "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
-            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 7.76, "tp_ff_tc_kernel": 44.2,
-                                            "source": "profiles/r2_frame_kernel.md: sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32, issued ops"},
+            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 8.58, "tp_ff_tc_kernel": 48.6, "tp_attn_tc_kernel": 7.26,
+                                            "source": "profiles/r2_frame_kernel.md, r2_predictor.md: sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32 (issued ops, % of peak sustained elapsed)"},
             "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"}
 
 
