@@ -375,7 +375,7 @@ def measure(args, trackers, K, W, rank, world, dev, local, clocks=None):
 
     # the only collective of the job: the K frames' result rows go to rank 0 in a few chunks, each gather running while the
     # next chunk's frames are computed; only the last chunk's gather is exposed
-    n_chunks = min(4, K) if world > 1 else 0
+    n_chunks = min(10, K) if world > 1 else 0  # two frames per chunk at the default K: only the last chunk (and its D2H in the e2e leg) is exposed
     bounds = [W + (K * i) // n_chunks for i in range(n_chunks + 1)] if n_chunks else []
     recv = [torch.empty((world, bounds[i + 1] - bounds[i], B, dpdist.ROW), dtype=torch.float32, device=dev) if rank == 0 else None
             for i in range(n_chunks)]

@@ -378,3 +378,33 @@ def test_batch_256_clips_vs_oracle(engine_factory, pose_model, model_npz, port_w
                               joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight, **opt)
         np.testing.assert_allclose(p1[0], pose[c], atol=2e-3)
         np.testing.assert_allclose(g1[0], gpos[c], atol=1e-5)
+
+
+def test_clocked_instantiation_is_bitwise_identical_and_timeline_is_ordered(engine_factory, pose_model, model_npz):
+    """The phase clock / timeline of the tcgen05 frame kernel lives in a second template instantiation (profiling level 2): it must
+    produce bit-identical frames, its eight phase counters must be filled, and the stamps of both clip groups of CTA 0 must be
+    ordered in time (loop top < forward < kinematics < barrier < two backward layers < last layer + Adam, iteration after iteration)."""
+    cfg = synthetic.config_6_trackers()
+    B, T = 600, 2
+    wl = synthetic.make_workload(pose_model, model_npz["offsets"], cfg, B, T)
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=0, max_iter=60, stop_eps_pos=-1.0, stop_eps_rot=-1.0,
+              min_loss_incr=-float("inf"), joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight,
+              decoder_path=3)
+    outs = []
+    for level in (0, 2):
+        eng = engine_factory(B)
+        eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+        eng.set_profiling(level)
+        for t in range(T):
+            res = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], **kw)
+        outs.append(res)
+        if level == 2:
+            cyc = eng.phase_cycles()
+            assert all(c > 0 for c in cyc[:5]), cyc
+            tl = eng.timeline()  # [group][iteration 40..43][6 stamps]
+            flat = tl.reshape(2, -1)
+            assert (np.diff(flat, axis=1) > 0).all(), tl
+            period = (tl[:, 1:, 0] - tl[:, :-1, 0]).mean()
+            print(f"clocked kernel: {period:.0f} cycles per iteration, phase counters {cyc[:5]}")
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
