@@ -310,7 +310,7 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
   CK(cudaMemcpy(e->d_mu, means_latent, DP_L * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->d_sigma, stds_latent, DP_L * 4, cudaMemcpyHostToDevice));
   {
-    std::vector<unsigned char> tiles(DP_TC_TILES_BYTES);
+    std::vector<unsigned char> tiles(DP_TC_IMAGE_TOTAL_BYTES);
     for (int l = 0; l < TP_NENC + TP_NDEC; ++l) {
       const TpFF& f = l < TP_NENC ? e->tl.enc[l].ff : e->tl.dec[l - TP_NENC].ff;
       dp_ff_tc_pack(blob + f.w1, blob + f.b1, blob + f.w2, tiles.data() + (size_t)l * FFT_LAYER_BYTES);
@@ -319,6 +319,10 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
       const TpAttn& a = i < TP_NENC ? e->tl.enc[i].sa : (i < TP_NENC + TP_NDEC ? e->tl.dec[i - TP_NENC].sa : e->tl.dec[i - TP_NENC - TP_NDEC].ca);
       dp_attn_tc_pack(blob + a.w_in, blob + a.b_in, blob + a.w_out, blob + a.b_out, tiles.data() + DP_TC_ATT_OFFSET + (size_t)i * ATT_LAYER_BYTES);
     }
+    float* wk_t = reinterpret_cast<float*>(tiles.data() + DP_TC_XA_OFFSET);
+    for (int l = 0; l < TP_NDEC; ++l)
+      for (int d = 0; d < TP_D; ++d)
+        for (int c = 0; c < TP_D; ++c) wk_t[((size_t)l * TP_D + d) * TP_D + c] = blob[e->tl.dec[l].ca.w_in + (size_t)c * 3 * TP_D + TP_D + d];
     if (!e->d_fftiles) CK(cudaMalloc(&e->d_fftiles, tiles.size()));
     CK(cudaMemcpy(e->d_fftiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
   }

@@ -41,6 +41,10 @@ cudaError_t dp_frame_tc16_launch(const DpFrameArgs& args, int num_sms, cudaStrea
 // TP_NDEC decoder cross-attention blocks; or null to run the fp32 CUDA-core kernels.
 #define DP_TC_ATT_OFFSET ((size_t)(TP_NENC + TP_NDEC) * FFT_LAYER_BYTES)
 #define DP_TC_TILES_BYTES (DP_TC_ATT_OFFSET + (size_t)(TP_NENC + 2 * TP_NDEC) * ATT_LAYER_BYTES)
+// ... followed by the key projections of the TP_NDEC decoder cross-attention blocks as fp32 [d = key feature][c = input] (the torch
+// layout; the blob stores every Linear as [in][out]): the folded single-token cross-attention reads them coalesced over c
+#define DP_TC_XA_OFFSET DP_TC_TILES_BYTES
+#define DP_TC_IMAGE_TOTAL_BYTES (DP_TC_XA_OFFSET + (size_t)TP_NDEC * TP_D * TP_D * 4)
 cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* mu, const float* sigma,
                             const float* latent_buf, const float* disp_buf, const float* height_buf, int head, int B,
                             int window, float* target_buf, const TpWork& w, const unsigned char* fftiles, cudaStream_t st,

@@ -97,9 +97,12 @@ __global__ void tp_dec_embed_kernel(const float* __restrict__ blob, TpLayout L, 
 }
 
 // ---- single-token decoder pass, first kernel: embedding of the one decoder token + the first layer's self-attention block
-// (one key: row-local, see TpFfTail); one warp per clip.
-__global__ void __launch_bounds__(256) tp_dec_start_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ dec_lat, int n_clips,
+// (one key: row-local, see TpFfTail) + its cross-attention block against the clip's encoder memory (tp_cross_attn_single); one warp
+// per clip.
+__global__ void __launch_bounds__(256) tp_dec_start_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ dec_lat,
+                                                           const float* __restrict__ wk_t, const float* __restrict__ mem, int n_clips,
                                                            float* __restrict__ dec) {
+  __shared__ __align__(16) float scr[8][TP_XA_SCR];
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= n_clips) return;
   const float lat = lane < TP_LAT ? dec_lat[(size_t)b * TP_MAXT * TP_LAT + lane] : 0.0f;
@@ -107,7 +110,8 @@ __global__ void __launch_bounds__(256) tp_dec_start_kernel(const float* __restri
   tp_warp_matvec<TP_LAT>(lat, 0.0f, blob + L.dec_in_w, TP_D, 0, blob + L.dec_in_b, TP_D, lane, x0, x1);
   x0 += blob[L.pe + lane];
   if (lane + 32 < TP_D) x1 += blob[L.pe + lane + 32];
-  tp_self_attn_single(blob, L.dec[0].sa, L.dec[0].n1, lane, x0, x1);
+  tp_self_attn_single_s(blob, L.dec[0].sa, L.dec[0].n1, scr[threadIdx.x >> 5] + (TP_H + TP_S) * TP_XA_STRIDE, lane, x0, x1);
+  tp_cross_attn_single(blob, L.dec[0].ca, L.dec[0].n2, wk_t, mem + (size_t)b * TP_S * TP_D, scr[threadIdx.x >> 5], lane, x0, x1);
   float* dst = dec + (size_t)b * TP_MAXT * TP_D;
   dst[lane] = x0;
   if (lane + 32 < TP_D) dst[lane + 32] = x1;
@@ -431,21 +435,26 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
   static const int fused_dec = getenv("DP_PRED_FUSED_DEC") ? atoi(getenv("DP_PRED_FUSED_DEC")) : 1;
   for (int i = 0; i <= window; i += 4, ++T) {
     if (fftiles && fused_dec && T == 1 && (size_t)4 * B * TP_D <= part_floats) {
-      // single-token pass: embedding + self-attention of layer 0 in one small kernel, then per layer { cross-attention, feed-forward
-      // with the next layer's self-attention (or the prediction head) fused into its finishing kernel }: 10 launches instead of 17
-      const unsigned char* att = fftiles + DP_TC_ATT_OFFSET;
-      tp_dec_start_kernel<<<(B + 7) / 8, 256, 0, st>>>(blob, L, w.dec_lat, B, w.dec2);
+      // single-token pass: embedding + self- and cross-attention of layer 0 in one small kernel, then per layer the feed-forward block
+      // with the next layer's two attention blocks (or the prediction head) fused into its finishing kernel: 7 launches, none of them
+      // an attention kernel (round 2 started at 17, then 10 with tcgen05 cross-attention launches)
+      float* cur = w.dec;
+      float* nxt = w.dec2;
+      const float* wk_t = reinterpret_cast<const float*>(fftiles + DP_TC_XA_OFFSET);  // [layer][key feature][input]
+      tp_dec_start_kernel<<<(B + 7) / 8, 256, 0, st>>>(blob, L, w.dec_lat, wk_t, e, B, cur);
       ++*launches;
       for (int l = 0; l < TP_NDEC; ++l) {
-        err = dp_attn_tc_launch(att + (size_t)(TP_NENC + TP_NDEC + l) * ATT_LAYER_BYTES, blob, L.dec[l].n2, w.dec2, 1, TP_MAXT, e, TP_S, TP_S, B, w.dec, st);
-        if (err != cudaSuccess) return err;
-        ++*launches;
         TpFfTail tail;
         memset(&tail, 0, sizeof(tail));
         if (l + 1 < TP_NDEC) {
           tail.next_self_attn = 1;
           tail.sa = L.dec[l + 1].sa;
           tail.n1 = L.dec[l + 1].n1;
+          tail.next_cross_attn = 1;
+          tail.ca = L.dec[l + 1].ca;
+          tail.n2 = L.dec[l + 1].n2;
+          tail.wk_t = wk_t + (size_t)(l + 1) * TP_D * TP_D;
+          tail.mem = e;
         } else {
           tail.out_head = 1;
           tail.out_w = L.out_w; tail.out_b = L.out_b;
@@ -453,9 +462,10 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
           tail.dec_lat = w.dec_lat; tail.target_buf = target_buf;
           tail.step_i = i; tail.window = window;
         }
-        err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm, l == TP_NDEC - 1, w.dec, B, 1,
-                              TP_MAXT, w.dec2, w.ffpart, part_floats, w.num_sms, st, launches, &tail);
+        err = dp_ff_tc_launch(fftiles + (size_t)(TP_NENC + l) * FFT_LAYER_BYTES, blob, L.dec[l].ff, L.dec[l].n3, L.dec_norm, l == TP_NDEC - 1, cur, B, 1,
+                              TP_MAXT, nxt, w.ffpart, part_floats, w.num_sms, st, launches, &tail);
         if (err != cudaSuccess) return err;
+        float* t = cur; cur = nxt; nxt = t;
       }
       continue;
     }

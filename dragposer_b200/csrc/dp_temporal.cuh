@@ -72,11 +72,18 @@ inline TpLayout tp_layout() {
 // Optional work fused behind the feed-forward block of a SINGLE-TOKEN decoder pass (T == 1: the first autoregressive step, the only
 // one when temporal_future_window == 0): the finished row goes straight through the next decoder layer's self-attention block
 // (one key: softmax == 1, so the block is LN(x + W_o (W_v x + b_v) + b_o), a row-local map) and / or through the prediction head
-// of drag_pose.py:275-289.  Saves the 32-CTA attention launch and the head launch of every layer of the pass.
+// of drag_pose.py:275-289.  Saves the 32-CTA attention launch and the head launch of every layer of the pass.  The cross-attention
+// block of a single query is row-local too once W_k is folded into the query and W_v behind the weighted sum of the memory tokens
+// (tp_cross_attn_single): it rides in the same kernels, so the pass needs no attention launch at all.
 struct TpFfTail {
   int next_self_attn;
   TpAttn sa;
   TpNorm n1;
+  int next_cross_attn;     // ... followed by that layer's cross-attention block against the clip's encoder memory (tp_cross_attn_single)
+  TpAttn ca;
+  TpNorm n2;
+  const float* wk_t;       // that block's key projection as [key feature][input] (DP_TC_XA_OFFSET)
+  const float* mem;        // encoder memory (n_clips, TP_S, TP_D)
   int out_head;
   size_t out_w, out_b;
   const float* mu;
@@ -116,13 +123,157 @@ __device__ __forceinline__ void tp_warp_matvec(float x0, float x1, const float* 
     if (has1) y1 = fmaf(xi, w[lane + 32], y1);
   }
 }
-// self-attention block of a single token (its only key is itself): x <- LN(x + W_o (W_v x + b_v) + b_o)
-__device__ __forceinline__ void tp_self_attn_single(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N, int lane, float& x0, float& x1) {
+// the same with the input row staged in shared memory (xs: K floats, 16-byte aligned, visible to the whole warp): the inputs arrive as
+// broadcast LDS.128 (K / 4 loads) instead of K shuffles -- a shuffle costs four issue cycles of a sub-partition, and the single-token
+// decoder blocks below are chains of these products
+template <int K>
+__device__ __forceinline__ void tp_warp_matvec_s(const float* __restrict__ xs, const float* __restrict__ W, int ldw, int col0,
+                                                 const float* __restrict__ bias, int n_out, int lane, float& y0, float& y1) {
+  static_assert(K % 4 == 0, "vectorised input row");
+  const bool has0 = lane < n_out, has1 = lane + 32 < n_out;
+  y0 = has0 ? bias[lane] : 0.0f;
+  y1 = has1 ? bias[lane + 32] : 0.0f;
+  const float* w = W + col0 + (has0 ? lane : 0);
+  const float* w1 = W + col0 + (has1 ? lane + 32 : 0);
+#pragma unroll 4
+  for (int i = 0; i < K; i += 4) {
+    const float4 xv = *reinterpret_cast<const float4*>(xs + i);
+    y0 = fmaf(xv.x, w[(size_t)i * ldw], fmaf(xv.y, w[(size_t)(i + 1) * ldw], fmaf(xv.z, w[(size_t)(i + 2) * ldw], fmaf(xv.w, w[(size_t)(i + 3) * ldw], y0))));
+    y1 = fmaf(xv.x, w1[(size_t)i * ldw], fmaf(xv.y, w1[(size_t)(i + 1) * ldw], fmaf(xv.z, w1[(size_t)(i + 2) * ldw], fmaf(xv.w, w1[(size_t)(i + 3) * ldw], y1))));
+  }
+  if (!has0) y0 = 0.0f;
+  if (!has1) y1 = 0.0f;
+}
+// publish a row held as (lane, lane + 32) to the warp's staging row
+__device__ __forceinline__ void tp_stage_row(float* __restrict__ xs, int lane, float v0, float v1) {
+  __syncwarp();  // earlier readers of the staging row are done
+  xs[lane] = v0;
+  if (lane + 32 < TP_D) xs[lane + 32] = v1;
+  __syncwarp();
+}
+// self-attention block of a single token (its only key is itself): x <- LN(x + W_o (W_v x + b_v) + b_o); xs: TP_D floats of
+// shared memory owned by this warp (staging row)
+__device__ __forceinline__ void tp_self_attn_single_s(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N, float* __restrict__ xs, int lane,
+                                                      float& x0, float& x1) {
   float v0, v1, o0, o1;
-  tp_warp_matvec<TP_D>(x0, x1, blob + A.w_in, 3 * TP_D, 2 * TP_D, blob + A.b_in + 2 * TP_D, TP_D, lane, v0, v1);
-  tp_warp_matvec<TP_D>(v0, v1, blob + A.w_out, TP_D, 0, blob + A.b_out, TP_D, lane, o0, o1);
+  tp_stage_row(xs, lane, x0, x1);
+  tp_warp_matvec_s<TP_D>(xs, blob + A.w_in, 3 * TP_D, 2 * TP_D, blob + A.b_in + 2 * TP_D, TP_D, lane, v0, v1);
+  tp_stage_row(xs, lane, v0, v1);
+  tp_warp_matvec_s<TP_D>(xs, blob + A.w_out, TP_D, 0, blob + A.b_out, TP_D, lane, o0, o1);
   x0 += o0;
   x1 += o1;
+  tp_ln_row_warp(x0, x1, blob + N.w, blob + N.b, lane);
+}
+// Cross-attention block of a SINGLE decoder token against the S = 14 encoder-memory rows m_s of its clip, one warp per token:
+//   x <- LN(x + W_o concat_h(W_v,h mbar_h + b_v,h) + b_o),  mbar_h = sum_s a_hs m_s,  a_h = softmax_s((W_k,h^T q_h) . m_s / sqrt(12))
+// -- nn.MultiheadAttention (temporal_transformer.py:53-78) with the key projection folded into the query (the bias term q_h . b_k,h is
+// the same for every key and cancels in the softmax) and the value projection applied once to the weighted sum of the memory tokens
+// (the probabilities sum to one, so b_v passes through): 4 x 48 x 12 + 4 x 48 x 12 multiply-adds instead of two 14 x 48 x 48
+// projections, all in fp32, nothing but the 14 memory rows read.  `scr`: TP_XA_SCR floats of shared memory owned by this warp.
+#define TP_XA_STRIDE 52   // row stride of the scratch (floats): 16-byte aligned rows that start in different banks
+#define TP_XA_SCR ((TP_H + TP_S) * TP_XA_STRIDE + TP_D + TP_S * TP_H)   // four per-head rows + the clip's 14 memory rows + a staging row + the probabilities
+// wk_t: the key projection as [key feature d][input c] (so that a warp reads one d-row coalesced over c).
+__device__ __forceinline__ void tp_cross_attn_single(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N, const float* __restrict__ wk_t,
+                                                     const float* __restrict__ mem, float* __restrict__ scr, int lane, float& x0, float& x1) {
+  static_assert(TP_H * TP_HD == TP_D && TP_S <= 16 && TP_D % 4 == 0, "layout of the folded cross-attention");
+  const bool has1 = lane + 32 < TP_D;
+  const float* Win = blob + A.w_in;   // [in 48][q 48 | k 48 | v 48]
+  float* ms = scr + TP_H * TP_XA_STRIDE;  // the clip's memory rows, staged once (coalesced) and read three times
+  float* xs = scr + (TP_H + TP_S) * TP_XA_STRIDE;      // staging row of the matrix-vector products
+  float* as = xs + TP_D;                               // probabilities a[s][h] (14 x 4 floats)
+  static_assert(((TP_H + TP_S) * TP_XA_STRIDE) % 4 == 0 && TP_D % 4 == 0 && TP_XA_SCR % 4 == 0, "16-byte aligned scratch rows");
+  for (int i = lane; i < TP_S * (TP_D / 4); i += 32) {
+    const int s = i / (TP_D / 4), c4 = i % (TP_D / 4);
+    reinterpret_cast<float4*>(ms + s * TP_XA_STRIDE)[c4] = reinterpret_cast<const float4*>(mem)[i];
+  }
+  float q0, q1;
+  tp_stage_row(xs, lane, x0, x1);
+  tp_warp_matvec_s<TP_D>(xs, Win, 3 * TP_D, 0, blob + A.b_in, TP_D, lane, q0, q1);
+  tp_stage_row(xs, lane, q0, q1);
+  // qt_h[c] = (1 / sqrt(12)) sum_{d in head h} W_k[d][c] q[d]; this lane owns c = lane and c = lane + 32
+  {
+    const float scale = rsqrtf((float)TP_HD);
+#pragma unroll
+    for (int h = 0; h < TP_H; ++h) {
+      float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+      for (int j4 = 0; j4 < TP_HD; j4 += 4) {
+        const int d = h * TP_HD + j4;
+        const float4 qv = *reinterpret_cast<const float4*>(xs + d);  // broadcast
+        a0 = fmaf(wk_t[d * TP_D + lane], qv.x, fmaf(wk_t[(d + 1) * TP_D + lane], qv.y, fmaf(wk_t[(d + 2) * TP_D + lane], qv.z, fmaf(wk_t[(d + 3) * TP_D + lane], qv.w, a0))));
+        if (has1)
+          a1 = fmaf(wk_t[d * TP_D + lane + 32], qv.x,
+                    fmaf(wk_t[(d + 1) * TP_D + lane + 32], qv.y, fmaf(wk_t[(d + 2) * TP_D + lane + 32], qv.z, fmaf(wk_t[(d + 3) * TP_D + lane + 32], qv.w, a1))));
+      }
+      scr[h * TP_XA_STRIDE + lane] = a0 * scale;
+      if (has1) scr[h * TP_XA_STRIDE + lane + 32] = a1 * scale;
+    }
+  }
+  __syncwarp();
+  // scores of key s on lane s (all heads), softmax across the lanes
+  {
+    float a[TP_H];
+    const bool key = lane < TP_S;
+    float sc[TP_H] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float4* mrow = reinterpret_cast<const float4*>(ms + (key ? lane : 0) * TP_XA_STRIDE);
+#pragma unroll
+    for (int c4 = 0; c4 < TP_D / 4; ++c4) {
+      const float4 mv = mrow[c4];
+#pragma unroll
+      for (int h = 0; h < TP_H; ++h) {
+        const float4 qv = reinterpret_cast<const float4*>(scr + h * TP_XA_STRIDE)[c4];
+        sc[h] = fmaf(mv.x, qv.x, fmaf(mv.y, qv.y, fmaf(mv.z, qv.z, fmaf(mv.w, qv.w, sc[h]))));
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < TP_H; ++h) {
+      const float v = key ? sc[h] : -3.0e38f;
+      float mx = v;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));  // the keys live on lanes 0..13 of the lower half
+      const float p = key ? expf(v - mx) : 0.0f;
+      float sum = p;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      a[h] = key ? p / sum : 0.0f;  // (the upper half-warp sums to zero; its lanes publish nothing)
+    }
+    if (key) *reinterpret_cast<float4*>(as + 4 * lane) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  __syncwarp();  // probabilities published; every lane has read the folded queries: the per-head rows are free again
+  // mbar_h[c] = sum_s a_hs m_s[c]
+  {
+    float b0[TP_H] = {0.0f, 0.0f, 0.0f, 0.0f}, b1[TP_H] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int s = 0; s < TP_S; ++s) {
+      const float m0 = ms[s * TP_XA_STRIDE + lane], m1 = has1 ? ms[s * TP_XA_STRIDE + lane + 32] : 0.0f;
+      const float4 av = *reinterpret_cast<const float4*>(as + 4 * s);  // broadcast
+      b0[0] = fmaf(av.x, m0, b0[0]); b0[1] = fmaf(av.y, m0, b0[1]); b0[2] = fmaf(av.z, m0, b0[2]); b0[3] = fmaf(av.w, m0, b0[3]);
+      b1[0] = fmaf(av.x, m1, b1[0]); b1[1] = fmaf(av.y, m1, b1[1]); b1[2] = fmaf(av.z, m1, b1[2]); b1[3] = fmaf(av.w, m1, b1[3]);
+    }
+#pragma unroll
+    for (int h = 0; h < TP_H; ++h) {
+      scr[h * TP_XA_STRIDE + lane] = b0[h];
+      if (has1) scr[h * TP_XA_STRIDE + lane + 32] = b1[h];
+    }
+  }
+  __syncwarp();
+  // o[d] = b_v[d] + sum_c W_v[c][d] mbar_{head(d)}[c]; this lane owns d = lane and d = lane + 32
+  float o0 = blob[A.b_in + 2 * TP_D + lane], o1 = has1 ? blob[A.b_in + 2 * TP_D + lane + 32] : 0.0f;
+  {
+    const float* mb0 = scr + (lane / TP_HD) * TP_XA_STRIDE;
+    const float* mb1 = scr + ((has1 ? lane + 32 : lane) / TP_HD) * TP_XA_STRIDE;
+    const float* wv = Win + 2 * TP_D;
+#pragma unroll 8
+    for (int c = 0; c < TP_D; ++c) {
+      o0 = fmaf(mb0[c], wv[(size_t)c * 3 * TP_D + lane], o0);
+      if (has1) o1 = fmaf(mb1[c], wv[(size_t)c * 3 * TP_D + lane + 32], o1);
+    }
+  }
+  float y0, y1;
+  tp_stage_row(xs, lane, o0, o1);
+  tp_warp_matvec_s<TP_D>(xs, blob + A.w_out, TP_D, 0, blob + A.b_out, TP_D, lane, y0, y1);
+  x0 += y0;
+  x1 += y1;
   tp_ln_row_warp(x0, x1, blob + N.w, blob + N.b, lane);
 }
 // prediction head on a finished last-token row (drag_pose.py:275-289): appends the standardised prediction to the decoder inputs

@@ -38,6 +38,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
 __global__ void __launch_bounds__(256)
 tp_ff_finish_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2, const float* __restrict__ x_g, int n_rows, int T,
                     int row_stride, const float* __restrict__ part, int n_split, float* __restrict__ out_g, const __grid_constant__ TpFfTail tail) {
+  __shared__ __align__(16) float scr[8][TP_XA_SCR];
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n_rows) return;
   const bool has1 = lane + 32 < TP_D;
@@ -53,7 +54,9 @@ tp_ff_finish_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2
   v1 += a1;
   tp_ln_row_warp(v0, v1, blob + N1.w, blob + N1.b, lane);
   if (has_n2) tp_ln_row_warp(v0, v1, blob + N2.w, blob + N2.b, lane);
-  if (tail.next_self_attn) tp_self_attn_single(blob, tail.sa, tail.n1, lane, v0, v1);
+  if (tail.next_self_attn) tp_self_attn_single_s(blob, tail.sa, tail.n1, scr[threadIdx.x >> 5] + (TP_H + TP_S) * TP_XA_STRIDE, lane, v0, v1);
+  if (tail.next_cross_attn)  // T == 1: row == clip
+    tp_cross_attn_single(blob, tail.ca, tail.n2, tail.wk_t, tail.mem + (size_t)row * TP_S * TP_D, scr[threadIdx.x >> 5], lane, v0, v1);
   out_g[g + lane] = v0;
   if (has1) out_g[g + lane + 32] = v1;
   if (tail.out_head) tp_out_head_row(blob, tail, row / T, T, lane, v0, v1);
