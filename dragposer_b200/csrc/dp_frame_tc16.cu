@@ -19,24 +19,32 @@
 
 namespace {
 
-constexpr int NC = 32;            // clip columns per CTA: two groups of 16 (UMMA N = 16)
-constexpr int kWarps = 16;     // two groups of 8 warps
+#ifndef DP_TC16_GROUPS
+#define DP_TC16_GROUPS 4
+#endif
+constexpr int NC = 32;                     // clip columns per CTA
+constexpr int kWarps = 16;
+constexpr int kGroups = DP_TC16_GROUPS;    // independent clip groups of a CTA (2 or 4)
+constexpr int kGW = kWarps / kGroups;      // warps per group: 8 (16 clips) or 4 (8 clips)
+constexpr int kGC = NC / kGroups;          // clip columns per group
+constexpr int kG8 = kGC / 8;               // 8-clip groups per fp16 piece of a group
+static_assert(kGroups == 2 || kGroups == 4, "two groups of 8 warps or four groups of 4 warps");
 constexpr int EC = 8;             // clips per epilogue thread: a group's 8 warps = 4 TMEM lane quarters x 2 clip halves
 // activation image (B operand, MN-major, no swizzle).  The two fp16 pieces of a group's 16 clips lie SIDE BY SIDE along N, so that
 // one N = 32 instruction multiplies a weight piece with both of them: element (feature k, group g, piece p, clip n < 16) at
-//   (k / 8) * kB_LBO + (k % 8) * 16 + (4 g + 2 p + n / 8) * kB_SBO + (n % 8) * 2 bytes.
+//   (k / 8) * kB_LBO + (k % 8) * 16 + ((2 g + p) kG8 + n / 8) * kB_SBO + (n % 8) * 2 bytes   (kG8 = 8-clip groups per piece: 2 or 1).
 // The K 8-groups are padded from 1024 to 1040 bytes: unpadded, every 8-group starts in the same bank and the 32 lanes of an
 // epilogue warp (consecutive features, one 16-byte store each) collide four ways; the pad moves each group on by four banks.
-constexpr uint32_t kB_SBO = 128, kB_PIECE = 2 * kB_SBO;
+constexpr uint32_t kB_SBO = 128, kB_PIECE = kG8 * kB_SBO;
 constexpr uint32_t kB_LBO = kB_SBO * 2 * (NC / 8) + 16;
 constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LBO;  // both pieces
 // dL/dy image (B operand of the first backward layer only), K-MAJOR: element (group g, piece p, clip n < 16, feature k) at
-//   (4 g + 2 p + n / 8) * kD_SBO + (k / 8) * kD_LBO + (n % 8) * 16 + (k % 8) * 2 bytes,
+//   ((2 g + p) kG8 + n / 8) * kD_SBO + (k / 8) * kD_LBO + (n % 8) * 16 + (k % 8) * 2 bytes,
 // so that the kinematics lane of joint j stores its four values dL/dy[4j .. 4j+3] of a clip as ONE 8-byte word per piece -- the
 // adjoint writes the tensor-core operand itself and the backward layers start after a single group barrier (round 1 wrote fp32
 // rows, and the epilogue warps re-read them transposed, split them and stored them behind a second barrier).  kD_LBO is padded
 // from 128 to 144 bytes for the same bank reason as kB_LBO.
-constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kD_PIECE = 2 * kD_SBO, kDyBytes = 2 * (NC / 8) * kD_SBO;
+constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kD_PIECE = kG8 * kD_SBO, kDyBytes = 2 * (NC / 8) * kD_SBO;
 constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scaled per clip into [16, 32) (see dp_frame_tc.cu)
 // Generic-proxy writes of an operand image (st.shared by the epilogue / kinematics / Adam threads) must be ordered before the
 // tensor core's async-proxy reads.  true: the ONE issuing thread executes fence.proxy.async after the group barrier that made the
@@ -49,7 +57,7 @@ constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scale
 #endif
 constexpr bool kIssuerFence = DP_ISSUER_FENCE != 0;
 enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
-// tensor-memory columns: accumulators of group g at 32 g (16 columns per B piece); then the weight pieces (two K elements per word)
+// tensor-memory columns: accumulators of group g at 2 kGC g (kGC columns per B piece); then the weight pieces (two K elements per word)
 constexpr uint32_t kT_D = 0, kT_W = 64, kT_COLS = 512;
 static_assert(kT_W + DP_TC_TMEM_WORDS <= kT_COLS, "weights must fit in tensor memory");
 
@@ -69,19 +77,19 @@ struct SmemT {
   double prev[NC];                                  // previous total loss (early stopping compares in double)
   float loss[NC][3];                                // last evaluated lp, lr, lt
   int iters[NC];
-  uint64_t bar_w, bar_mma[2];
+  uint64_t bar_w, bar_mma[kGroups];
   uint32_t tmem_base;
   __device__ __forceinline__ const DpModelImageTC& M() const { return *reinterpret_cast<const DpModelImageTC*>(model); }
 };
 
-// named block barriers of the two groups (ids 1, 2; id 0 is __syncthreads)
-__device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, 256;" ::"r"(gid + 1) : "memory"); }
+// named block barriers of the groups (ids 1 .. kGroups; id 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int gid) { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kGW * 32) : "memory"); }
 __device__ __forceinline__ bool group_or(int gid, bool p) {
   uint32_t r;
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, 256, p;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
       : "=r"(r)
-      : "r"((uint32_t)p), "r"(gid + 1)
+      : "r"((uint32_t)p), "r"(gid + 1), "n"(kGW * 32)
       : "memory");
   return r != 0;
 }
@@ -106,7 +114,7 @@ __device__ __forceinline__ void store_pieces4(unsigned char* img, int k, int slo
 }
 // one feature of a clip PAIR (columns cl, cl + 1 of group g, cl even) -> its pieces, one 32-bit store each (latent rows of ping)
 __device__ __forceinline__ void store_piece_pair(unsigned char* img, int k, int g, int cl, float x0, float x1) {
-  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (4 * g + (cl >> 3)) * kB_SBO + (cl & 7) * 2;
+  unsigned char* dst = img + (k >> 3) * kB_LBO + (k & 7) * 16 + (2 * kG8 * g + (cl >> 3)) * kB_SBO + (cl & 7) * 2;
   const uint32_t p = pack_f16x2(x0, x1);
   float h0, h1;
   unpack_f16x2(p, h0, h1);
@@ -138,7 +146,7 @@ struct EmitDyPieces {
   }
   __device__ __forceinline__ void operator()(const P2 (&o)[4], const P2 (&db)[3]) const {
     // the two clips share an 8-group (cl is even): rows (cl % 8) and (cl % 8) + 1 of the same core matrices
-    unsigned char* base = img + (4 * g + (cl >> 3)) * kD_SBO + (cl & 7) * 16;
+    unsigned char* base = img + (2 * kG8 * g + (cl >> 3)) * kD_SBO + (cl & 7) * 16;
     if (lane < DP_J) {
       unsigned char* dst = base + (lane >> 1) * kD_LBO + (lane & 1) * 8;  // k = 4 lane: 8-group lane / 2, first or second half
       put(dst, o[0].v.x, o[1].v.x, o[2].v.x, o[3].v.x);
@@ -173,10 +181,12 @@ __device__ __forceinline__ void tc_issue(Ctx& c, const unsigned char* src) {
       if (kIssuerFence) fence_proxy_async();  // see kIssuerFence
       // fp16 x fp16 -> fp32, M 128; bit 16: B is MN-major
       constexpr uint32_t idesc = (1u << 4) | (B_KMAJOR ? 0u : (1u << 16)) | (8u << 24);
-      constexpr uint32_t idesc16 = idesc | ((uint32_t)(16 >> 3) << 17), idesc32 = idesc | ((uint32_t)(32 >> 3) << 17);
+      // both pieces: N = 2 kGC; first piece only: N = kGC -- but an M = 128 instruction needs N >= 16, so four groups of 8 clips issue the
+      // second instruction on both pieces as well (it adds the (2,2) product, a term of relative size 2^-22, to the second column block)
+      constexpr uint32_t idesc32 = idesc | ((uint32_t)((2 * kGC) >> 3) << 17), idesc16 = idesc | ((uint32_t)((kGC >= 16 ? kGC : 2 * kGC) >> 3) << 17);
       constexpr uint32_t lbo = B_KMAJOR ? kD_LBO : kB_LBO, sbo = B_KMAJOR ? kD_SBO : kB_SBO;
-      const UmmaDescBase b = umma_desc_base(smem_u32(src) + (uint32_t)c.gid * 4 * sbo, lbo, sbo);  // the group's four 8-groups
-      const uint32_t d = c.tmem + kT_D + 32 * c.gid, a1 = c.tmem + kT_W + WT<L, FWD>::p1, a2 = c.tmem + kT_W + WT<L, FWD>::p2;
+      const UmmaDescBase b = umma_desc_base(smem_u32(src) + (uint32_t)c.gid * 2 * kG8 * sbo, lbo, sbo);  // the group's 8-groups (both pieces)
+      const uint32_t d = c.tmem + kT_D + 2 * kGC * c.gid, a1 = c.tmem + kT_W + WT<L, FWD>::p1, a2 = c.tmem + kT_W + WT<L, FWD>::p2;
 #pragma unroll
       for (int k = 0; k < (int)WT<L, FWD>::ksteps; ++k) {
         const uint32_t bo = k * 2 * lbo;  // K = 16 per instruction: two 8-groups of K
@@ -199,9 +209,9 @@ __device__ __forceinline__ void tc_layer(Ctx& c, const unsigned char* src, int o
     mbar_wait(&S.bar_mma[c.gid], c.phase);
       tc_fence_after();
     float v[EC], w[EC];
-    const uint32_t t = c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(32 * c.gid + EC * half);
+    const uint32_t t = c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(2 * kGC * c.gid + EC * half);
     tmem_ld8(t, v);
-    tmem_ld8(t + 16, w);
+    tmem_ld8(t + kGC, w);
     tmem_ld_wait();
   #pragma unroll
     for (int i = 0; i < EC; ++i) v[i] += w[i];
@@ -226,9 +236,9 @@ __device__ __forceinline__ void tc_layer4(Ctx& c, const unsigned char* src, int 
     mbar_wait(&S.bar_mma[c.gid], c.phase);
     tc_fence_after();
     float v[4], w[4];
-    const uint32_t t = c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(32 * c.gid + EC * half + 4 * sub);
+    const uint32_t t = c.tmem + ((uint32_t)(quarter * 32) << 16) + kT_D + (uint32_t)(2 * kGC * c.gid + EC * half + 4 * sub);
     tmem_ld4(t, v);
-    tmem_ld4(t + 16, w);
+    tmem_ld4(t + kGC, w);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] += w[i];
@@ -248,11 +258,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   SmemT& S = *reinterpret_cast<SmemT*>(smem_raw);
   const DpModelImageTC& M = S.M();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gid = warp >> 3, wg = warp & 7;  // group, warp within the group
+  const int gid = warp / kGW, wg = warp % kGW;  // group, warp within the group
   if (threadIdx.x == 0) {
     mbar_init(&S.bar_w, 1);
-    mbar_init(&S.bar_mma[0], 1);
-    mbar_init(&S.bar_mma[1], 1);
+    for (int g = 0; g < kGroups; ++g) mbar_init(&S.bar_mma[g], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&S.tmem_base, kT_COLS);
@@ -281,9 +290,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   }
   Ctx ctx{&S, tmem, gid, wg, lane, 0u};
   constexpr int CPW = 2;            // clips per warp in the per-clip phases
-  const int n0 = warp * CPW;        // clip column of this warp's first clip (group g owns columns 16 g .. 16 g + 15)
-  const int cpg = (A.clips_per_cta + 1) / 2;  // real clips per group
-  const int clip0 = blockIdx.x * A.clips_per_cta + gid * cpg + 2 * wg;
+  const int n0 = warp * CPW;        // clip column of this warp's first clip (group g owns columns kGC g .. kGC g + kGC - 1)
+  // the CTA's clip PAIRS are dealt to the groups as evenly as possible (28 clips = 14 pairs: 7 + 7, or 4 + 4 + 3 + 3), one pair per warp
+  const int n_pairs = (A.clips_per_cta + 1) / 2;
+  int first_pair = 0;
+  for (int g = 0; g < gid; ++g) first_pair += (n_pairs + kGroups - 1 - g) / kGroups;
+  const int my_pairs = (n_pairs + kGroups - 1 - gid) / kGroups;
+  const int col0 = 2 * (first_pair + wg);  // this warp's first clip inside the CTA's tile
+  const int clip0 = blockIdx.x * A.clips_per_cta + col0;
 
   // ---- per-clip frame inputs (same as the fp32 kernel)
   static_assert(CPW == 2, "the kinematics pass packs exactly two clips per warp");
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
 #pragma unroll
   for (int c = 0; c < CPW; ++c) {
     const int clip = clip0 + c;
-    valid[c] = clip < A.n_clips && 2 * wg + c < cpg && gid * cpg + 2 * wg + c < A.clips_per_cta;
+    valid[c] = clip < A.n_clips && wg < my_pairs && col0 + c < A.clips_per_cta;
     const int cc = valid[c] ? clip : 0;
     int ne = A.n_ee ? A.n_ee[cc] : A.ee_stride;
     ne = max(1, min(ne, A.ee_stride));
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
 
   const FkLaneIdx lane_idx = fk_lane_idx(M, lane);  // skeleton indices of this lane, in registers for the whole launch
   constexpr float wsc = 1.0f / kWScale;  // undoes the weight-image scaling
-  const int slot0 = 4 * gid;             // first 8-group (piece 1) of this group in the activation images
+  const int slot0 = 2 * kG8 * gid;       // first 8-group (piece 1) of this group in the activation images
   unsigned neg0 = 0, neg1 = 0;           // LeakyReLU slope bits of (feature k, this thread's 4 clips) for the backward pass
   auto forward = [&]() {
     tc_layer4<0, true>(ctx, S.ping, DP_H0, [&](int k, int half, int sub, float (&v)[4]) {
@@ -380,8 +394,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     tc_layer<2, true>(ctx, S.ping, DP_Y, [&](int k, int half, float (&v)[EC]) {
       const float b = M.b2[k];
 #pragma unroll
-      for (int i = 0; i < EC; i += 2)  // clips 2p, 2p + 1 of this 8-clip half = pair 8 gid + 4 half + p; feature k = 4 j + c
-        *reinterpret_cast<float2*>(reinterpret_cast<float*>(&S.y2[8 * gid + 4 * half + i / 2][(k >> 1) & 1][k >> 2]) + 2 * (k & 1)) =
+      for (int i = 0; i < EC; i += 2)  // clips 2p, 2p + 1 of this 8-clip half = pair kGW gid + 4 half + p; feature k = 4 j + c
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(&S.y2[kGW * gid + 4 * half + i / 2][(k >> 1) & 1][k >> 2]) + 2 * (k & 1)) =
             make_float2(fmaf(v[i], wsc, b), fmaf(v[i + 1], wsc, b));
     });
   };
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     }
   };
   // optional timeline of both groups over iterations 40..43 (scripts/timeline.py): six stamps per group and iteration
-  const bool tl_on = CLOCK && A.phase_cycles != nullptr && blockIdx.x == 0 && wg == 0 && lane == 0;
+  const bool tl_on = CLOCK && A.phase_cycles != nullptr && blockIdx.x == 0 && wg == 0 && lane == 0 && gid < 2;  // the first two groups
   auto stamp = [&](int it, int k) {
     if (CLOCK && tl_on && it >= 40 && it < 44) A.phase_cycles[16 + gid * 24 + (it - 40) * 6 + k] = (unsigned long long)clock64();
   };
@@ -467,9 +481,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
       mbar_wait(&S.bar_mma[gid], ctx.phase);
       tc_fence_after();
       float d1[2], d2[2];
-      const uint32_t t = tmem + ((uint32_t)((wg & 3) * 32) << 16) + kT_D + (uint32_t)(32 * gid + 2 * wg);
+      const uint32_t t = tmem + ((uint32_t)((wg & 3) * 32) << 16) + kT_D + (uint32_t)(2 * kGC * gid + 2 * wg);
       tmem_ld2(t, d1);
-      tmem_ld2(t + 16, d2);
+      tmem_ld2(t + kGC, d2);
       tmem_ld_wait();
       tc_fence_before();
       ctx.phase ^= 1u;
