@@ -47,13 +47,15 @@ constexpr uint32_t kPingBytes = (64 / 8) * kB_LBO, kPongBytes = (96 / 8) * kB_LB
 constexpr uint32_t kD_LBO = 144, kD_SBO = (96 / 8) * kD_LBO, kD_PIECE = kG8 * kD_SBO, kDyBytes = 2 * (NC / 8) * kD_SBO;
 constexpr float kWScale = 16.0f;  // the weight image holds 16 W; dL/dy is scaled per clip into [16, 32) (see dp_frame_tc.cu)
 // Generic-proxy writes of an operand image (st.shared by the epilogue / kinematics / Adam threads) must be ordered before the
-// tensor core's async-proxy reads.  true: the ONE issuing thread executes fence.proxy.async after the group barrier that made the
-// writes visible to it (writer -> barrier -> fence -> tcgen05.mma is a causality chain through the fence; the barrier has drained
-// the stores, so the fence is cheap); false: every writer fences before the barrier (MEMBAR.ALL.CTA with its stores in flight) --
-// the pattern CUTLASS uses, and the default: the issuer-only variant measured 0.664 vs 0.666 ms per frame (scripts/ab_frame.sh),
-// nothing worth leaving the documented pattern for.
+// tensor core's async-proxy reads.  1 (default): the ONE issuing thread executes fence.proxy.async after the group barrier that made
+// the writes visible to it -- writer's st.shared -> (program order) barrier arrive -> (synchronizes with) issuer's barrier ->
+// (program order) fence.proxy.async -> tcgen05.mma: the proxy fence lies on the base-causality path from the write to the read, which
+// is what the PTX memory model asks for; the barrier has drained the stores, so the fence is cheap.  0: every writer fences before
+// the barrier (the pattern of CUTLASS's TMA-store epilogues; MEMBAR.ALL.CTA with the warp's stores still in flight, 50-110 cycles
+// in each of the 7 hand-offs of an iteration).  Measured (scripts/ab_frame.sh, ms per frame at 4 096 clips): four groups 0.629 vs
+// 0.641; two groups 0.664 vs 0.666.  The whole GPU suite (bitwise permutation test included) passes either way.
 #ifndef DP_ISSUER_FENCE
-#define DP_ISSUER_FENCE 0
+#define DP_ISSUER_FENCE 1
 #endif
 constexpr bool kIssuerFence = DP_ISSUER_FENCE != 0;
 enum { ST_Z = 0, ST_TL = 1, ST_M = 2, ST_V = 3, ST_ZLAST = 4 };
