@@ -42,7 +42,7 @@ KERNEL_NAMES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture whose
 # summary is committed under profiles/ (keyed by decoder path, clips per GPU, tracker config); null for other configurations
-NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 2471424}  # profiles/r2_frame_kernel.md (final capture): 2 470 912 read + 512 written
+NCU_DRAM_BYTES_PER_LAUNCH = {(3, 4096, "6"): 2472448}  # profiles/r2_frame_kernel.md (final capture): 2 468 864 read + 3 584 written
 
 
 def fixed_opts(cfg):
@@ -517,7 +517,7 @@ def roofline(m, B, trackers, peaks):
             "frac": achieved_tf / tf32_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((m["path"], B, trackers)), "peak_source": which,
             "kernel_ms_per_launch": m["frame_ms"], "predictor_ms_per_step": m["pred_ms"],
             "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
-            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 8.58, "tp_ff_tc_kernel": 48.6, "tp_attn_tc_kernel": 7.26,
+            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 12.12, "tp_ff_tc_kernel": 48.6, "tp_attn_tc_kernel": 7.26,
                                             "source": "profiles/r2_frame_kernel.md, r2_predictor.md: sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32 (issued ops, % of peak sustained elapsed)"},
             "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"}
 
