@@ -144,7 +144,8 @@ struct FkEmitNone {
 template <bool ADJOINT, bool EPILOGUE, bool SCALE = false, class MODEL, class EMIT = FkEmitNone>
 DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float4* __restrict__ y2, const float4* __restrict__ trk2,
                       const float2* __restrict__ groot2, float2* __restrict__ scr, P2 inv3e, P2 lrot9e, int lane,
-                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr, EMIT emit = EMIT()) {
+                      P2 q_out[4], P2 r_out[4], P2 p_out[3], P2 d_out[3], float* __restrict__ inv_scale = nullptr, EMIT emit = EMIT(),
+                      bool want_loss = true) {
   const bool is_joint = lane < DP_J;
   const bool is_root = lane == 0;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -231,18 +232,21 @@ DP_DI FkOut2 fk_loss2(const MODEL& M, const FkLaneIdx ix, const float4* __restri
   for (int i = 1; i < 9; ++i) sr = mad(eR[i], eR[i], sr);
   sp = sp * wp;
   sr = sr * wr;
-  {  // four warp sums with 6 + 4 shuffles
+  // want_loss == false (warp-uniform): the caller runs a fixed number of iterations and reads the loss VALUES of this iteration for
+  // nothing -- unless one of them is not finite (the reference's loop would stop on it).  One vote over the per-lane terms replaces the
+  // two warp sums (14 shuffles + selects); a non-finite term anywhere takes the full path, so the stop semantics are unchanged.
+  FkOut2 out;
+  out.lp = splat(0.0f);
+  out.lr = splat(0.0f);
+  const float probe = (sp.v.x + sp.v.y) + (sr.v.x + sr.v.y);
+  if (want_loss || __any_sync(0xffffffffu, !(fabsf(probe) <= 3.0e38f))) {  // four warp sums with 6 + 4 shuffles
     const float four[4] = {sp.v.x, sp.v.y, sr.v.x, sr.v.y};
     const float k = warp_sum4_scatter(four, lane);
     sp = mk2(__shfl_sync(0xffffffffu, k, 0), __shfl_sync(0xffffffffu, k, 8));
     sr = mk2(__shfl_sync(0xffffffffu, k, 16), __shfl_sync(0xffffffffu, k, 24));
+    out.lp = sp * inv3e;
+    out.lr = sr * lrot9e;
   }
-  // (Skipping these two sums on the iterations of a fixed-iteration run that never look at them -- 14 shuffles, ~45 instructions --
-  // was measured on the GPU: 0.666 -> 0.678 ms per frame at 4 096 clips, i.e. SLOWER; the loop is paced by the interplay of the two
-  // groups of a CTA, not by this warp's instruction count.  Not shipped.)
-  FkOut2 out;
-  out.lp = sp * inv3e;
-  out.lr = sr * lrot9e;
   if (EPILOGUE) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { q_out[i] = q[i]; r_out[i] = r[i]; }

@@ -408,3 +408,36 @@ def test_clocked_instantiation_is_bitwise_identical_and_timeline_is_ordered(engi
             print(f"clocked kernel: {period:.0f} cycles per iteration, phase counters {cyc[:5]}")
         eng.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_fixed_iterations_with_a_non_finite_target_stop_like_the_reference_loop(engine_factory, pose_model, model_npz):
+    """A fixed-iteration run (negative thresholds, min_loss_incr = -inf) never reads the tracker losses of an iteration except the last
+    ones, and the tcgen05 kernel skips their warp sums -- but `while ... and prev_loss - loss > min_loss_incr` (drag_pose.py:296-300)
+    still ends on a NaN loss.  A clip with a NaN target must therefore stop after its first iteration on both frame kernels, the other
+    clips must run all iterations, and the reported final losses must be the real ones (the two kernels agree)."""
+    cfg = synthetic.config_6_trackers()
+    B, iters = 600, 30
+    wl = synthetic.make_workload(pose_model, model_npz["offsets"], cfg, B, 1)
+    tp = wl["tgt_pos"][0].copy()
+    bad = [5, 301, 599]
+    tp[bad[0], 2, 1] = np.nan
+    tp[bad[1], 0, 0] = np.inf
+    tp[bad[2], 5, 2] = np.nan
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=0, max_iter=iters, stop_eps_pos=-1.0, stop_eps_rot=-1.0,
+              min_loss_incr=-float("inf"), joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
+    stats = {}
+    for path in (1, 3):
+        eng = engine_factory(B)
+        eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+        eng.run(tp, wl["tgt_rot"][0], wl["joints"], wl["weights"], decoder_path=path, **kw)
+        stats[path] = eng.frame_stats()
+        eng.close()
+    good = np.setdiff1d(np.arange(B), bad)
+    for path in (1, 3):
+        it, losses = stats[path]
+        assert (it[bad] == 1).all(), (path, it[bad])
+        assert (it[good] == iters).all()
+        assert np.isfinite(losses[good]).all() and (losses[good, 0] > 0).all() and (losses[good, 1] > 0).all()
+    rel = np.abs(stats[3][1][good] - stats[1][1][good]) / np.maximum(np.abs(stats[1][1][good]), 1e-6)
+    print(f"final losses of the {len(good)} finite clips, tcgen05 vs fp32 kernel: max relative difference {rel.max():.2e}")
+    assert rel.max() < 5e-3
