@@ -19,7 +19,7 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
   extern __shared__ __align__(1024) unsigned char raw[];
   Smem& S = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, warp = tid >> 5;
-  if (trace && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) trace[7] = clock64();
+  if (trace && blockIdx.x == (unsigned)trace[3] && blockIdx.y == 0 && tid == 0) trace[7] = clock64();
   if (tid == 0) {
     ff_init_barriers(S);
     fence_barrier_init();
@@ -119,6 +119,7 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
   long long* trace = nullptr;
   if (want_trace && ++n_launch == want_trace && cudaMallocManaged(&trace, kChunks * 8 * sizeof(long long)) == cudaSuccess) {
     memset(trace, 0, kChunks * 8 * sizeof(long long));
+    trace[3] = getenv("DP_FF_TRACE_CTA") ? atoll(getenv("DP_FF_TRACE_CTA")) : 0;  // which tile's CTA is clocked (a later wave: > 2 x SMs)
     cudaMemPrefetchAsync(trace, kChunks * 8 * sizeof(long long), 0, st);
   }
   tp_ff_tc_kernel<<<dim3(tiles, n_split), kThreads, smem, st>>>(wimg, blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, out, part, trace);

@@ -117,7 +117,7 @@ __device__ __forceinline__ void ff_tile(Smem& S, const uint32_t tmem, const unsi
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_loc = kChunks / n_split, c0 = split * n_loc;  // this call's chunks: c0 .. c0 + n_loc - 1
   const unsigned char* steps = wimg + TP_FF * 4;
-  const bool trace0 = trace && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool trace0 = trace && blockIdx.x == (unsigned)trace[3] && blockIdx.y == 0;  // trace[3]: the CTA to clock (DP_FF_TRACE_CTA)
   if (warp == 9 && elect_one()) {  // TMA producer, part 1 (no waits before the block barrier below): bias slice + first stages
     mbar_expect_tx(&S.b1full, (uint32_t)(n_loc * kHC * 4));
     tma_bulk_g2s(S.b1 + c0 * kHC, wimg + (size_t)c0 * kHC * 4, (uint32_t)(n_loc * kHC * 4), &S.b1full);
