@@ -57,6 +57,17 @@ struct dp_engine {
   int lookahead = DP_LOOKAHEAD;   // 1 disables (environment DP_LOOKAHEAD=1)
   float* d_target_pre = nullptr;  // (B, DP_LOOKAHEAD, 24)
   int look_left = 0, look_next = 0, look_last_row = -1;
+  // Predictor ahead of time in the small-batch streaming mode (window >= 4, <= DP_PREFETCH_MAX_CLIPS clips; DP_PRED_PREFETCH=0 turns it
+  // off).  The same three-frame slack as above: what the predictor reads at the window's first frame t (chronological ring rows
+  // 0..56) is complete once frame t-4 is, so the call for frame t is issued three frames early, on its own stream, with the ring head
+  // advanced by three and a second target buffer as destination; frame t only waits for its event and swaps the two buffers.  Same
+  // kernels on the same rows: bitwise the targets of the call at frame t.  A real-time caller (one frame every few milliseconds) never
+  // sees the ~0.45 ms predictor chain on its frame path; back-to-back callers overlap it with three frames.
+  float* d_target_alt = nullptr;
+  cudaStream_t pre_stream = nullptr;
+  cudaEvent_t ev_pre_fork = nullptr, ev_pre_done = nullptr;
+  bool pre_valid = false;
+  int pre_window = -1, prefetch = 1;
   // outputs / diagnostics
   int32_t* d_iters = nullptr;
   float* d_losses = nullptr;
@@ -84,6 +95,14 @@ struct dp_engine {
 };
 
 extern "C" const char* dp_engine_last_error(void) { return g_err.c_str(); }
+#define DP_PREFETCH_MAX_CLIPS 256
+// targets computed ahead of time are void (ring rows, model, path, window or clip set changed), or the predictor's work buffers are
+// about to be used by someone else: let the early call finish and forget it
+static void drop_prefetch(dp_engine* e) {
+  if (e->pre_valid) cudaStreamSynchronize(e->pre_stream);
+  e->pre_valid = false;
+}
+
 extern "C" int dp_engine_version(void) { return 100; }
 extern "C" size_t dp_engine_temporal_blob_floats(void) { return tp_layout().total; }
 extern "C" int dp_engine_n_clips(const dp_engine* e) { return e ? e->n_clips : 0; }
@@ -131,6 +150,12 @@ extern "C" int dp_engine_create(dp_engine** out, int device, int max_clips) {
   CK(cudaMalloc(&e->tw.dec_lat, V * TP_MAXT * TP_LAT * 4));
   CK(cudaMalloc(&e->tw.ffpart, DP_FF_PART_FLOATS * 4));
   e->tw.num_sms = e->num_sms;
+  e->tw.graphs = dp_temporal_graphs_create();
+  if (const char* s = getenv("DP_PRED_PREFETCH")) e->prefetch = atoi(s) != 0;
+  CK(cudaMalloc(&e->d_target_alt, B * (DP_MAX_WINDOW + 1) * DP_L * 4));
+  CK(cudaStreamCreateWithFlags(&e->pre_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->ev_pre_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_pre_done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->tw.ev_fork, cudaEventDisableTiming));
   for (int i = 0; i < DP_PRED_MAX_PARTS - 1; ++i) {
     CK(cudaStreamCreateWithFlags(&e->tw.st_extra[i], cudaStreamNonBlocking));
@@ -165,6 +190,11 @@ extern "C" int dp_engine_destroy(dp_engine* e) {
   for (int i = 0; i < DP_PRED_MAX_PARTS - 1; ++i)
     if (e->tw.st_extra[i]) { cudaStreamSynchronize(e->tw.st_extra[i]); cudaStreamDestroy(e->tw.st_extra[i]); cudaEventDestroy(e->tw.ev_join[i]); }
   if (e->tw.ev_fork) cudaEventDestroy(e->tw.ev_fork);
+  if (e->pre_stream) { cudaStreamSynchronize(e->pre_stream); cudaStreamDestroy(e->pre_stream); }
+  if (e->ev_pre_fork) cudaEventDestroy(e->ev_pre_fork);
+  if (e->ev_pre_done) cudaEventDestroy(e->ev_pre_done);
+  cudaFree(e->d_target_alt);
+  dp_temporal_graphs_destroy(e->tw.graphs);
   cudaStreamDestroy(e->stream);
   delete e;
   return DP_OK;
@@ -305,6 +335,7 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
   if (!e || !blob || !means_latent || !stds_latent) return fail(DP_ERR_ARG, "dp_engine_set_temporal_model: null argument");
   if (n_floats != e->tl.total) return fail(DP_ERR_ARG, "dp_engine_set_temporal_model: blob size mismatch");
   CK(cudaSetDevice(e->device));
+  drop_prefetch(e);
   if (!e->d_tblob) CK(cudaMalloc(&e->d_tblob, n_floats * 4));
   CK(cudaMemcpy(e->d_tblob, blob, n_floats * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->d_mu, means_latent, DP_L * 4, cudaMemcpyHostToDevice));
@@ -328,6 +359,7 @@ extern "C" int dp_engine_set_temporal_model(dp_engine* e, const float* blob, siz
   }
   e->look_left = 0;
   e->has_temporal = true;
+  dp_temporal_graphs_clear(e->tw.graphs);
   return DP_OK;
 }
 
@@ -337,6 +369,7 @@ extern "C" int dp_engine_init_clips(dp_engine* e, int n, const float* latent0, c
   if (n <= 0 || n > e->max_clips) return fail(DP_ERR_ARG, "dp_engine_init_clips: n_clips out of range");
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
+  drop_prefetch(e);
   std::vector<float> lb((size_t)n * DP_PAST * DP_L), hb((size_t)n * DP_PAST * DP_NH);
   for (int c = 0; c < n; ++c)
     for (int r = 0; r < DP_PAST; ++r) {
@@ -422,6 +455,7 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
                    cudaStream_t st) {
   const int W = p->temporal_future_window;
   if (e->target_rows != W + 1) {  // drag_pose.py:237-244: fresh zero buffer when the window changes
+    drop_prefetch(e);
     CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (W + 1) * DP_L * 4, st));
     e->target_rows = W + 1;
     // The reference keeps current_index: rows of the zero buffer are used until the index wraps to 0.  An index beyond the new
@@ -439,11 +473,30 @@ static int run_one(dp_engine* e, const dp_run_params* p, const int32_t* n_ee, co
     e->look_last_row = -1;
     if (e->current_index == 0) {
       if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
+      if (e->pre_valid && e->pre_window == W) {  // issued three frames ago into the other buffer
+        CK(cudaStreamWaitEvent(st, e->ev_pre_done, 0));
+        std::swap(e->d_target_buf, e->d_target_alt);
+        e->pre_valid = false;
+      } else {
+        drop_prefetch(e);
+        CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
+                           e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
+                           &e->launches));
+      }
+    } else if (e->prefetch && W >= 4 && e->current_index == W - 3 && e->n_clips <= DP_PREFETCH_MAX_CLIPS && e->has_temporal && !e->pre_valid) {
+      // three frames before the window's first frame: every ring row that frame's predictor call will read is final (frame t-4 is
+      // the newest one in the ring, enqueued on st before this point), and it will see the head three slots further on
+      CK(cudaEventRecord(e->ev_pre_fork, st));
+      CK(cudaStreamWaitEvent(e->pre_stream, e->ev_pre_fork, 0));
       CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
-                         e->ring_head, e->n_clips, W, e->d_target_buf, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles, st,
-                         &e->launches));
+                         (e->ring_head + 3) % DP_PAST, e->n_clips, W, e->d_target_alt, e->tw, e->predictor_path == 1 ? nullptr : e->d_fftiles,
+                         e->pre_stream, &e->launches));
+      CK(cudaEventRecord(e->ev_pre_done, e->pre_stream));
+      e->pre_valid = true;
+      e->pre_window = W;
     }
   } else {
+    drop_prefetch(e);
     if (e->look_left == 0) {  // targets of this frame and of the next lookahead - 1 frames in one call
       if (!e->has_temporal) return fail(DP_ERR_STATE, "temporal model not set");
       CK(dp_temporal_run(e->d_tblob, e->tl, e->d_mu, e->d_sigma, e->d_latent_buf, e->d_disp_buf, e->d_height_buf,
@@ -875,6 +928,7 @@ extern "C" int dp_engine_set_ring_buffers(dp_engine* e, const float* latent_buf,
   CK(cudaMemcpy(e->d_height_buf, height_buf, B * DP_PAST * DP_NH * 4, cudaMemcpyHostToDevice));
   e->ring_head = 0;  // rows were given in chronological order
   e->look_left = 0;  // targets computed ahead from the old rows are void
+  drop_prefetch(e);
   return DP_OK;
 }
 
@@ -885,6 +939,7 @@ extern "C" int dp_engine_predict_targets(dp_engine* e, int window, void* stream)
   if (window < 0 || window > DP_MAX_WINDOW || window % 4) return fail(DP_ERR_ARG, "window must be a multiple of 4 in [0,116]");
   CK(cudaSetDevice(e->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  drop_prefetch(e);  // this call uses the predictor's work buffers
   if (e->target_rows != window + 1) {
     CK(cudaMemsetAsync(e->d_target_buf, 0, (size_t)e->n_clips * (window + 1) * DP_L * 4, st));
     e->target_rows = window + 1;
@@ -948,6 +1003,7 @@ extern "C" int dp_engine_set_predictor_path(dp_engine* e, int path) {
   if (!e || path < 0 || path > 1) return fail(DP_ERR_ARG, "predictor path must be 0 (tcgen05 fp16x2 attention + FF) or 1 (fp32 CUDA-core kernels)");
   e->predictor_path = path;
   e->look_left = 0;
+  drop_prefetch(e);
   return DP_OK;
 }
 

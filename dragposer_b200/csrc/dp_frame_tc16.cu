@@ -24,6 +24,13 @@ namespace {
 #endif
 constexpr int NC = 32;                     // clip columns per CTA
 constexpr int kWarps = 16;
+// DP_KIN_GATE=1: the groups form two teams (gid & 1) that take turns in the kinematics pass -- team 0 starts pass n when team 1 has
+// finished pass n - 1, team 1 starts pass n when team 0 has finished pass n -- so that a sub-partition never runs more than two of
+// the 971-instruction passes at once and one team's tensor phases lie under the other team's kinematics.
+#ifndef DP_KIN_GATE
+#define DP_KIN_GATE 0
+#endif
+constexpr bool kKinGate = DP_KIN_GATE && DP_TC16_GROUPS == 4;
 constexpr int kGroups = DP_TC16_GROUPS;    // independent clip groups of a CTA (2 or 4)
 constexpr int kGW = kWarps / kGroups;      // warps per group: 8 (16 clips) or 4 (8 clips)
 constexpr int kGC = NC / kGroups;          // clip columns per group
@@ -81,6 +88,7 @@ struct SmemT {
   int iters[NC];
   uint64_t bar_w, bar_mma[kGroups];
   uint32_t tmem_base;
+  uint32_t kin_done[2];                             // kinematics passes finished by the groups of a team (DP_KIN_GATE)
   __device__ __forceinline__ const DpModelImageTC& M() const { return *reinterpret_cast<const DpModelImageTC*>(model); }
 };
 
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   const P2 inv3e2 = mk2(inv3e[0], inv3e[1]), lrot9e2 = mk2(lrot9e[0], lrot9e[1]);
   __syncwarp();
   fence_proxy_async();
+  if (kKinGate && threadIdx.x < 2) S.kin_done[threadIdx.x] = 0;
   mbar_wait(&S.bar_w, 0);  // model image (biases, statistics, skeleton tables) has landed
   tc_fence_before();
   __syncthreads();         // tensor-memory weights written by all warps; latent pieces and tracker rows of both groups in place
@@ -426,6 +435,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
   auto stamp = [&](int it, int k) {
     if (CLOCK && tl_on && it >= 40 && it < 44) A.phase_cycles[16 + gid * 24 + (it - 40) * 6 + k] = (unsigned long long)clock64();
   };
+  const bool gate_on = kKinGate && A.max_iter < (1 << 18);
   for (int it = 0; it < A.max_iter; ++it) {
     if (!group_or(gid, active[0] || active[1])) break;  // also publishes the latent pieces written by the Adam epilogue
     if (lane == 0) {  // the Adam epilogue reads two table entries: pull their lines into L1 now instead of stalling there
@@ -438,6 +448,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     phase_done(0);
     stamp(it, 1);
     float nlp[CPW] = {0.f, 0.f}, nlr[CPW] = {0.f, 0.f};
+    if (kKinGate && gate_on) {  // wait for this team's turn (the counters only grow; a group that leaves the loop opens the gate for good)
+      const uint32_t need = 2u * (uint32_t)(it + (gid & 1));
+      const volatile uint32_t* other = &S.kin_done[(gid & 1) ^ 1];
+      while ((int32_t)(*other - need) < 0) {}
+    }
     if (active[0] || active[1]) {  // both clips of the warp in one packed pass; results of a stopped clip are discarded
       // one packed pass; dL/dy leaves it scaled per clip into [16, 32) (exact powers of two, undone when dL/dz is read)
       const FkOut2 o = fk_loss2<true, false, true>(M, lane_idx, &S.y2[warp][0][0], &S.trk2[warp][0][0], &S.groot2[warp][0], &S.fkscr[warp][0],
@@ -450,6 +465,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     stamp(it, 2);
     if (!kIssuerFence) fence_proxy_async();  // the dL/dy pieces are read by the tensor core (async proxy)
     group_sync(gid);
+    if (kKinGate && gate_on && wg == 0 && lane == 0) atomicAdd(&S.kin_done[gid & 1], 1u);
     phase_done(1);
     stamp(it, 3);
     // backward layers; dL/dy pieces were written by the kinematics warps (EmitDyPieces)
@@ -554,6 +570,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) dp_frame_tc16_kernel(const __g
     stamp(it, 5);
   }
 
+  if (kKinGate && gate_on && wg == 0 && lane == 0) atomicAdd(&S.kin_done[gid & 1], 1u << 20);  // out of the loop: never make the other team wait again
   // ---- frame epilogue (drag_pose.py:369-414) from the LAST EVALUATED latent (pre-step)
   __syncwarp();
   if (lane < DP_L) {

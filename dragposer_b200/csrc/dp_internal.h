@@ -31,7 +31,15 @@ struct TpWork {
   int num_sms;
   cudaStream_t st_extra[DP_PRED_MAX_PARTS - 1];  // extra streams + fork/join events: the predictor of a large batch runs in parts
   cudaEvent_t ev_fork, ev_join[DP_PRED_MAX_PARTS - 1];
+  struct TpGraphCache* graphs;  // replayable launch chains of small predictor calls (dp_temporal.cu); null = always launch kernel by kernel
 };
+// A small predictor call (B = 1 streaming: ~70 kernels of a few microseconds each at window 16) is bound by launch gaps, not by work.
+// Everything after the ring-buffer embedding depends only on pointers and sizes that stay the same from call to call, so the chain is
+// captured once per (clips, window, look-ahead, path, buffers) and replayed as ONE cudaGraphLaunch; the embedding kernel, which takes
+// the moving ring head by value, is launched in front of it.  Same kernels, same arguments, same order: bitwise the same targets.
+struct TpGraphCache* dp_temporal_graphs_create();
+void dp_temporal_graphs_clear(struct TpGraphCache* c);    // drop every captured chain (model / path changes)
+void dp_temporal_graphs_destroy(struct TpGraphCache* c);
 #define DP_FF_PART_FLOATS ((size_t)8 * 296 * 128 * TP_D / 2)
 
 cudaError_t dp_frame_simt_launch(const DpFrameArgs& args, int num_sms, cudaStream_t stream);

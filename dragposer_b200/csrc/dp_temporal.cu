@@ -406,14 +406,18 @@ static const size_t kFfSmem = sizeof(float) * (2 * TP_D * FF_HC + FF_TM * (TP_D 
 // height_buf are the UNSHIFTED ring buffers, target_buf and the work buffers of `w` start at the part's first virtual clip.
 static cudaError_t run_part(const float* blob, const TpLayout& L, const float* mu, const float* sigma, const float* latent_buf,
                             const float* disp_buf, const float* height_buf, int head, int B, int v0, int J, int window, float* target_buf,
-                            const TpWork& w, size_t part_floats, const unsigned char* fftiles, cudaStream_t st, long long* launches) {
+                            const TpWork& w, size_t part_floats, const unsigned char* fftiles, cudaStream_t st, long long* launches,
+                            int stage = 0) {  // stage 0: everything; 1: only the embedding (the one kernel that sees `head`); 2: the rest
   cudaError_t err = cudaSuccess;
 
   float* e = w.enc;
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
-  tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, v0, J, w.enc, w.dec_lat);
-  ++*launches;
+  if (stage != 2) {
+    tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, v0, J, w.enc, w.dec_lat);
+    ++*launches;
+    if (stage == 1) return cudaGetLastError();
+  }
   for (int l = 0; l < TP_NENC; ++l) {
     if (fftiles)
       err = dp_attn_tc_launch(fftiles + DP_TC_ATT_OFFSET + (size_t)l * ATT_LAYER_BYTES, blob, L.enc[l].n1, e, TP_S, TP_S, e, TP_S, TP_S, B, e2, st);
@@ -504,6 +508,46 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
   return cudaGetLastError();
 }
 
+struct TpGraphCache {
+  struct Entry {
+    int B, window, J, state;  // state: 0 seen once, -1 not capturable
+    const void *blob, *fftiles, *mu, *sigma, *target;
+    cudaGraphExec_t exec;
+    long long launches;
+  };
+  static constexpr int kMax = 8;
+  Entry e[kMax];
+  int n = 0, next = 0;
+  Entry* find(int B, int window, int J, const void* blob, const void* fftiles, const void* mu, const void* sigma, const void* target) {
+    for (int i = 0; i < n; ++i)
+      if (e[i].B == B && e[i].window == window && e[i].J == J && e[i].blob == blob && e[i].fftiles == fftiles && e[i].mu == mu &&
+          e[i].sigma == sigma && e[i].target == target)
+        return &e[i];
+    return nullptr;
+  }
+  void add(int B, int window, int J, const void* blob, const void* fftiles, const void* mu, const void* sigma, const void* target) {
+    Entry* s = n < kMax ? &e[n++] : &e[next++ % kMax];  // full: recycle round robin
+    if (s->exec) cudaGraphExecDestroy(s->exec);
+    *s = Entry{B, window, J, 0, blob, fftiles, mu, sigma, target, nullptr, 0};
+  }
+  void clear() {
+    for (int i = 0; i < n; ++i)
+      if (e[i].exec) cudaGraphExecDestroy(e[i].exec);
+    n = next = 0;
+  }
+};
+TpGraphCache* dp_temporal_graphs_create() {
+  TpGraphCache* c = new TpGraphCache();
+  memset(c->e, 0, sizeof(c->e));
+  return c;
+}
+void dp_temporal_graphs_clear(TpGraphCache* c) { if (c) c->clear(); }
+void dp_temporal_graphs_destroy(TpGraphCache* c) {
+  if (!c) return;
+  c->clear();
+  delete c;
+}
+
 // The predictor of a large batch runs as several parts on their own streams: each kernel of a part has fewer tiles than the device has
 // CTA slots, so the block scheduler interleaves the parts and fills the tail of one kernel with the head of another
 // (448 tiles on 296 slots otherwise leave a third, half-empty round in every encoder kernel).
@@ -517,8 +561,45 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
   static const int split_min = getenv("DP_PRED_SPLIT_MIN") ? atoi(getenv("DP_PRED_SPLIT_MIN")) : 2048;
   static const int n_parts_env = getenv("DP_PRED_PARTS") ? atoi(getenv("DP_PRED_PARTS")) : DP_PRED_PARTS_DEFAULT;
   const int n_parts = n_parts_env < 1 ? 1 : (n_parts_env > DP_PRED_MAX_PARTS ? DP_PRED_MAX_PARTS : n_parts_env);
-  if (!fftiles || n_parts == 1 || B < split_min)
-    return run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, 0, J, window, target_buf, w, DP_FF_PART_FLOATS, fftiles, st, launches);
+  if (!fftiles || n_parts == 1 || B < split_min) {
+    // DP_PRED_GRAPH=0 turns the replay off; the pipeline-clock switches synchronise inside a launch function, which a capture forbids
+    static const int use_graphs = (getenv("DP_PRED_GRAPH") ? atoi(getenv("DP_PRED_GRAPH")) : 1) && !getenv("DP_FF_TRACE") && !getenv("DP_ATTN_TRACE");
+    auto eager = [&](int stage) {
+      return run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, 0, J, window, target_buf, w, DP_FF_PART_FLOATS, fftiles, st, launches, stage);
+    };
+    if (!use_graphs || !w.graphs) return eager(0);
+    // replayable chain (see dp_internal.h): first call of a shape runs kernel by kernel (it also does the one-off function-attribute
+    // set-up, which cannot be captured), the second one is captured, later ones replay
+    TpGraphCache::Entry* g = w.graphs->find(B, window, J, blob, fftiles, mu, sigma, target_buf);
+    if (!g) {
+      w.graphs->add(B, window, J, blob, fftiles, mu, sigma, target_buf);
+      return eager(0);
+    }
+    if (g->state < 0) return eager(0);  // capture failed once (e.g. a caller's stream that cannot be captured): stay with plain launches
+    if ((err = eager(1)) != cudaSuccess) return err;
+    if (!g->exec) {
+      long long n = 0;
+      cudaGraph_t graph = nullptr;
+      cudaError_t cerr = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      if (cerr == cudaSuccess) {
+        cerr = run_part(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, 0, J, window, target_buf, w, DP_FF_PART_FLOATS, fftiles, st, &n, 2);
+        const cudaError_t eerr = cudaStreamEndCapture(st, &graph);
+        if (cerr == cudaSuccess) cerr = eerr;
+      }
+      if (cerr == cudaSuccess) cerr = cudaGraphInstantiate(&g->exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (cerr != cudaSuccess) {
+        cudaGetLastError();  // clear the sticky-free error of the failed capture
+        g->exec = nullptr;
+        g->state = -1;
+        return eager(2);
+      }
+      g->launches = n;
+    }
+    if ((err = cudaGraphLaunch(g->exec, st)) != cudaSuccess) return err;
+    *launches += g->launches;
+    return cudaSuccess;
+  }
   if ((err = cudaEventRecord(w.ev_fork, st)) != cudaSuccess) return err;
   const int per = (B + n_parts - 1) / n_parts;
   for (int p = 0; p < n_parts; ++p) {

@@ -216,6 +216,46 @@ def test_run_frames_pipelined_equals_frame_by_frame(engine_factory, pose_model, 
     assert np.isfinite(outs[0][0]).all()
 
 
+@pytest.mark.parametrize("mode", ["frames", "single"])
+def test_predictor_issued_three_frames_early_gives_bitwise_the_same_frames(engine_factory, pose_model, model_npz, monkeypatch, mode):
+    """Small-batch streaming mode (window 16): the predictor call of a window's first frame is issued three frames early on its own
+    stream into a second target buffer (dp_engine.cu:run_one; its inputs end three frames in the past).  40 frames -- two such early
+    calls, the second one a CUDA-graph replay -- must equal the engine that calls the predictor at the frame itself, bit for bit,
+    including the target rows a caller reads back, through run() and through the pipelined multi-frame call, with a
+    set_ring_buffers in the middle of a window (which voids the early call)."""
+    offsets = model_npz["offsets"]
+    cfg = synthetic.config_3_trackers()
+    assert cfg.temporal_future_window == 16
+    B, T = 3, 40
+    wl = synthetic.make_workload(pose_model, offsets, cfg, B, T, variable_mask=True)
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=16, max_iter=8,
+              joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
+    outs = []
+    for prefetch in ("1", "0"):
+        monkeypatch.setenv("DP_PRED_PREFETCH", prefetch)  # read when the engine is created
+        eng = engine_factory(8)
+        eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+        ps, gs, tb = [], [], []
+        if mode == "frames":
+            p_, g_ = eng.run_frames(wl["tgt_pos"], wl["tgt_rot"], wl["joints_tb"], wl["weights_tb"], n_ee=wl["n_ee"], **kw)
+            ps, gs = list(p_), list(g_)
+            tb.append(eng.state(16)["target_buf"].copy())
+        else:
+            for t in range(T):
+                if t == 30:  # between the early call (frame 29 = index 13) and its use (frame 32): the early targets are void
+                    st = eng.state(16)
+                    order = (np.arange(60) + 7) % 60  # any other chronological content
+                    eng.set_ring_buffers(st["latent_buf"][:, order], st["disp_buf"][:, order], st["height_buf"][:, order])
+                p_, g_ = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints_tb"][t], wl["weights_tb"][t], n_ee=wl["n_ee"][t], **kw)
+                ps.append(p_); gs.append(g_)
+                if t in (15, 16, 31, 32, 39):
+                    tb.append(eng.state(16)["target_buf"].copy())
+        outs.append((np.stack(ps), np.stack(gs), np.stack(tb)))
+        eng.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
 def test_clip_order_is_exact(engine_factory, pose_model, model_npz, path):
     """Clip indexing: shuffling the clips of a batch shuffles the results and nothing else, bit for bit (a clip's arithmetic does
@@ -321,6 +361,37 @@ def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory,
         err = np.abs(tc[:, rows] - ref[:, rows]).max()
         print(f"{n_clips} clips, window {W}: tensor-core vs CUDA-core predictor max abs diff {err:.2e}")
         assert np.isfinite(tc[:, rows]).all() and err <= 2e-5
+
+
+@pytest.mark.parametrize("n_clips", [1, 37])
+def test_predictor_graph_replay_is_bitwise_the_kernel_by_kernel_chain(golden_dir, engine_factory, n_clips):
+    """A small predictor call is captured into a CUDA graph on its second use and replayed afterwards (dp_temporal.cu): the first
+    (kernel by kernel), second (capture + launch) and third (replay) call agree bit for bit, and a replay on NEW ring contents still
+    matches the fp32 CUDA-core chain, which is never captured with the same key."""
+    g = np.load(os.path.join(golden_dir, "ref_temporal.npz"))
+    rng = np.random.default_rng(11)
+    reps = -(-n_clips // g["latent_buf"].shape[0])
+    tile = lambda a: np.tile(a, (reps, 1, 1))[:n_clips]
+    eng = engine_factory(64)
+    eng.set_initial_state(np.zeros((n_clips, 24)), np.zeros((n_clips, 3)), np.tile([[1.0, 0, 0, 0]], (n_clips, 1)), np.zeros((n_clips, 6)))
+    for W in (0, 16):
+        eng.set_ring_buffers(tile(g["latent_buf"]), tile(g["disp_buf"]), tile(g["height_buf"]))
+        rows = slice(0, max(W, 1))
+        a = eng.predict_targets(W)[:, rows].copy()
+        n0 = eng.launch_count()
+        b = eng.predict_targets(W)[:, rows].copy()
+        n1 = eng.launch_count()
+        c = eng.predict_targets(W)[:, rows].copy()
+        n2 = eng.launch_count()
+        assert np.isfinite(a).all() and np.array_equal(a, b) and np.array_equal(a, c)
+        assert n1 - n0 == n2 - n1 > 0  # the replay reports the kernels it launches
+        lat = tile(g["latent_buf"]) + rng.normal(0, 0.05, (n_clips, 60, 24)).astype(np.float32)
+        eng.set_ring_buffers(lat, tile(g["disp_buf"]), tile(g["height_buf"]))
+        d = eng.predict_targets(W)[:, rows].copy()  # replay on new inputs
+        eng.set_predictor_path(1)
+        ref = eng.predict_targets(W)[:, rows].copy()
+        eng.set_predictor_path(0)
+        assert np.abs(d - a).max() > 1e-4 and np.abs(d - ref).max() <= 2e-5
 
 
 @pytest.mark.parametrize("path", [1, 3], ids=["fp32", "tcgen05-fp16x2"])
