@@ -225,7 +225,13 @@ def dll_latency(calls=1000):
     n_fixed = max(160, calls // 4)
     wl, quats = latency_stream(calls + 24)
     out = {"boundary": "DragPoserDLL C ABI drag_pose, B = 1, 6 trackers, host buffers in/out, window 16",
-           "stream": "clip 0 of the synthetic 6-tracker workload (latent random walk), one new target set per call"}
+           "stream": "clip 0 of the synthetic 6-tracker workload (latent random walk), one new target set per call",
+           "predictor": "every 16th frame needs new targets (5 decoder passes, ~70 kernels, 0.41 ms on the device as a replayed CUDA graph); "
+                        "its inputs end three frames in the past, so the engine issues that call three frames early on a side stream "
+                        "(dp_engine.cu:run_one, DP_PRED_PREFETCH=0 turns it off) and 'predictor_frames' only wait for what is left of it: "
+                        "nothing in this per-frame call sequence (DragPoser.cs:137-173; the un-timed setter calls between two drag_pose "
+                        "calls are part of it), 0.28 ms for a caller that issues drag_pose back to back (scripts/latency_by_index.py); "
+                        "without the early call: p50 0.56 ms on those frames (start of round 2), 0.45 ms with the graph alone"}
     settings = (("max_iter_5", 5, False, calls), ("max_iter_10", 10, False, calls), ("max_iter_100", 100, False, max(200, calls // 2)),
                 ("fixed_100_iterations", 100, True, n_fixed))
     with tempfile.TemporaryDirectory() as d:

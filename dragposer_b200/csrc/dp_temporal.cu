@@ -601,8 +601,13 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     return cudaSuccess;
   }
   if ((err = cudaEventRecord(w.ev_fork, st)) != cudaSuccess) return err;
-  const int per = (B + n_parts - 1) / n_parts;
-  for (int p = 0; p < n_parts; ++p) {
+  static const int part_clips_env = getenv("DP_PRED_PART_CLIPS") ? atoi(getenv("DP_PRED_PART_CLIPS")) : 0;
+  int per = (B + n_parts - 1) / n_parts, parts = n_parts;
+  if (part_clips_env > 0 && (B + part_clips_env - 1) / part_clips_env <= DP_PRED_MAX_PARTS) {
+    per = part_clips_env;
+    parts = (B + per - 1) / per;
+  }
+  for (int p = 0; p < parts; ++p) {
     const int b0 = p * per, nb = (b0 + per <= B ? per : B - b0);
     if (nb <= 0) break;
     cudaStream_t sp = p == 0 ? st : w.st_extra[p - 1];
