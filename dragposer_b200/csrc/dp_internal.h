@@ -1,5 +1,6 @@
 // dp_internal.h -- declarations shared by the engine translation units.
 #pragma once
+#include <cstdlib>
 #include <atomic>
 
 #include "dp_common.cuh"
@@ -62,6 +63,11 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
 // train_temporal.param["past_frames"] ends at row 56 of 60 (drag_pose.py:249-266), so what it reads j <= 3 frames from now is
 // already in the ring today.
 #define DP_LOOKAHEAD 4
+// single-token decoder pass with four clips per warp (default) or one (DP_DEC_ROWS=0, the cross-check); read on every call
+inline int dp_dec_rows() {
+  const char* s = getenv("DP_DEC_ROWS");
+  return !(s && s[0] == '0');
+}
 void dp_attn_tc_pack(const float* w_in_t, const float* b_in, const float* w_out_t, const float* b_out, unsigned char* dst);
 cudaError_t dp_attn_tc_launch(const unsigned char* wimg, const float* blob, const TpNorm& N1, const float* xq, int T, int q_stride,
                               const float* xkv, int S, int kv_stride, int n_clips, float* out, cudaStream_t st);

@@ -117,6 +117,49 @@ __global__ void __launch_bounds__(256) tp_dec_start_kernel(const float* __restri
   if (lane + 32 < TP_D) dst[lane + 32] = x1;
 }
 
+// The same for TP_R clips per warp (tp_self_attn_rows / tp_cross_attn_rows: every weight is loaded once per four clips); bitwise the
+// results of tp_dec_start_kernel, which stays as the cross-check (DP_DEC_ROWS=0).
+__global__ void __launch_bounds__(128) tp_dec_start_rows_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ dec_lat,
+                                                                const float* __restrict__ wk_t, const float* __restrict__ mem, int n_clips,
+                                                                float* __restrict__ dec) {
+  __shared__ __align__(16) float scr[4][TP_XR_SCR];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tp_prefetch_l1(blob + L.dec_in_w, TP_LAT * TP_D);
+  tp_prefetch_attn(blob, L.dec[0].sa, L.dec[0].n1);
+  tp_prefetch_attn(blob, L.dec[0].ca, L.dec[0].n2);
+  tp_prefetch_l1(wk_t, TP_D * TP_D);
+  const int b0 = (blockIdx.x * 4 + warp) * TP_R;
+  if (b0 >= n_clips) return;
+  const int n_here = min(TP_R, n_clips - b0);
+  float* xs = scr[warp];
+  if (lane < TP_LAT) {
+    float v[TP_R];
+#pragma unroll
+    for (int r = 0; r < TP_R; ++r) v[r] = dec_lat[(size_t)(b0 + min(r, n_here - 1)) * TP_MAXT * TP_LAT + lane];
+    *reinterpret_cast<float4*>(xs + 4 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncwarp();
+  float x0[TP_R], x1[TP_R];
+  tp_warp_matvec_asc_r<TP_LAT>(xs, blob + L.dec_in_w, TP_D, blob + L.dec_in_b, TP_D, lane, x0, x1);
+  const bool has1 = lane + 32 < TP_D;
+  const float pe0 = blob[L.pe + lane], pe1 = has1 ? blob[L.pe + lane + 32] : 0.0f;
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    x0[r] += pe0;
+    if (has1) x1[r] += pe1;
+  }
+  tp_self_attn_rows(blob, L.dec[0].sa, L.dec[0].n1, xs, lane, x0, x1);
+  tp_cross_attn_rows(blob, L.dec[0].ca, L.dec[0].n2, wk_t, mem + (size_t)b0 * TP_S * TP_D, n_here, scr[warp], lane, x0, x1);
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    if (r < n_here) {
+      float* dst = dec + (size_t)(b0 + r) * TP_MAXT * TP_D;
+      dst[lane] = x0[r];
+      if (has1) dst[lane + 32] = x1[r];
+    }
+  }
+}
+
 // ---- out = LayerNorm(xq + MHA(xq, xkv, xkv)); one CTA (160 threads) per clip.
 // Projections are register tiled: a thread owns ONE output feature and keeps the accumulators of up to 16
 // tokens in registers, so every weight is fetched once per CTA (coalesced, L1/L2 resident) and every
@@ -435,6 +478,9 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
     }
     *launches += 2;
   }
+#ifdef DP_DEBUG_SKIP_DEC  // measurement only (wrong targets): how much of a call is the decoder?
+  if (B > 1024) return cudaGetLastError();
+#endif
   int T = 1;
   static const int fused_dec = getenv("DP_PRED_FUSED_DEC") ? atoi(getenv("DP_PRED_FUSED_DEC")) : 1;
   for (int i = 0; i <= window; i += 4, ++T) {
@@ -445,7 +491,10 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
       float* cur = w.dec;
       float* nxt = w.dec2;
       const float* wk_t = reinterpret_cast<const float*>(fftiles + DP_TC_XA_OFFSET);  // [layer][key feature][input]
-      tp_dec_start_kernel<<<(B + 7) / 8, 256, 0, st>>>(blob, L, w.dec_lat, wk_t, e, B, cur);
+      if (dp_dec_rows())
+        tp_dec_start_rows_kernel<<<(B + 4 * TP_R - 1) / (4 * TP_R), 128, 0, st>>>(blob, L, w.dec_lat, wk_t, e, B, cur);
+      else
+        tp_dec_start_kernel<<<(B + 7) / 8, 256, 0, st>>>(blob, L, w.dec_lat, wk_t, e, B, cur);
       ++*launches;
       for (int l = 0; l < TP_NDEC; ++l) {
         TpFfTail tail;
@@ -570,9 +619,10 @@ cudaError_t dp_temporal_run(const float* blob, const TpLayout& L, const float* m
     if (!use_graphs || !w.graphs) return eager(0);
     // replayable chain (see dp_internal.h): first call of a shape runs kernel by kernel (it also does the one-off function-attribute
     // set-up, which cannot be captured), the second one is captured, later ones replay
-    TpGraphCache::Entry* g = w.graphs->find(B, window, J, blob, fftiles, mu, sigma, target_buf);
+    const int variant = J | (dp_dec_rows() << 8);  // everything that changes which kernels the chain holds
+    TpGraphCache::Entry* g = w.graphs->find(B, window, variant, blob, fftiles, mu, sigma, target_buf);
     if (!g) {
-      w.graphs->add(B, window, J, blob, fftiles, mu, sigma, target_buf);
+      w.graphs->add(B, window, variant, blob, fftiles, mu, sigma, target_buf);
       return eager(0);
     }
     if (g->state < 0) return eager(0);  // capture failed once (e.g. a caller's stream that cannot be captured): stay with plain launches

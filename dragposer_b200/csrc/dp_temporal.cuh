@@ -276,6 +276,254 @@ __device__ __forceinline__ void tp_cross_attn_single(const float* __restrict__ b
   x1 += y1;
   tp_ln_row_warp(x0, x1, blob + N.w, blob + N.b, lane);
 }
+// ---- the same single-token blocks for TP_R rows per warp.  The blocks above are chains of 48 x 48 matrix-vector products whose
+// cost is the weight loads (two per multiply-add pair and row); here a warp carries TP_R rows through every product, so a weight is
+// loaded once per TP_R rows and the inputs of all rows at one k arrive as ONE broadcast LDS.128 (staging layout [k][row]): 12 memory
+// instructions per 32 multiply-adds instead of 9 per 8.  Every row's arithmetic -- the order of every fused multiply-add, the softmax,
+// the LayerNorm reductions -- is exactly that of the one-row functions, so the results are bitwise the same.
+#define TP_R 4
+// Every launch starts with a cold L1, and a warp walks the ~80 KB of weights of its blocks exactly once with eight loads in flight:
+// without help the whole kernel is one L2-latency-bound pass (measured: 47 us for 8 192 rows against ~10 us of issue time).  Each CTA
+// therefore asks for all the lines it is going to read up front, in parallel.
+__device__ __forceinline__ void tp_prefetch_l1(const float* __restrict__ p, int n_floats) {
+  for (int i = threadIdx.x * 32; i < n_floats; i += blockDim.x * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+}
+__device__ __forceinline__ void tp_prefetch_attn(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N) {
+  tp_prefetch_l1(blob + A.w_in, 3 * TP_D * TP_D);
+  tp_prefetch_l1(blob + A.w_out, TP_D * TP_D);
+  tp_prefetch_l1(blob + A.b_in, 3 * TP_D);
+  tp_prefetch_l1(blob + A.b_out, TP_D);
+  tp_prefetch_l1(blob + N.w, TP_D);
+  tp_prefetch_l1(blob + N.b, TP_D);
+}
+// per-warp scratch (floats): staging [48][TP_R] | per-row per-head rows [TP_R][4][52] (folded queries, then weighted memory sums) |
+// ONE clip's 14 memory rows [14][52] | its probabilities [14][4]
+#define TP_XR_SCR (TP_D * TP_R + TP_R * TP_H * TP_XA_STRIDE + TP_S * TP_XA_STRIDE + TP_S * TP_H)
+__device__ __forceinline__ void tp_stage_rows(float* __restrict__ xs, int lane, const float (&v0)[TP_R], const float (&v1)[TP_R]) {
+  static_assert(TP_R == 4, "one float4 per k");
+  __syncwarp();  // earlier readers of the staging rows are done
+  *reinterpret_cast<float4*>(xs + 4 * lane) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+  if (lane + 32 < TP_D) *reinterpret_cast<float4*>(xs + 4 * (lane + 32)) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+  __syncwarp();
+}
+// tp_warp_matvec_s for TP_R rows (inputs staged as [k][row])
+template <int K>
+__device__ __forceinline__ void tp_warp_matvec_r(const float* __restrict__ xs, const float* __restrict__ W, int ldw, int col0,
+                                                 const float* __restrict__ bias, int n_out, int lane, float (&y0)[TP_R], float (&y1)[TP_R]) {
+  static_assert(K % 4 == 0, "vectorised input rows");
+  const bool has0 = lane < n_out, has1 = lane + 32 < n_out;
+  const float b0 = has0 ? bias[lane] : 0.0f, b1 = has1 ? bias[lane + 32] : 0.0f;
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) { y0[r] = b0; y1[r] = b1; }
+  const float* w = W + col0 + (has0 ? lane : 0);
+  const float* w1 = W + col0 + (has1 ? lane + 32 : 0);
+#pragma unroll 4
+  for (int i = 0; i < K; i += 4) {
+    float xk[4][TP_R];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(xk[j]) = *reinterpret_cast<const float4*>(xs + 4 * (i + j));
+    const float wa0 = w[(size_t)i * ldw], wa1 = w[(size_t)(i + 1) * ldw], wa2 = w[(size_t)(i + 2) * ldw], wa3 = w[(size_t)(i + 3) * ldw];
+    const float wb0 = w1[(size_t)i * ldw], wb1 = w1[(size_t)(i + 1) * ldw], wb2 = w1[(size_t)(i + 2) * ldw], wb3 = w1[(size_t)(i + 3) * ldw];
+#pragma unroll
+    for (int r = 0; r < TP_R; ++r) {
+      y0[r] = fmaf(xk[0][r], wa0, fmaf(xk[1][r], wa1, fmaf(xk[2][r], wa2, fmaf(xk[3][r], wa3, y0[r]))));
+      y1[r] = fmaf(xk[0][r], wb0, fmaf(xk[1][r], wb1, fmaf(xk[2][r], wb2, fmaf(xk[3][r], wb3, y1[r]))));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    if (!has0) y0[r] = 0.0f;
+    if (!has1) y1[r] = 0.0f;
+  }
+}
+// tp_warp_matvec (ascending one-by-one accumulation: the embedding and the prediction head) for TP_R rows, inputs staged as [k][row]
+template <int K>
+__device__ __forceinline__ void tp_warp_matvec_asc_r(const float* __restrict__ xs, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                                                     int n_out, int lane, float (&y0)[TP_R], float (&y1)[TP_R]) {
+  const bool has0 = lane < n_out, has1 = lane + 32 < n_out;
+  const float b0 = has0 ? bias[lane] : 0.0f, b1 = has1 ? bias[lane + 32] : 0.0f;
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) { y0[r] = b0; y1[r] = b1; }
+#pragma unroll 8
+  for (int i = 0; i < K; ++i) {
+    float xi[TP_R];
+    *reinterpret_cast<float4*>(xi) = *reinterpret_cast<const float4*>(xs + 4 * i);
+    const float* w = W + (size_t)i * ldw;
+    const float wa = has0 ? w[lane] : 0.0f, wb = has1 ? w[lane + 32] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < TP_R; ++r) {
+      if (has0) y0[r] = fmaf(xi[r], wa, y0[r]);
+      if (has1) y1[r] = fmaf(xi[r], wb, y1[r]);
+    }
+  }
+}
+__device__ __forceinline__ void tp_self_attn_rows(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N, float* __restrict__ xs, int lane,
+                                                  float (&x0)[TP_R], float (&x1)[TP_R]) {
+  float v0[TP_R], v1[TP_R], o0[TP_R], o1[TP_R];
+  tp_stage_rows(xs, lane, x0, x1);
+  tp_warp_matvec_r<TP_D>(xs, blob + A.w_in, 3 * TP_D, 2 * TP_D, blob + A.b_in + 2 * TP_D, TP_D, lane, v0, v1);
+  tp_stage_rows(xs, lane, v0, v1);
+  tp_warp_matvec_r<TP_D>(xs, blob + A.w_out, TP_D, 0, blob + A.b_out, TP_D, lane, o0, o1);
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    x0[r] += o0[r];
+    x1[r] += o1[r];
+    tp_ln_row_warp(x0[r], x1[r], blob + N.w, blob + N.b, lane);
+  }
+}
+// mem: encoder memory of the FIRST of the warp's rows (consecutive clips: row r at mem + r * TP_S * TP_D); rows >= n_here are padding
+// (they read the last valid clip's memory and their results are discarded by the caller).  scr: TP_XR_SCR floats owned by this warp.
+__device__ __forceinline__ void tp_cross_attn_rows(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N, const float* __restrict__ wk_t,
+                                                   const float* __restrict__ mem, int n_here, float* __restrict__ scr, int lane,
+                                                   float (&x0)[TP_R], float (&x1)[TP_R]) {
+  const bool has1 = lane + 32 < TP_D;
+  const float* Win = blob + A.w_in;   // [in 48][q 48 | k 48 | v 48]
+  float* xs = scr;                                      // staging [48][TP_R]
+  float* hr = xs + TP_D * TP_R;                         // [TP_R][TP_H][TP_XA_STRIDE]
+  float* ms = hr + TP_R * TP_H * TP_XA_STRIDE;          // one clip's memory rows
+  float* as = ms + TP_S * TP_XA_STRIDE;                 // its probabilities a[s][h]
+  static_assert((TP_D * TP_R) % 4 == 0 && (TP_R * TP_H * TP_XA_STRIDE) % 4 == 0 && (TP_S * TP_XA_STRIDE) % 4 == 0, "16-byte aligned scratch parts");
+  float q0[TP_R], q1[TP_R];
+  tp_stage_rows(xs, lane, x0, x1);
+  tp_warp_matvec_r<TP_D>(xs, Win, 3 * TP_D, 0, blob + A.b_in, TP_D, lane, q0, q1);
+  tp_stage_rows(xs, lane, q0, q1);
+  // qt_{r,h}[c] = (1 / sqrt(12)) sum_{d in head h} W_k[d][c] q_r[d]; this lane owns c = lane and c = lane + 32
+  {
+    const float scale = rsqrtf((float)TP_HD);
+#pragma unroll
+    for (int h = 0; h < TP_H; ++h) {
+      float a0[TP_R], a1[TP_R];
+#pragma unroll
+      for (int r = 0; r < TP_R; ++r) a0[r] = a1[r] = 0.0f;
+#pragma unroll
+      for (int j4 = 0; j4 < TP_HD; j4 += 4) {
+        const int d = h * TP_HD + j4;
+        float qk[4][TP_R];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(qk[j]) = *reinterpret_cast<const float4*>(xs + 4 * (d + j));
+        const float wa0 = wk_t[d * TP_D + lane], wa1 = wk_t[(d + 1) * TP_D + lane], wa2 = wk_t[(d + 2) * TP_D + lane], wa3 = wk_t[(d + 3) * TP_D + lane];
+        float wb0 = 0.f, wb1 = 0.f, wb2 = 0.f, wb3 = 0.f;
+        if (has1) { wb0 = wk_t[d * TP_D + lane + 32]; wb1 = wk_t[(d + 1) * TP_D + lane + 32]; wb2 = wk_t[(d + 2) * TP_D + lane + 32]; wb3 = wk_t[(d + 3) * TP_D + lane + 32]; }
+#pragma unroll
+        for (int r = 0; r < TP_R; ++r) {
+          a0[r] = fmaf(wa0, qk[0][r], fmaf(wa1, qk[1][r], fmaf(wa2, qk[2][r], fmaf(wa3, qk[3][r], a0[r]))));
+          if (has1) a1[r] = fmaf(wb0, qk[0][r], fmaf(wb1, qk[1][r], fmaf(wb2, qk[2][r], fmaf(wb3, qk[3][r], a1[r]))));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TP_R; ++r) {
+        hr[(r * TP_H + h) * TP_XA_STRIDE + lane] = a0[r] * scale;
+        if (has1) hr[(r * TP_H + h) * TP_XA_STRIDE + lane + 32] = a1[r] * scale;
+      }
+    }
+  }
+  // per clip: scores of key s on lane s (all heads), softmax across the lanes, weighted memory sums over its own folded queries
+  // (the next clip's memory rows travel while this clip's scores are computed: a warp has few others to hide that latency behind)
+  constexpr int kMemV = TP_S * (TP_D / 4), kMemPer = (kMemV + 31) / 32;
+  float4 pre[kMemPer];
+  auto fetch = [&](int r) {
+    const float4* mr = reinterpret_cast<const float4*>(mem + (size_t)(r < n_here ? r : n_here - 1) * TP_S * TP_D);
+#pragma unroll
+    for (int j = 0; j < kMemPer; ++j) {
+      const int i = lane + 32 * j;
+      pre[j] = i < kMemV ? mr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  for (int r = 0; r < TP_R; ++r) {
+    float* hq = hr + r * TP_H * TP_XA_STRIDE;
+    __syncwarp();  // folded queries published (first clip); the previous clip's readers of ms / as are done
+#pragma unroll
+    for (int j = 0; j < kMemPer; ++j) {
+      const int i = lane + 32 * j;
+      if (i < kMemV) reinterpret_cast<float4*>(ms + (i / (TP_D / 4)) * TP_XA_STRIDE)[i % (TP_D / 4)] = pre[j];
+    }
+    if (r + 1 < TP_R) fetch(r + 1);
+    __syncwarp();
+    {
+      float a[TP_H];
+      const bool key = lane < TP_S;
+      float sc[TP_H] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float4* mrow = reinterpret_cast<const float4*>(ms + (key ? lane : 0) * TP_XA_STRIDE);
+#pragma unroll
+      for (int c4 = 0; c4 < TP_D / 4; ++c4) {
+        const float4 mv = mrow[c4];
+#pragma unroll
+        for (int h = 0; h < TP_H; ++h) {
+          const float4 qv = reinterpret_cast<const float4*>(hq + h * TP_XA_STRIDE)[c4];
+          sc[h] = fmaf(mv.x, qv.x, fmaf(mv.y, qv.y, fmaf(mv.z, qv.z, fmaf(mv.w, qv.w, sc[h]))));
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < TP_H; ++h) {
+        const float v = key ? sc[h] : -3.0e38f;
+        float mx = v;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float p = key ? expf(v - mx) : 0.0f;
+        float sum = p;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        a[h] = key ? p / sum : 0.0f;
+      }
+      if (key) *reinterpret_cast<float4*>(as + 4 * lane) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    __syncwarp();  // probabilities published; every lane has read this clip's folded queries: its per-head rows are free again
+    {
+      float b0[TP_H] = {0.0f, 0.0f, 0.0f, 0.0f}, b1[TP_H] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int s = 0; s < TP_S; ++s) {
+        const float m0 = ms[s * TP_XA_STRIDE + lane], m1 = has1 ? ms[s * TP_XA_STRIDE + lane + 32] : 0.0f;
+        const float4 av = *reinterpret_cast<const float4*>(as + 4 * s);  // broadcast
+        b0[0] = fmaf(av.x, m0, b0[0]); b0[1] = fmaf(av.y, m0, b0[1]); b0[2] = fmaf(av.z, m0, b0[2]); b0[3] = fmaf(av.w, m0, b0[3]);
+        b1[0] = fmaf(av.x, m1, b1[0]); b1[1] = fmaf(av.y, m1, b1[1]); b1[2] = fmaf(av.z, m1, b1[2]); b1[3] = fmaf(av.w, m1, b1[3]);
+      }
+#pragma unroll
+      for (int h = 0; h < TP_H; ++h) {
+        hq[h * TP_XA_STRIDE + lane] = b0[h];
+        if (has1) hq[h * TP_XA_STRIDE + lane + 32] = b1[h];
+      }
+    }
+  }
+  __syncwarp();
+  // o_r[d] = b_v[d] + sum_c W_v[c][d] mbar_{r,head(d)}[c]; this lane owns d = lane and d = lane + 32
+  float o0[TP_R], o1[TP_R];
+  {
+    const float bv0 = blob[A.b_in + 2 * TP_D + lane], bv1 = has1 ? blob[A.b_in + 2 * TP_D + lane + 32] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < TP_R; ++r) { o0[r] = bv0; o1[r] = bv1; }
+    const float* mb0 = hr + (lane / TP_HD) * TP_XA_STRIDE;
+    const float* mb1 = hr + ((has1 ? lane + 32 : lane) / TP_HD) * TP_XA_STRIDE;
+    const float* wv = Win + 2 * TP_D;
+#pragma unroll 2
+    for (int c = 0; c < TP_D; c += 4) {
+      float wa[4], wb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        wa[j] = wv[(size_t)(c + j) * 3 * TP_D + lane];
+        wb[j] = has1 ? wv[(size_t)(c + j) * 3 * TP_D + lane + 32] : 0.0f;
+      }
+#pragma unroll
+      for (int r = 0; r < TP_R; ++r) {
+        const float4 ma = *reinterpret_cast<const float4*>(mb0 + r * TP_H * TP_XA_STRIDE + c);
+        o0[r] = fmaf(ma.w, wa[3], fmaf(ma.z, wa[2], fmaf(ma.y, wa[1], fmaf(ma.x, wa[0], o0[r]))));
+        if (has1) {
+          const float4 mb = *reinterpret_cast<const float4*>(mb1 + r * TP_H * TP_XA_STRIDE + c);
+          o1[r] = fmaf(mb.w, wb[3], fmaf(mb.z, wb[2], fmaf(mb.y, wb[1], fmaf(mb.x, wb[0], o1[r]))));
+        }
+      }
+    }
+  }
+  float y0[TP_R], y1[TP_R];
+  tp_stage_rows(xs, lane, o0, o1);
+  tp_warp_matvec_r<TP_D>(xs, blob + A.w_out, TP_D, 0, blob + A.b_out, TP_D, lane, y0, y1);
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    x0[r] += y0[r];
+    x1[r] += y1[r];
+    tp_ln_row_warp(x0[r], x1[r], blob + N.w, blob + N.b, lane);
+  }
+}
 // prediction head on a finished last-token row (drag_pose.py:275-289): appends the standardised prediction to the decoder inputs
 // and writes the de-standardised one into target_buf with the step-function up-sampling
 __device__ __forceinline__ void tp_out_head_row(const float* __restrict__ blob, const TpFfTail& t, int b, int T, int lane, float x0, float x1) {

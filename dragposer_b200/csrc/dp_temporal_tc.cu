@@ -62,6 +62,75 @@ tp_ff_finish_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2
   if (tail.out_head) tp_out_head_row(blob, tail, row / T, T, lane, v0, v1);
 }
 
+// The finishing kernel of a single-token decoder pass (T == 1: row == clip) with TP_R rows per warp: the partial sums and LayerNorms
+// row by row as above, then the next layer's two attention blocks (or the prediction head) with every weight loaded once per four
+// rows (tp_self_attn_rows / tp_cross_attn_rows).  Bitwise the results of tp_ff_finish_kernel (DP_DEC_ROWS=0).
+__global__ void __launch_bounds__(128)
+tp_ff_finish_rows_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2, const float* __restrict__ x_g, int n_rows,
+                         int row_stride, const float* __restrict__ part, int n_split, float* __restrict__ out_g, const __grid_constant__ TpFfTail tail) {
+  __shared__ __align__(16) float scr[4][TP_XR_SCR];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (tail.next_self_attn) tp_prefetch_attn(blob, tail.sa, tail.n1);
+  if (tail.next_cross_attn) {
+    tp_prefetch_attn(blob, tail.ca, tail.n2);
+    tp_prefetch_l1(tail.wk_t, TP_D * TP_D);
+  }
+  if (tail.out_head) tp_prefetch_l1(blob + tail.out_w, TP_D * TP_LAT);
+  const int b0 = (blockIdx.x * 4 + warp) * TP_R;
+  if (b0 >= n_rows) return;
+  const int n_here = min(TP_R, n_rows - b0);
+  const bool has1 = lane + 32 < TP_D;
+  float v0[TP_R], v1[TP_R];
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    const int row = b0 + min(r, n_here - 1);
+    const size_t g = (size_t)row * row_stride * TP_D;
+    v0[r] = blob[F.b2 + lane] + x_g[g + lane];
+    v1[r] = has1 ? blob[F.b2 + lane + 32] + x_g[g + lane + 32] : 0.0f;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int s = 0; s < n_split; ++s) {  // fixed order: the result does not depend on scheduling
+      const float* p = part + ((size_t)s * n_rows + row) * TP_D;
+      a0 += p[lane];
+      if (has1) a1 += p[lane + 32];
+    }
+    v0[r] += a0;
+    v1[r] += a1;
+    tp_ln_row_warp(v0[r], v1[r], blob + N1.w, blob + N1.b, lane);
+    if (has_n2) tp_ln_row_warp(v0[r], v1[r], blob + N2.w, blob + N2.b, lane);
+  }
+  if (tail.next_self_attn) tp_self_attn_rows(blob, tail.sa, tail.n1, scr[warp], lane, v0, v1);
+  if (tail.next_cross_attn) tp_cross_attn_rows(blob, tail.ca, tail.n2, tail.wk_t, tail.mem + (size_t)b0 * TP_S * TP_D, n_here, scr[warp], lane, v0, v1);
+#pragma unroll
+  for (int r = 0; r < TP_R; ++r) {
+    if (r < n_here) {
+      const size_t g = (size_t)(b0 + r) * row_stride * TP_D;
+      out_g[g + lane] = v0[r];
+      if (has1) out_g[g + lane + 32] = v1[r];
+    }
+  }
+  if (tail.out_head) {  // tp_out_head_row for the warp's rows
+    float a[TP_R], unused[TP_R];
+    tp_stage_rows(scr[warp], lane, v0, v1);
+    tp_warp_matvec_asc_r<TP_D>(scr[warp], blob + tail.out_w, TP_LAT, blob + tail.out_b, TP_LAT, lane, a, unused);
+    if (lane < TP_LAT) {
+#pragma unroll
+      for (int r = 0; r < TP_R; ++r) {
+        if (r >= n_here) continue;
+        const int b = b0 + r;
+        if (1 < TP_MAXT) tail.dec_lat[((size_t)b * TP_MAXT + 1) * TP_LAT + lane] = a[r];
+        const float val = a[r] * tail.sigma[lane] + tail.mu[lane];
+        float* tb = tail.target_buf + (size_t)b * (tail.window + 1) * TP_LAT;
+        if (tail.window == 0) {
+          tb[lane] = val;
+        } else if (tail.step_i >= 4) {
+          for (int q = tail.step_i - 4; q < tail.step_i; ++q) tb[q * TP_LAT + lane] = val;
+          if (tail.step_i == tail.window) tb[tail.window * TP_LAT + lane] = val;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // Host: build the pre-split, pre-tiled weight image of one FF block (FFT_LAYER_BYTES).
@@ -138,7 +207,10 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
     TpFfTail t;
     memset(&t, 0, sizeof(t));
     if (tail) t = *tail;
-    tp_ff_finish_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, part, n_split, out, t);
+    if (tail && T == 1 && dp_dec_rows())
+      tp_ff_finish_rows_kernel<<<(n_rows + 4 * TP_R - 1) / (4 * TP_R), 128, 0, st>>>(blob, F, N1, N2, has_n2, x, n_rows, row_stride, part, n_split, out, t);
+    else
+      tp_ff_finish_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(blob, F, N1, N2, has_n2, x, n_rows, T, row_stride, part, n_split, out, t);
     ++*launches;
   }
   return cudaGetLastError();

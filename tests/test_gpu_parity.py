@@ -363,6 +363,29 @@ def test_temporal_predictor_tensor_core_vs_cuda_core(golden_dir, engine_factory,
         assert np.isfinite(tc[:, rows]).all() and err <= 2e-5
 
 
+@pytest.mark.parametrize("n_clips", [1, 2, 37, 2101])
+def test_single_token_decoder_pass_four_clips_per_warp_is_bitwise_the_one_clip_kernels(golden_dir, engine_factory, n_clips, monkeypatch):
+    """The single-token decoder pass runs four clips per warp (every weight of its matrix-vector chains loaded once per four clips,
+    dp_temporal.cuh: tp_self_attn_rows / tp_cross_attn_rows); each clip's arithmetic keeps the order of the one-clip kernels, which
+    stay as the cross-check (DP_DEC_ROWS=0, read on every call): bitwise equal targets, ragged last warps (n % 4 = 1, 2) and the
+    two-part split included, at window 0 (the pass is the whole decoder) and window 16 (it is the first of five passes)."""
+    g = np.load(os.path.join(golden_dir, "ref_temporal.npz"))
+    rng = np.random.default_rng(17)
+    reps = -(-n_clips // g["latent_buf"].shape[0])
+    tile = lambda a: np.tile(a, (reps, 1, 1))[:n_clips]
+    eng = engine_factory(max(512, n_clips))
+    eng.set_initial_state(np.zeros((n_clips, 24)), np.zeros((n_clips, 3)), np.tile([[1.0, 0, 0, 0]], (n_clips, 1)), np.zeros((n_clips, 6)))
+    eng.set_ring_buffers(tile(g["latent_buf"]) + rng.normal(0, 0.05, (n_clips, 60, 24)).astype(np.float32), tile(g["disp_buf"]), tile(g["height_buf"]))
+    for W in (0, 16):
+        rows = slice(0, max(W, 1))
+        monkeypatch.setenv("DP_DEC_ROWS", "1")
+        a = eng.predict_targets(W)[:, rows].copy()
+        monkeypatch.setenv("DP_DEC_ROWS", "0")
+        b = eng.predict_targets(W)[:, rows].copy()
+        monkeypatch.delenv("DP_DEC_ROWS")
+        assert np.isfinite(a).all() and np.abs(a).max() > 1e-3 and np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("n_clips", [1, 37])
 def test_predictor_graph_replay_is_bitwise_the_kernel_by_kernel_chain(golden_dir, engine_factory, n_clips):
     """A small predictor call is captured into a CUDA graph on its second use and replayed afterwards (dp_temporal.cu): the first
