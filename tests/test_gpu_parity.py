@@ -216,6 +216,31 @@ def test_run_frames_pipelined_equals_frame_by_frame(engine_factory, pose_model, 
     assert np.isfinite(outs[0][0]).all()
 
 
+def test_early_predictor_call_survives_window_changes_and_teardown(engine_factory, pose_model, model_npz, monkeypatch):
+    """The early predictor call is tied to the window it was issued for: a caller that changes temporal_future_window between the
+    early call and its use (16 -> 8 -> 4 -> 16, the reference's fresh-zero-buffer rule, drag_pose.py:237-244) gets bitwise the frames
+    of the engine without early calls, and an engine can be closed while such a call is still in flight."""
+    offsets = model_npz["offsets"]
+    cfg = synthetic.config_6_trackers()
+    B, T = 2, 65
+    wl = synthetic.make_workload(pose_model, offsets, cfg, B, T)
+    windows = [16] * 14 + [8] * 13 + [4] * 9 + [16] * 29  # changes right after an early call was issued (index W - 3) and mid-window
+    kw = dict(lambda_rot=1, lambda_temporal=0.02, max_iter=6, joint_adjustment_indices=cfg.joint_adjustment,
+              joint_adjustment_weight=cfg.joint_adjustment_weight)
+    outs = []
+    for prefetch in ("1", "0"):
+        monkeypatch.setenv("DP_PRED_PREFETCH", prefetch)
+        eng = engine_factory(4)
+        eng.set_initial_state(wl["latent0"], np.zeros((B, 3)), np.tile([[1.0, 0, 0, 0]], (B, 1)), np.zeros((B, 6)))
+        ps = []
+        for t in range(T):
+            p_, g_ = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], temporal_future_window=windows[t], **kw)
+            ps.append(np.concatenate([p_.ravel(), g_.ravel()]))
+        outs.append(np.stack(ps))
+        eng.close()  # frame 64 has index 13 of a 16-frame window: an early call was issued on it
+    assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("mode", ["frames", "single"])
 def test_predictor_issued_three_frames_early_gives_bitwise_the_same_frames(engine_factory, pose_model, model_npz, monkeypatch, mode):
     """Small-batch streaming mode (window 16): the predictor call of a window's first frame is issued three frames early on its own
