@@ -124,10 +124,6 @@ __global__ void __launch_bounds__(128) tp_dec_start_rows_kernel(const float* __r
                                                                 float* __restrict__ dec) {
   __shared__ __align__(16) float scr[4][TP_XR_SCR];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  tp_prefetch_l1(blob + L.dec_in_w, TP_LAT * TP_D);
-  tp_prefetch_attn(blob, L.dec[0].sa, L.dec[0].n1);
-  tp_prefetch_attn(blob, L.dec[0].ca, L.dec[0].n2);
-  tp_prefetch_l1(wk_t, TP_D * TP_D);
   const int b0 = (blockIdx.x * 4 + warp) * TP_R;
   if (b0 >= n_clips) return;
   const int n_here = min(TP_R, n_clips - b0);

@@ -282,20 +282,6 @@ __device__ __forceinline__ void tp_cross_attn_single(const float* __restrict__ b
 // instructions per 32 multiply-adds instead of 9 per 8.  Every row's arithmetic -- the order of every fused multiply-add, the softmax,
 // the LayerNorm reductions -- is exactly that of the one-row functions, so the results are bitwise the same.
 #define TP_R 4
-// Every launch starts with a cold L1, and a warp walks the ~80 KB of weights of its blocks exactly once with eight loads in flight:
-// without help the whole kernel is one L2-latency-bound pass (measured: 47 us for 8 192 rows against ~10 us of issue time).  Each CTA
-// therefore asks for all the lines it is going to read up front, in parallel.
-__device__ __forceinline__ void tp_prefetch_l1(const float* __restrict__ p, int n_floats) {
-  for (int i = threadIdx.x * 32; i < n_floats; i += blockDim.x * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
-}
-__device__ __forceinline__ void tp_prefetch_attn(const float* __restrict__ blob, const TpAttn& A, const TpNorm& N) {
-  tp_prefetch_l1(blob + A.w_in, 3 * TP_D * TP_D);
-  tp_prefetch_l1(blob + A.w_out, TP_D * TP_D);
-  tp_prefetch_l1(blob + A.b_in, 3 * TP_D);
-  tp_prefetch_l1(blob + A.b_out, TP_D);
-  tp_prefetch_l1(blob + N.w, TP_D);
-  tp_prefetch_l1(blob + N.b, TP_D);
-}
 // per-warp scratch (floats): staging [48][TP_R] | per-row per-head rows [TP_R][4][52] (folded queries, then weighted memory sums) |
 // ONE clip's 14 memory rows [14][52] | its probabilities [14][4]
 #define TP_XR_SCR (TP_D * TP_R + TP_R * TP_H * TP_XA_STRIDE + TP_S * TP_XA_STRIDE + TP_S * TP_H)
@@ -426,7 +412,7 @@ __device__ __forceinline__ void tp_cross_attn_rows(const float* __restrict__ blo
 #pragma unroll
     for (int j = 0; j < kMemPer; ++j) {
       const int i = lane + 32 * j;
-      pre[j] = i < kMemV ? mr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      pre[j] = i < kMemV ? __ldcs(mr + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // streamed once: keep the weights in L1
     }
   };
   fetch(0);

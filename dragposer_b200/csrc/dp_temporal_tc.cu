@@ -70,12 +70,6 @@ tp_ff_finish_rows_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNo
                          int row_stride, const float* __restrict__ part, int n_split, float* __restrict__ out_g, const __grid_constant__ TpFfTail tail) {
   __shared__ __align__(16) float scr[4][TP_XR_SCR];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (tail.next_self_attn) tp_prefetch_attn(blob, tail.sa, tail.n1);
-  if (tail.next_cross_attn) {
-    tp_prefetch_attn(blob, tail.ca, tail.n2);
-    tp_prefetch_l1(tail.wk_t, TP_D * TP_D);
-  }
-  if (tail.out_head) tp_prefetch_l1(blob + tail.out_w, TP_D * TP_LAT);
   const int b0 = (blockIdx.x * 4 + warp) * TP_R;
   if (b0 >= n_rows) return;
   const int n_here = min(TP_R, n_rows - b0);
@@ -85,13 +79,13 @@ tp_ff_finish_rows_kernel(const float* __restrict__ blob, TpFF F, TpNorm N1, TpNo
   for (int r = 0; r < TP_R; ++r) {
     const int row = b0 + min(r, n_here - 1);
     const size_t g = (size_t)row * row_stride * TP_D;
-    v0[r] = blob[F.b2 + lane] + x_g[g + lane];
-    v1[r] = has1 ? blob[F.b2 + lane + 32] + x_g[g + lane + 32] : 0.0f;
+    v0[r] = blob[F.b2 + lane] + __ldcs(x_g + g + lane);  // rows and partial sums are streamed once: keep the weights in L1
+    v1[r] = has1 ? blob[F.b2 + lane + 32] + __ldcs(x_g + g + lane + 32) : 0.0f;
     float a0 = 0.0f, a1 = 0.0f;
     for (int s = 0; s < n_split; ++s) {  // fixed order: the result does not depend on scheduling
       const float* p = part + ((size_t)s * n_rows + row) * TP_D;
-      a0 += p[lane];
-      if (has1) a1 += p[lane + 32];
+      a0 += __ldcs(p + lane);
+      if (has1) a1 += __ldcs(p + lane + 32);
     }
     v0[r] += a0;
     v1[r] += a1;
