@@ -190,7 +190,8 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
   if (trace) {
     cudaStreamSynchronize(st);
     const long long t0 = trace[4];
-    printf("FF trace: kernel start %lld, end %lld (cycles relative to the first H accumulator)\n", trace[7] - t0, trace[15] - t0);
+    printf("FF trace: kernel start %lld, end %lld, chunk 0 pieces computed %lld (cycles relative to the first H accumulator)\n", trace[7] - t0, trace[15] - t0,
+           trace[11] - t0);
     printf("FF trace (%d rows, split %d): chunk | issuer: weights ready, pieces ready, issued | epilogue: H ready, loaded, stored\n", n_rows, n_split);
     for (int c = 0; c < kChunks / n_split; ++c)
       printf("  %2d | %7lld %7lld %7lld | %7lld %7lld %7lld\n", c, trace[c * 8] - t0, trace[c * 8 + 1] - t0, trace[c * 8 + 2] - t0, trace[c * 8 + 4] - t0,

@@ -226,6 +226,7 @@ __device__ __forceinline__ void ff_tile(Smem& S, const uint32_t tmem, const unsi
         p1[j / 2] = __uint_as_float(w);
         p2[j / 2] = __uint_as_float(w2);
       }
+      if (traced && i == 0) trace[11] = clock64();  // chunk 0: pieces computed, before the tensor-memory stores
       tmem_st16(tmem + lane_base + hcol + (uint32_t)(chalf * 32), p1);
       tmem_st16(tmem + lane_base + hcol + (uint32_t)(chalf * 32) + 16u, p2);
       tmem_st_wait();
