@@ -99,6 +99,17 @@ constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 64;  // 8 epilogue war
 // and the LayerNorms (few-row launches: a 4096-row decoder step would otherwise occupy 32 SMs for 32 serial chunks).
 // Called by all kThreads threads with kT_COLS columns of tensor memory at `tmem` and the mbarriers of S freshly initialised and
 // published by a block barrier; returns after a block barrier.  x_g is read with ld.global.cg (see dp_temporal_attn_tc.cuh).
+// bulk copy of local step j of a CTA's chunk range into ring stage st.  The first two steps are only read for their W1 half (MMA1 of
+// chunks 0 and 1) and the last two only for their W2 half: the unused halves stay in L2 -- 24 KB less in the fill burst with which every
+// CTA of a wave starts at the same moment (profiles/r2_ff_pipeline_clock.md), 48 KB of 816 KB less per tile.
+__device__ __forceinline__ void load_step(Smem& S, const unsigned char* steps, int c0, int j, int n_loc, int st) {
+  const unsigned char* src = steps + (size_t)(c0 + j) * kStepBytes;
+  uint32_t off = 0, bytes = kStepBytes;
+  if (j < 2) { off = 2 * kW2Bytes; bytes = 2 * kW1Bytes; }
+  else if (j >= n_loc) bytes = 2 * kW2Bytes;
+  mbar_expect_tx(&S.wfull[st], bytes);
+  tma_bulk_g2s(S.w[st] + off, src + off, bytes, &S.wfull[st]);
+}
 __device__ __forceinline__ void ff_init_barriers(Smem& S) {
   for (int i = 0; i < kStages; ++i) { mbar_init(&S.wfull[i], 1); mbar_init(&S.wfree[i], 1); }
   mbar_init(&S.hfull[0], 1); mbar_init(&S.hfull[1], 1);
@@ -122,8 +133,7 @@ __device__ __forceinline__ void ff_tile(Smem& S, const uint32_t tmem, const unsi
     mbar_expect_tx(&S.b1full, (uint32_t)(n_loc * kHC * 4));
     tma_bulk_g2s(S.b1 + c0 * kHC, wimg + (size_t)c0 * kHC * 4, (uint32_t)(n_loc * kHC * 4), &S.b1full);
     for (int j = 0; j < kStages && j < n_loc + 2; ++j) {  // local step j == image step c0 + j
-      mbar_expect_tx(&S.wfull[j], kStepBytes);
-      tma_bulk_g2s(S.w[j], steps + (size_t)(c0 + j) * kStepBytes, kStepBytes, &S.wfull[j]);
+      load_step(S, steps, c0, j, n_loc, j);
     }
   }
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -190,8 +200,7 @@ __device__ __forceinline__ void ff_tile(Smem& S, const uint32_t tmem, const unsi
       for (int j = kStages; j < n_loc + 2; ++j) {
         const int st = j % kStages;
         mbar_wait(&S.wfree[st], ((j / kStages) - 1) & 1);
-        mbar_expect_tx(&S.wfull[st], kStepBytes);
-        tma_bulk_g2s(S.w[st], steps + (size_t)(c0 + j) * kStepBytes, kStepBytes, &S.wfull[st]);
+        load_step(S, steps, c0, j, n_loc, st);
       }
     }
     __syncwarp();
