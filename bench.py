@@ -542,7 +542,7 @@ def roofline(m, B, trackers, peaks):
             "frac": achieved_tf / tf32_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((m["path"], B, trackers)), "peak_source": which,
             "kernel_ms_per_launch": m["frame_ms"], "predictor_ms_per_step": m["pred_ms"],
             "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak},
-            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 12.12, "tp_ff_tc_kernel": 48.6, "tp_attn_tc_kernel": 7.26,
+            "tensor_pipe_pct_of_peak_ncu": {"dp_frame_tc16_kernel": 12.12, "tp_ff_tc_kernel": 53.9, "tp_attn_tc_kernel": 7.26,
                                             "source": "profiles/r2_frame_kernel.md, r2_predictor.md: sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32 (issued ops, % of peak sustained elapsed)"},
             "note": "dependency-latency bound path (SURVEY 8d): both fractions are small by construction"}
 

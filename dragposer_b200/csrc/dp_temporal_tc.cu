@@ -6,14 +6,19 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "dp_temporal.cuh"
+#if DP_FF_QUAD
+#include "dp_temporal_tc4.cuh"
+#else
 #include "dp_temporal_tc.cuh"
+#endif
 
 using namespace tpf;
 
 namespace {
 
 // Grid: (row tiles, n_split).
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict__ blob, TpFF F, TpNorm N1, TpNorm N2, int has_n2,
                 const float* x_g, int n_rows, int T, int row_stride, float* out_g, float* __restrict__ part, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) unsigned char raw[];
@@ -24,13 +29,13 @@ tp_ff_tc_kernel(const unsigned char* __restrict__ wimg, const float* __restrict_
     ff_init_barriers(S);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&S.tmem_base, kT_COLS);
+  if (warp == kEpiThreads / 32) tmem_alloc(&S.tmem_base, kT_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
   ff_tile(S, tmem, wimg, blob, F, N1, N2, has_n2, x_g, n_rows, T, row_stride, blockIdx.x * kTM, kTM, blockIdx.y, gridDim.y, out_g, part, trace);
-  if (warp == 8) tmem_dealloc(tmem, kT_COLS);
+  if (warp == kEpiThreads / 32) tmem_dealloc(tmem, kT_COLS);
 }
 
 // second half of the hidden-split mode: out = LN(x + sum of partials + b2) [+ second LayerNorm] [+ the TpFfTail work of a
@@ -147,8 +152,8 @@ void dp_ff_tc_pack(const float* w1t, const float* b1, const float* w2t, unsigned
         }
       }
     // W2c as B operand [N = out 48][K = hidden chunk] -> first half of step c + 2
-    __half* w2p[2] = {reinterpret_cast<__half*>(steps + (size_t)(c + 2) * kStepBytes),
-                      reinterpret_cast<__half*>(steps + (size_t)(c + 2) * kStepBytes + kW2Bytes)};
+    __half* w2p[2] = {reinterpret_cast<__half*>(steps + (size_t)(c + kLag) * kStepBytes),
+                      reinterpret_cast<__half*>(steps + (size_t)(c + kLag) * kStepBytes + kW2Bytes)};
     for (int n = 0; n < TP_D; ++n)
       for (int k = 0; k < kHC; ++k) {
         float r = kFfWScale * w2t[(size_t)(c * kHC + k) * TP_D + n];
@@ -170,7 +175,8 @@ cudaError_t dp_ff_tc_launch(const unsigned char* wimg, const float* blob, const 
   const int tiles = (n_rows + kTM - 1) / kTM;
   // hidden split: largest power of two that still leaves every CTA resident at once (two CTAs per SM) and >= 4 chunks each
   int n_split = 1;
-  while (n_split < 8 && tiles * n_split * 2 <= 2 * num_sms && (size_t)(n_split * 2) * n_rows * TP_D <= part_floats) n_split *= 2;
+  constexpr int kMaxSplit = kChunks / 4;  // at least four chunks per CTA: 8 with 64-unit chunks, 16 with 32-unit chunks
+  while (n_split < kMaxSplit && tiles * n_split * 2 <= kCtasPerSm * num_sms && (size_t)(n_split * 2) * n_rows * TP_D <= part_floats) n_split *= 2;
   if (!part) n_split = 1;
   if (tail) {  // the tail runs in the finish kernel: keep the split path even for a batch that would fill the device unsplit
     if (!part || T != 1 || (size_t)4 * n_rows * TP_D > part_floats) return cudaErrorInvalidValue;

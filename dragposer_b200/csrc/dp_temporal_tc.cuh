@@ -30,6 +30,8 @@ namespace tpf {
 constexpr int kTM = 128;
 constexpr int kHC = FFT_HC;                    // 64 hidden units per chunk
 constexpr int kChunks = TP_FF / kHC;           // 32
+constexpr int kLag = 2;                        // step t carries W2 of chunk t - kLag
+constexpr int kCtasPerSm = 2;
 constexpr float kFfWScale = 64.0f;             // weight image holds 64 W
 constexpr uint32_t kW1Bytes = kHC * TP_D * 2;  // 6144: one fp16 image of W1c [64][48]
 constexpr uint32_t kW2Bytes = TP_D * kHC * 2;  // 6144: one fp16 image of W2c [48][64]
