@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(EMB_THREADS) tp_embed_kernel(const float* __re
   __shared__ float xs[EMB_CLIPS * TP_S * EMB_XS];
   const int tid = threadIdx.x, clip0 = blockIdx.x * EMB_CLIPS;
   const int g_here = min(EMB_CLIPS, n_clips - clip0), rows = g_here * TP_S;
+#pragma unroll 4  // the loads of four elements in flight (the gather is latency-bound: index arithmetic, then a dependent load)
   for (int idx = tid; idx < rows * TP_ENC_IN; idx += EMB_THREADS) {
     const int r = idx / TP_ENC_IN, i = idx % TP_ENC_IN, k = r % TP_S;
     const int v = v0 + clip0 + r / TP_S, ahead = v % J;
