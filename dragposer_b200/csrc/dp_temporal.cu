@@ -97,6 +97,72 @@ __global__ void tp_dec_embed_kernel(const float* __restrict__ blob, TpLayout L, 
   }
 }
 
+// ---- the same embedding for the look-ahead batching (J > 1 virtual clips per real clip): the J views of a clip, J consecutive shifts of
+// its ring buffers, touch every ring row of the clip exactly once between them (token k of shift j is row 4k + j), so instead of
+// gathering 33 inputs per token from global memory -- index arithmetic, then a dependent load, per element -- a CTA copies the WHOLE
+// ring of its (at most three) real clips into shared memory with coalesced 16-byte loads, standardising the latents on the way, and
+// every token reads its inputs from there.  Eight virtual clips (112 tokens) per CTA.  Each value is computed by the same operations
+// in the same order as in tp_embed_kernel (which stays for J = 1 and as the cross-check, DP_EMBED_RING=0): bitwise the same tokens.
+#define EMBR_CLIPS 8
+#define EMBR_REAL 3
+#define EMBR_THREADS 288
+__global__ void __launch_bounds__(EMBR_THREADS) tp_embed_ring_kernel(const float* __restrict__ blob, TpLayout L, const float* __restrict__ mu,
+                                                                     const float* __restrict__ sigma, const float* __restrict__ latent_buf,
+                                                                     const float* __restrict__ disp_buf, const float* __restrict__ height_buf, int head,
+                                                                     int n_clips, int v0, int J, float* __restrict__ enc, float* __restrict__ dec_lat) {
+  __shared__ __align__(16) float lat[EMBR_REAL][DP_PAST * DP_L];   // standardised latents, physical slot order
+  __shared__ __align__(16) float dsp[EMBR_REAL][DP_PAST * 3];
+  __shared__ __align__(16) float hgt[EMBR_REAL][DP_PAST * DP_NH];
+  const int tid = threadIdx.x, clip0 = blockIdx.x * EMBR_CLIPS;
+  const int g_here = min(EMBR_CLIPS, n_clips - clip0), rows = g_here * TP_S;
+  const int real0 = (v0 + clip0) / J, n_real = (v0 + clip0 + g_here - 1) / J - real0 + 1;  // <= EMBR_REAL for J >= 4
+  for (int idx = tid; idx < n_real * (DP_PAST * DP_L / 4); idx += EMBR_THREADS) {
+    const int c = idx / (DP_PAST * DP_L / 4), q = idx % (DP_PAST * DP_L / 4), i = (4 * q) % DP_L;  // DP_L is a multiple of 4
+    const float4 v = reinterpret_cast<const float4*>(latent_buf + (size_t)(real0 + c) * DP_PAST * DP_L)[q];
+    reinterpret_cast<float4*>(lat[c])[q] = make_float4((v.x - mu[i]) / sigma[i], (v.y - mu[i + 1]) / sigma[i + 1], (v.z - mu[i + 2]) / sigma[i + 2],
+                                                       (v.w - mu[i + 3]) / sigma[i + 3]);
+  }
+  for (int idx = tid; idx < n_real * (DP_PAST * 3 / 4); idx += EMBR_THREADS) {
+    const int c = idx / (DP_PAST * 3 / 4), q = idx % (DP_PAST * 3 / 4);
+    reinterpret_cast<float4*>(dsp[c])[q] = reinterpret_cast<const float4*>(disp_buf + (size_t)(real0 + c) * DP_PAST * 3)[q];
+  }
+  for (int idx = tid; idx < n_real * (DP_PAST * DP_NH / 4); idx += EMBR_THREADS) {
+    const int c = idx / (DP_PAST * DP_NH / 4), q = idx % (DP_PAST * DP_NH / 4);
+    reinterpret_cast<float4*>(hgt[c])[q] = reinterpret_cast<const float4*>(height_buf + (size_t)(real0 + c) * DP_PAST * DP_NH)[q];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < g_here * TP_LAT; idx += EMBR_THREADS) {
+    const int lv = clip0 + idx / TP_LAT, v = v0 + lv, i = idx % TP_LAT;
+    dec_lat[(size_t)lv * TP_MAXT * TP_LAT + i] = lat[v / J - real0][((head + 56 + v % J) % DP_PAST) * DP_L + i];
+  }
+  const int f = tid % TP_D, rg = tid / TP_D;  // 6 row groups
+  float w[TP_ENC_IN];
+#pragma unroll
+  for (int i = 0; i < TP_ENC_IN; ++i) w[i] = blob[L.enc_in_w + i * TP_D + f];
+  const float bias = blob[L.enc_in_b + f];
+  for (int r = rg; r < rows; r += EMBR_THREADS / TP_D) {
+    const int v = v0 + clip0 + r / TP_S, k = r % TP_S, ahead = v % J, c = v / J - real0;
+    const int slot = (head + 4 * k + ahead) % DP_PAST;
+    float a = bias;
+    const float4* lr = reinterpret_cast<const float4*>(lat[c] + slot * DP_L);
+#pragma unroll
+    for (int i4 = 0; i4 < DP_L / 4; ++i4) {
+      const float4 x = lr[i4];
+      a = fmaf(x.x, w[4 * i4], a); a = fmaf(x.y, w[4 * i4 + 1], a); a = fmaf(x.z, w[4 * i4 + 2], a); a = fmaf(x.w, w[4 * i4 + 3], a);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float x = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x += dsp[c][((head + 4 * k + q + ahead) % DP_PAST) * 3 + i];
+      a = fmaf(x, w[TP_LAT + i], a);
+    }
+#pragma unroll
+    for (int i = 0; i < DP_NH; ++i) a = fmaf(hgt[c][slot * DP_NH + i], w[TP_LAT + 3 + i], a);
+    enc[((size_t)clip0 * TP_S + r) * TP_D + f] = a + blob[L.pe + k * TP_D + f];
+  }
+}
+
 // ---- single-token decoder pass, first kernel: embedding of the one decoder token + the first layer's self-attention block
 // (one key: row-local, see TpFfTail) + its cross-attention block against the clip's encoder memory (tp_cross_attn_single); one warp
 // per clip.
@@ -454,7 +520,11 @@ static cudaError_t run_part(const float* blob, const TpLayout& L, const float* m
   float* e2 = w.enc2;
   const int enc_rows = B * TP_S;
   if (stage != 2) {
-    tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, v0, J, w.enc, w.dec_lat);
+    const char* ring_env = getenv("DP_EMBED_RING");  // read on every call (test switch)
+    if (J >= 4 && !(ring_env && ring_env[0] == '0'))
+      tp_embed_ring_kernel<<<(B + EMBR_CLIPS - 1) / EMBR_CLIPS, EMBR_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, v0, J, w.enc, w.dec_lat);
+    else
+      tp_embed_kernel<<<(B + EMB_CLIPS - 1) / EMB_CLIPS, EMB_THREADS, 0, st>>>(blob, L, mu, sigma, latent_buf, disp_buf, height_buf, head, B, v0, J, w.enc, w.dec_lat);
     ++*launches;
     if (stage == 1) return cudaGetLastError();
   }

@@ -411,6 +411,34 @@ def test_single_token_decoder_pass_four_clips_per_warp_is_bitwise_the_one_clip_k
         assert np.isfinite(a).all() and np.abs(a).max() > 1e-3 and np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("n_clips", [1, 2, 37, 2101])
+def test_ring_copy_embedding_is_bitwise_the_gathering_embedding(engine_factory, pose_model, model_npz, n_clips, monkeypatch):
+    """Look-ahead calls (window 0: four virtual clips per clip, one predictor call per four frames) embed their tokens from a coalesced
+    copy of each clip's whole ring (tp_embed_ring_kernel) instead of gathering 33 inputs per token (tp_embed_kernel, DP_EMBED_RING=0,
+    read on every call): same operations in the same order, so ten frames -- three look-ahead calls, the ring head moving, CTAs that
+    straddle clip and part boundaries -- come out bitwise equal."""
+    cfg = synthetic.config_6_trackers()
+    T = 10
+    wl = synthetic.make_workload(pose_model, model_npz["offsets"], cfg, n_clips, T)
+    kw = dict(lambda_rot=1, lambda_temporal=cfg.lambda_temporal, temporal_future_window=0, max_iter=4,
+              joint_adjustment_indices=cfg.joint_adjustment, joint_adjustment_weight=cfg.joint_adjustment_weight)
+    outs = []
+    for ring in ("1", "0"):
+        monkeypatch.setenv("DP_EMBED_RING", ring)
+        eng = engine_factory(max(512, n_clips))
+        eng.set_initial_state(wl["latent0"], np.zeros((n_clips, 3)), np.tile([[1.0, 0, 0, 0]], (n_clips, 1)), np.zeros((n_clips, 6)))
+        ps = []
+        for t in range(T):
+            p_, g_ = eng.run(wl["tgt_pos"][t], wl["tgt_rot"][t], wl["joints"], wl["weights"], **kw)
+            ps.append(np.concatenate([p_.ravel(), g_.ravel()]))
+        st = eng.state()
+        outs.append((np.stack(ps), st["latent_buf"].copy()))
+        eng.close()
+    monkeypatch.delenv("DP_EMBED_RING")
+    assert np.isfinite(outs[0][0]).all() and np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.abs(np.diff(outs[0][0], axis=0)).max() > 1e-4  # the frames differ from one another: the targets are in play
+
+
 @pytest.mark.parametrize("n_clips", [1, 37])
 def test_predictor_graph_replay_is_bitwise_the_kernel_by_kernel_chain(golden_dir, engine_factory, n_clips):
     """A small predictor call is captured into a CUDA graph on its second use and replayed afterwards (dp_temporal.cu): the first
